@@ -1,0 +1,107 @@
+// dfx_pack.h -- "ModelPack": the static description of ONE articulation, shared by every
+// environment of a batch (all environments of a DFlexEnv are copies of the same articulation,
+// reference envs/ant.py:97-124 with env_dist = 0), plus the per-environment scratch layout.
+//
+// The pack is built on the host (dfx_capi.cu) from the reference Model's flat tensors
+// (dflex/dflex/model.py:1646-1879 field names) and lives in device global memory; kernels read it
+// through the read-only path (it is a few KB and stays L1/L2 resident).
+#pragma once
+
+namespace dfx {
+
+enum JointType { JOINT_PRISMATIC = 0, JOINT_REVOLUTE = 1, JOINT_BALL = 2, JOINT_FIXED = 3, JOINT_FREE = 4 };
+
+struct Pack {
+    // sizes (per environment)
+    int L;       // links
+    int D;       // dofs            (joint_qd)
+    int Q;       // coordinates     (joint_q)
+    int C;       // ground-contact points
+    int M;       // muscles
+    int W;       // muscle way-points
+    int nlev;    // tree depth
+    int ground;  // model.ground && C > 0
+    float gx, gy, gz;
+
+    // ---- per link (L) ----
+    const int* type;
+    const int* parent;       // local link index, -1 for roots
+    const int* q_start;      // (L+1)
+    const int* qd_start;     // (L+1)
+    const int* level_start;  // (nlev+1) offsets into level_links
+    const int* level_links;  // (L) links ordered by depth
+    const int* child_start;  // (L+1)
+    const int* child_idx;    // children lists
+    const int* anc_start;    // (L+1) ancestor-or-self dof lists, ascending dof index
+    const int* anc_dofs;
+    const int* sub_start;    // (L+1) subtree (descendant-or-self) link lists
+    const int* sub_links;
+    const float* X_pj;       // (L,7)
+    const float* X_cm;       // (L,7)
+    const float* axis;       // (L,3)
+    const float* I_c;        // (L,9) rotational inertia about the COM, body frame (row-major)
+    const float* mass;       // (L)
+    const float* target_ke;  // (L)
+    const float* target_kd;  // (L)
+    const float* limit_ke;   // (L)
+    const float* limit_kd;   // (L)
+    // ---- per coordinate (Q) ----
+    const float* target;
+    const float* limit_lower;
+    const float* limit_upper;
+    // ---- per dof (D) ----
+    const float* armature;
+    const int* dof_link;
+    // ---- contacts, grouped by body, original order kept inside a body ----
+    const int* cbody_start;  // (L+1)
+    const int* cbody;        // (C)
+    const float* cpoint;     // (C,3)
+    const float* cdist;      // (C)
+    const float* cmat;       // (C,4)  ke, kd, kf, mu
+    // ---- muscles ----
+    const int* mstart;       // (M+1)
+    const int* mlinks;       // (W) local link index
+    const float* mpoints;    // (W,3)
+};
+
+// Offsets (in floats) of the per-environment scratch block.  Forward kernels use [0, fwd_size),
+// backward kernels additionally [fwd_size, bwd_size).
+struct Layout {
+    // primal
+    int q, qd, act, musc, tau, qdd;
+    int Xsc, Xsm, S, v, a, f, ft;
+    int cw;    // contact wrenches (C,6) forward; (C,13) adjoint staging in backward
+    int A;     // H, then H^-1 (D,D)
+    int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
+    int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
+    int fwd_size;
+    // adjoint
+    int aq, aqd, aqdd, aact, amusc;
+    int aXsc, aXsm, aS, av, aa, af, aIbar /* (L,12): dL/dR (9) + dL/du (3) */, pX;
+    int bwd_size;
+};
+
+inline int dfx_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline Layout make_layout(int L, int D, int Q, int C, int M) {
+    Layout y;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += n; return r; };
+    y.q = take(Q); y.qd = take(D); y.act = take(D); y.musc = take(M); y.tau = take(D); y.qdd = take(D);
+    y.Xsc = take(L * 7); y.Xsm = take(L * 7); y.S = take(D * 6); y.v = take(L * 6); y.a = take(L * 6);
+    y.f = take(L * 6); y.ft = take(L * 6);
+    y.A = take(D * D); y.Lm = take(D * D);
+    y.Icmp = take(L * 21 + D * 6);
+    // the contact staging buffer aliases nothing in forward; in backward it needs 13 floats/contact
+    y.cw = take(C * 6);
+    y.fwd_size = o;
+    // backward: widen the contact buffer in place (it is the last forward field)
+    o = y.cw + C * 13;
+    y.aq = take(Q); y.aqd = take(D); y.aqdd = take(D); y.aact = take(D); y.amusc = take(M);
+    y.aXsc = take(L * 7); y.aXsm = take(L * 7); y.aS = take(D * 6); y.av = take(L * 6); y.aa = take(L * 6);
+    y.af = take(L * 6); y.aIbar = take(L * 12); y.pX = take(L * 7);
+    y.bwd_size = o;
+    return y;
+}
+
+}  // namespace dfx

@@ -1,0 +1,921 @@
+// dfx_phases.h -- the phases of one semi-implicit substep of the articulated rigid-body
+// simulator and their hand-derived adjoints, written once for a cooperative "group" of G lanes
+// that owns one environment whose working set lives in a scratch block (shared memory on the GPU).
+//
+// What is computed follows the reference step (NVlabs/DiffRL dflex/dflex/sim.py:2316-2601):
+//   kin_*         eval_rigid_fk :1681 + the velocity half of eval_rigid_id :1716-1763
+//   body_force_*  the force half of eval_rigid_id :1765-1787 (+ spatial_transform_inertia :1116)
+//   contact_*     eval_rigid_contacts_art :1137
+//   muscle_*      eval_muscles :1245 / compute_muscle_force :1209
+//   tau_*         eval_rigid_tau :1896 / jcalc_tau :1421
+//   crba_*        eval_rigid_jacobian/mass + the two batched GEMMs + Cholesky :2475-2561
+//   solve_*       eval_dense_solve_batched :2047 (adjoint: matnn.h:310-336)
+//   integrate_*   eval_rigid_integrate :2052 / jcalc_integrate :1505
+// HOW it is computed is different by design: the joint-space inertia H = J^T M J is accumulated
+// with the composite-rigid-body recursion instead of two dense GEMMs, the 6x6 world inertia
+// T^T I T is never formed per substep (it is applied in factored form), q'' = H^-1 tau uses an explicitly formed
+// H^-1 (one mat-vec per substep instead of two triangular sweeps), scatter-adds are replaced by
+// deterministic gathers, and nothing but (q, qd) per substep is taped: the adjoint recomputes
+// the substep in scratch memory.
+//
+// `Grp` provides: static G, lane, sync(), atomic_add(float*, float).
+#pragma once
+
+#include "dfx_math.h"
+#include "dfx_pack.h"
+
+namespace dfx {
+
+struct GroupSerial {  // host / single-lane execution
+    static constexpr int G = 1;
+    int lane;
+    DFX_HD void sync() const {}
+    DFX_HD void atomic_add(float* p, float v) const { *p += v; }
+};
+
+#define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
+
+template <class Grp>
+DFX_HD void zero_range(float* p, int n, const Grp& g) {
+    DFX_FOR(i, n) p[i] = 0.0f;
+}
+
+// =====================================================================================
+// kinematics: transforms, motion subspace, velocity and bias acceleration, root -> leaves
+// =====================================================================================
+DFX_HD void kin_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+    const int par = P.parent[i], type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+    Xf Xp = xf_ident();
+    SV vp = sv_zero(), ap = sv_zero();
+    if (par >= 0) {
+        Xp = ld7(s + Y.Xsc + par * 7);
+        vp = ld6(s + Y.v + par * 6);
+        ap = ld6(s + Y.a + par * 6);
+    }
+    const Xf Xsj = xf_mul(Xp, ld7(P.X_pj + i * 7));
+    const V3 axis = ld3(P.axis + i * 3);
+    const float* q = s + Y.q;
+    const float* qd = s + Y.qd;
+    float* S = s + Y.S;
+    Xf Xjc = xf_ident();
+    SV vj = sv_zero();
+    if (type == JOINT_PRISMATIC) {
+        Xjc.p = axis * q[qs];
+        SV Sk = SV{v3zero(), qrot(Xsj.q, axis)};
+        st6(S + ds * 6, Sk);
+        vj = Sk * qd[ds];
+    } else if (type == JOINT_REVOLUTE) {
+        Xjc.q = q_from_axis_angle(axis, q[qs]);
+        V3 w = qrot(Xsj.q, axis);
+        SV Sk = SV{w, cross(Xsj.p, w)};
+        st6(S + ds * 6, Sk);
+        vj = Sk * qd[ds];
+    } else if (type == JOINT_BALL) {
+        Xjc.q = ld4(q + qs);
+        for (int k = 0; k < 3; ++k) {
+            V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
+            V3 w = qrot(Xsj.q, e);
+            SV Sk = SV{w, cross(Xsj.p, w)};
+            st6(S + (ds + k) * 6, Sk);
+            vj = (k == 0) ? Sk * qd[ds] : vj + Sk * qd[ds + k];
+        }
+    } else if (type == JOINT_FREE) {
+        Xjc.p = ld3(q + qs);
+        Xjc.q = ld4(q + qs + 3);
+        for (int k = 0; k < 6; ++k)
+            for (int c = 0; c < 6; ++c) S[(ds + k) * 6 + c] = (k == c) ? 1.0f : 0.0f;
+        vj = ld6(qd + ds);
+    }
+    // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
+    // derivative along |q| (q is not assumed unit) agrees
+    const Xf Xsc = xf_mul(Xp, xf_mul(ld7(P.X_pj + i * 7), Xjc));
+    const Xf Xsm = xf_mul(Xsc, ld7(P.X_cm + i * 7));
+    const SV v = vp + vj;
+    const SV a = ap + sv_cross(v, vj);
+    st7(s + Y.Xsc + i * 7, Xsc);
+    st7(s + Y.Xsm + i * 7, Xsm);
+    st6(s + Y.v + i * 6, v);
+    st6(s + Y.a + i * 6, a);
+}
+
+template <class Grp>
+DFX_HD void kin_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    for (int lev = 0; lev < P.nlev; ++lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int k = b + g.lane; k < e; k += Grp::G) kin_link_fwd(P, Y, s, P.level_links[k]);
+        g.sync();
+    }
+}
+
+// Adjoint of kin_link_fwd.  On entry aXsc[i], aXsm[i], aS[dofs of i], av[i], aa[i] hold the adjoints
+// from everything downstream EXCEPT the children's kinematics, which are gathered here from the
+// children's slots (av[c], aa[c] = totals pushed to the parent, pX[c] = adjoint of the parent
+// transform).  Leaves first.
+DFX_HD void kin_link_adj(const Pack& P, const Layout& Y, float* s, int i) {
+    const int par = P.parent[i], type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+    Xf aXsc = ld7(s + Y.aXsc + i * 7);
+    SV av = ld6(s + Y.av + i * 6);
+    SV aa = ld6(s + Y.aa + i * 6);
+    for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) {
+        const int c = P.child_idx[k];
+        aXsc += ld7(s + Y.pX + c * 7);
+        av += ld6(s + Y.av + c * 6);
+        aa += ld6(s + Y.aa + c * 6);
+    }
+    // ---- recompute the primal pieces
+    Xf Xp = xf_ident();
+    if (par >= 0) Xp = ld7(s + Y.Xsc + par * 7);
+    const Xf Xpj = ld7(P.X_pj + i * 7);
+    const Xf Xsj = xf_mul(Xp, Xpj);
+    const V3 axis = ld3(P.axis + i * 3);
+    const float* q = s + Y.q;
+    const float* qd = s + Y.qd;
+    const float* S = s + Y.S;
+    float* aq = s + Y.aq;
+    float* aqd = s + Y.aqd;
+    const float* aS = s + Y.aS;
+    Xf Xjc = xf_ident();
+    SV vj = sv_zero();
+    if (type == JOINT_PRISMATIC) {
+        Xjc.p = axis * q[qs];
+        vj = ld6(S + ds * 6) * qd[ds];
+    } else if (type == JOINT_REVOLUTE) {
+        Xjc.q = q_from_axis_angle(axis, q[qs]);
+        vj = ld6(S + ds * 6) * qd[ds];
+    } else if (type == JOINT_BALL) {
+        Xjc.q = ld4(q + qs);
+        for (int k = 0; k < 3; ++k) vj += ld6(S + (ds + k) * 6) * qd[ds + k];
+    } else if (type == JOINT_FREE) {
+        Xjc.p = ld3(q + qs);
+        Xjc.q = ld4(q + qs + 3);
+        vj = ld6(qd + ds);
+    }
+    const Xf Xsc = ld7(s + Y.Xsc + i * 7);
+    const SV v = ld6(s + Y.v + i * 6);
+    // ---- reverse
+    // a = ap + v x vj
+    SV avj = sv_zero();
+    sv_cross_adj(v, vj, aa, av, avj);
+    // v = vp + vj
+    avj += av;
+    // Xsm = Xsc * Xcm
+    xf_mul_adj_a(Xsc, ld7(P.X_cm + i * 7), ld7(s + Y.aXsm + i * 7), aXsc);
+    // Xsc = Xp * (Xpj * Xjc)
+    Xf aXsj = xf_zero(), aXjc = xf_zero(), aXp = xf_zero(), aXpjc = xf_zero();
+    xf_mul_adj(Xp, xf_mul(Xpj, Xjc), aXsc, aXp, aXpjc);
+    {
+        Xf unused = xf_zero();
+        xf_mul_adj(Xpj, Xjc, aXpjc, unused, aXjc);
+    }
+    if (type == JOINT_PRISMATIC) {
+        SV Sk = ld6(S + ds * 6);
+        SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
+        aqd[ds] += sv_dot(Sk, avj);
+        aXsj.q += qrot_adj_q(Xsj.q, axis, aSk.v);   // S.v = R axis
+        aq[qs] += dot(axis, aXjc.p);
+    } else if (type == JOINT_REVOLUTE) {
+        SV Sk = ld6(S + ds * 6);
+        SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
+        aqd[ds] += sv_dot(Sk, avj);
+        xf_twist_adj_t(Xsj, SV{axis, v3zero()}, aSk, aXsj);
+        aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
+    } else if (type == JOINT_BALL) {
+        for (int k = 0; k < 3; ++k) {
+            SV Sk = ld6(S + (ds + k) * 6);
+            SV aSk = ld6(aS + (ds + k) * 6) + avj * qd[ds + k];
+            aqd[ds + k] += sv_dot(Sk, avj);
+            V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
+            xf_twist_adj_t(Xsj, SV{e, v3zero()}, aSk, aXsj);
+        }
+        add4(aq + qs, aXjc.q);
+    } else if (type == JOINT_FREE) {
+        add6(aqd + ds, avj);
+        add3(aq + qs, aXjc.p);
+        add4(aq + qs + 3, aXjc.q);
+    }
+    // Xsj = Xp * Xpj ; push to the parent through this link's slots
+    xf_mul_adj_a(Xp, Xpj, aXsj, aXp);
+    st7(s + Y.pX + i * 7, aXp);
+    st6(s + Y.av + i * 6, av);   // == adjoint of v[parent] contributed by this subtree
+    st6(s + Y.aa + i * 6, aa);
+}
+
+template <class Grp>
+DFX_HD void kin_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    for (int lev = P.nlev - 1; lev >= 0; --lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int k = b + g.lane; k < e; k += Grp::G) kin_link_adj(P, Y, s, P.level_links[k]);
+        g.sync();
+    }
+}
+
+// =====================================================================================
+// rigid-body forces per link:  f = I a + v x* I v - f_gravity, with I in closed form
+// =====================================================================================
+// World-frame spatial inertia of a link, kept factored exactly as the reference builds it
+// (sim.py:1116-1134:  T^T I_m T  with  T = [[R^T, 0], [skew(-R^T c) R^T, R^T]]):
+//     I_s = Rb I_body Rb^T ,  Rb = blockdiag(R, R),  I_body = [[I_c + m(u.u 1 - u u^T), m[u]x], [m[u]x^T, m 1]],  u = R^T c
+// with R = R(q) the polynomial rotation of X_sm.q and c = X_sm.p.  R is NOT assumed orthogonal,
+// so the derivative along |q| matches the reference's as well.
+struct BodyInertia {
+    M3 R;     // R(X_sm.q)
+    M3 Ic;    // body-frame rotational inertia about the COM
+    V3 u;     // R^T c
+    float m;
+};
+DFX_HD BodyInertia body_inertia(const Pack& P, const float* Xsm7, int i) {
+    BodyInertia B;
+    B.R = q_to_m3(ld4(Xsm7 + 3));
+    B.Ic = ld9(P.I_c + i * 9);
+    B.u = m3_tmul(B.R, ld3(Xsm7));
+    B.m = P.mass[i];
+    return B;
+}
+// y = I_s x
+DFX_HD SV inertia_apply(const BodyInertia& B, SV x) {
+    const V3 wb = m3_tmul(B.R, x.w), vb = m3_tmul(B.R, x.v);
+    const V3 mu = (vb + cross(wb, B.u)) * B.m;
+    const V3 top = m3_mul(B.Ic, wb) + cross(B.u, mu);
+    return SV{m3_mul(B.R, top), m3_mul(B.R, mu)};
+}
+DFX_HD void outer_acc(M3& a, V3 x, V3 y) {  // a += x y^T
+    a.m[0][0] += x.x * y.x; a.m[0][1] += x.x * y.y; a.m[0][2] += x.x * y.z;
+    a.m[1][0] += x.y * y.x; a.m[1][1] += x.y * y.y; a.m[1][2] += x.y * y.z;
+    a.m[2][0] += x.z * y.x; a.m[2][1] += x.z * y.y; a.m[2][2] += x.z * y.z;
+}
+// adjoint of y = I_s x given dL/dy = r: accumulates dL/dR, dL/du, dL/dx
+DFX_HD void inertia_apply_adj(const BodyInertia& B, SV x, SV r, M3& aR, V3& au, SV& ax) {
+    const V3 wb = m3_tmul(B.R, x.w), vb = m3_tmul(B.R, x.v);
+    const V3 mu = (vb + cross(wb, B.u)) * B.m;
+    const V3 top = m3_mul(B.Ic, wb) + cross(B.u, mu);
+    // y.w = R top ; y.v = R mu
+    const V3 atop = m3_tmul(B.R, r.w);
+    V3 amu = m3_tmul(B.R, r.v);
+    outer_acc(aR, r.w, top);
+    outer_acc(aR, r.v, mu);
+    // top = Ic wb + u x mu
+    V3 awb = m3_tmul(B.Ic, atop);
+    cross_adj(B.u, mu, atop, au, amu);
+    // mu = m (vb + wb x u)
+    const V3 a2 = amu * B.m;
+    V3 avb = a2;
+    cross_adj(wb, B.u, a2, awb, au);
+    // wb = R^T x.w ; vb = R^T x.v
+    ax.w += m3_mul(B.R, awb);
+    ax.v += m3_mul(B.R, avb);
+    outer_acc(aR, x.w, awb);
+    outer_acc(aR, x.v, avb);
+}
+
+DFX_HD void body_force_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+    const BodyInertia B = body_inertia(P, s + Y.Xsm + i * 7, i);
+    const V3 c = ld3(s + Y.Xsm + i * 7);
+    const SV v = ld6(s + Y.v + i * 6), a = ld6(s + Y.a + i * 6);
+    const SV Ia = inertia_apply(B, a);
+    const SV h = inertia_apply(B, v);
+    const SV fb = Ia + sv_cross_dual(v, h);
+    const V3 mg = V3{P.gx, P.gy, P.gz} * B.m;
+    const SV fg = SV{cross(c, mg), mg};
+    st6(s + Y.f + i * 6, fb - fg);
+}
+
+template <class Grp>
+DFX_HD void body_force_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    DFX_FOR(i, P.L) body_force_link_fwd(P, Y, s, i);
+    g.sync();
+}
+
+// adjoint: af[i] (adjoint of body_f_s[i]) plus what crba_adj left in aR[i] / au[i] -> aXsm, av, aa
+DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, float* s, int i) {
+    const float* Xsm7 = s + Y.Xsm + i * 7;
+    const BodyInertia B = body_inertia(P, Xsm7, i);
+    const V3 c = ld3(Xsm7);
+    const SV v = ld6(s + Y.v + i * 6), a = ld6(s + Y.a + i * 6);
+    const SV h = inertia_apply(B, v);
+    const SV af = ld6(s + Y.af + i * 6);
+    M3 aR = ld9(s + Y.aIbar + i * 12);
+    V3 au = ld3(s + Y.aIbar + i * 12 + 9);
+    V3 ac = v3zero();
+    SV av = sv_zero(), aa = sv_zero(), ah = sv_zero();
+    // f = fb - fg ; fg = (c x mg, mg)
+    const V3 mg = V3{P.gx, P.gy, P.gz} * B.m;
+    ac += cross(mg, -af.w);
+    // fb = Ia + v x* h
+    sv_cross_dual_adj(v, h, af, av, ah);
+    inertia_apply_adj(B, v, ah, aR, au, av);
+    inertia_apply_adj(B, a, af, aR, au, aa);
+    // u = R^T c
+    ac += m3_mul(B.R, au);
+    outer_acc(aR, c, au);
+    add3(s + Y.aXsm + i * 7, ac);
+    add4(s + Y.aXsm + i * 7 + 3, q_to_m3_adj(ld4(Xsm7 + 3), aR));
+    add6(s + Y.av + i * 6, av);
+    add6(s + Y.aa + i * 6, aa);
+}
+
+template <class Grp>
+DFX_HD void body_force_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    DFX_FOR(i, P.L) body_force_link_adj(P, Y, s, i);
+    g.sync();
+}
+
+// =====================================================================================
+// penalty ground contact (y-up plane), smooth Coulomb friction
+// =====================================================================================
+DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int k) {
+    const int b = P.cbody[k];
+    const Xf X = ld7(s + Y.Xsc + b * 7);
+    const SV vs = ld6(s + Y.v + b * 6);
+    const float ke = P.cmat[k * 4 + 0], kd = P.cmat[k * 4 + 1], kf = P.cmat[k * 4 + 2], mu = P.cmat[k * 4 + 3];
+    V3 p = xf_point(X, ld3(P.cpoint + k * 3));
+    p.y -= P.cdist[k];
+    const V3 dpdt = vs.v + cross(vs.w, p);
+    const float c = p.y;
+    if (c >= 0.0f) return sv_zero();
+    const float vn = dpdt.y;
+    const V3 vt = V3{dpdt.x, 0.0f, dpdt.z};
+    const float fn = c * ke;
+    const float fd = fminf(vn, 0.0f) * kd * (0.0f - c);
+    const float len = sqrtf(dot(vt, vt));
+    const V3 nvt = len > 0.0f ? V3{vt.x / len, vt.y / len, vt.z / len} : v3zero();
+    const float cap = fminf(kf * len, 0.0f - mu * c * ke);
+    const V3 ft = nvt * cap;
+    const V3 ftot = V3{ft.x, (fn + fd) + ft.y, ft.z};
+    return SV{cross(p, ftot), ftot};
+}
+
+template <class Grp>
+DFX_HD void contact_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    if (!P.ground) return;
+    DFX_FOR(k, P.C) st6(s + Y.cw + k * 6, contact_point_fwd(P, Y, s, k));
+    g.sync();
+    DFX_FOR(it, P.L * 6) {
+        const int i = it / 6, c = it - i * 6;
+        float acc = s[Y.f + it];
+        for (int k = P.cbody_start[i]; k < P.cbody_start[i + 1]; ++k) acc += s[Y.cw + k * 6 + c];
+        s[Y.f + it] = acc;
+    }
+    g.sync();
+}
+
+// adjoint for one contact: cotangent r = af[body]; writes 13 floats (aXsc 7, av 6) to the staging row
+DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k) {
+    const int b = P.cbody[k];
+    const Xf X = ld7(s + Y.Xsc + b * 7);
+    const SV vs = ld6(s + Y.v + b * 6);
+    const float ke = P.cmat[k * 4 + 0], kd = P.cmat[k * 4 + 1], kf = P.cmat[k * 4 + 2], mu = P.cmat[k * 4 + 3];
+    const V3 pt = ld3(P.cpoint + k * 3);
+    V3 p = xf_point(X, pt);
+    p.y -= P.cdist[k];
+    const V3 dpdt = vs.v + cross(vs.w, p);
+    const float c = p.y;
+    float* out = s + Y.cw + k * 13;
+    if (c >= 0.0f) {
+        for (int j = 0; j < 13; ++j) out[j] = 0.0f;
+        return;
+    }
+    const SV r = ld6(s + Y.af + b * 6);
+    const float vn = dpdt.y;
+    const V3 vt = V3{dpdt.x, 0.0f, dpdt.z};
+    const float fn = c * ke;
+    const float mn = fminf(vn, 0.0f);
+    const float fd = mn * kd * (0.0f - c);
+    const float len = sqrtf(dot(vt, vt));
+    const V3 nvt = len > 0.0f ? V3{vt.x / len, vt.y / len, vt.z / len} : v3zero();
+    const float A = kf * len, Bc = 0.0f - mu * c * ke;
+    const float cap = fminf(A, Bc);
+    const V3 ft = nvt * cap;
+    const V3 ftot = V3{ft.x, (fn + fd) + ft.y, ft.z};
+    // t = p x ftot
+    V3 ap = v3zero(), aftot = r.v;
+    cross_adj(p, ftot, r.w, ap, aftot);
+    const float a_nf = aftot.y;  // d/d(fn+fd)
+    const V3 aft = aftot;
+    // ft = nvt * cap
+    const V3 anvt = aft * cap;
+    const float acap = dot(nvt, aft);
+    float ac = 0.0f, alen = 0.0f;
+    if (A < Bc) alen += kf * acap; else ac += -mu * ke * acap;
+    V3 avt = nvt * alen;
+    if (len > 0.0f) {
+        const float inv = 1.0f / len;
+        avt += (anvt - nvt * dot(nvt, anvt)) * inv;
+    }
+    // fd = min(vn,0) * kd * (-c)
+    float avn = 0.0f;
+    if (vn < 0.0f) avn += kd * (0.0f - c) * a_nf;
+    ac += -(mn * kd) * a_nf;
+    // fn = c ke
+    ac += ke * a_nf;
+    // vt = dpdt - n vn ; vn = dpdt.y
+    V3 adpdt = avt;
+    avn -= avt.y;
+    adpdt.y += avn;
+    ap.y += ac;
+    // dpdt = v + w x p
+    SV avs = sv_zero();
+    avs.v += adpdt;
+    cross_adj(vs.w, p, adpdt, avs.w, ap);
+    // p = X.p + R(X.q) pt - n d
+    Xf aX;
+    aX.p = ap;
+    aX.q = qrot_adj_q(X.q, pt, ap);
+    st7(out, aX);
+    st6(out + 7, avs);
+}
+
+template <class Grp>
+DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    if (!P.ground) return;
+    DFX_FOR(k, P.C) contact_point_adj(P, Y, s, k);
+    g.sync();
+    DFX_FOR(it, P.L * 13) {
+        const int i = it / 13, c = it - i * 13;
+        float acc = 0.0f;
+        for (int k = P.cbody_start[i]; k < P.cbody_start[i + 1]; ++k) acc += s[Y.cw + k * 13 + c];
+        if (c < 7) s[Y.aXsc + i * 7 + c] += acc; else s[Y.av + i * 6 + (c - 7)] += acc;
+    }
+    g.sync();
+}
+
+// =====================================================================================
+// muscles: straight-line way-point segments pulling two links together
+// =====================================================================================
+template <class Grp>
+DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    if (P.M == 0) return;
+    DFX_FOR(m, P.M) {
+        const float act = s[Y.musc + m];
+        for (int i = P.mstart[m]; i < P.mstart[m + 1] - 1; ++i) {
+            const int l0 = P.mlinks[i], l1 = P.mlinks[i + 1];
+            if (l0 == l1) continue;
+            const V3 p0 = xf_point(ld7(s + Y.Xsc + l0 * 7), ld3(P.mpoints + i * 3));
+            const V3 p1 = xf_point(ld7(s + Y.Xsc + l1 * 7), ld3(P.mpoints + (i + 1) * 3));
+            const V3 d = p1 - p0;
+            const float len = sqrtf(dot(d, d));
+            const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
+            const V3 f = n * act;
+            const V3 t0 = cross(p0, f), t1 = cross(p1, f);
+            float* f0 = s + Y.f + l0 * 6;
+            float* f1 = s + Y.f + l1 * 6;
+            g.atomic_add(f0 + 0, -t0.x); g.atomic_add(f0 + 1, -t0.y); g.atomic_add(f0 + 2, -t0.z);
+            g.atomic_add(f0 + 3, -f.x);  g.atomic_add(f0 + 4, -f.y);  g.atomic_add(f0 + 5, -f.z);
+            g.atomic_add(f1 + 0, t1.x);  g.atomic_add(f1 + 1, t1.y);  g.atomic_add(f1 + 2, t1.z);
+            g.atomic_add(f1 + 3, f.x);   g.atomic_add(f1 + 4, f.y);   g.atomic_add(f1 + 5, f.z);
+        }
+    }
+    g.sync();
+}
+
+template <class Grp>
+DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    if (P.M == 0) return;
+    DFX_FOR(m, P.M) {
+        const float act = s[Y.musc + m];
+        float aact = 0.0f;
+        for (int i = P.mstart[m]; i < P.mstart[m + 1] - 1; ++i) {
+            const int l0 = P.mlinks[i], l1 = P.mlinks[i + 1];
+            if (l0 == l1) continue;
+            const Xf X0 = ld7(s + Y.Xsc + l0 * 7), X1 = ld7(s + Y.Xsc + l1 * 7);
+            const V3 r0 = ld3(P.mpoints + i * 3), r1 = ld3(P.mpoints + (i + 1) * 3);
+            const V3 p0 = xf_point(X0, r0), p1 = xf_point(X1, r1);
+            const V3 d = p1 - p0;
+            const float len = sqrtf(dot(d, d));
+            const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
+            const V3 f = n * act;
+            const SV c0 = ld6(s + Y.af + l0 * 6), c1 = ld6(s + Y.af + l1 * 6);
+            // L = -c0.(p0 x f, f) + c1.(p1 x f, f)
+            V3 af = c1.v - c0.v + cross(c1.w, p1) - cross(c0.w, p0);
+            V3 ap0 = -cross(f, c0.w);
+            V3 ap1 = cross(f, c1.w);
+            aact += dot(n, af);
+            const V3 an = af * act;
+            if (len > 0.0f) {
+                const V3 ad = (an - n * dot(n, an)) * (1.0f / len);
+                ap1 += ad;
+                ap0 -= ad;
+            }
+            const Q4 aq0 = qrot_adj_q(X0.q, r0, ap0), aq1 = qrot_adj_q(X1.q, r1, ap1);
+            float* a0 = s + Y.aXsc + l0 * 7;
+            float* a1 = s + Y.aXsc + l1 * 7;
+            g.atomic_add(a0 + 0, ap0.x); g.atomic_add(a0 + 1, ap0.y); g.atomic_add(a0 + 2, ap0.z);
+            g.atomic_add(a0 + 3, aq0.x); g.atomic_add(a0 + 4, aq0.y); g.atomic_add(a0 + 5, aq0.z); g.atomic_add(a0 + 6, aq0.w);
+            g.atomic_add(a1 + 0, ap1.x); g.atomic_add(a1 + 1, ap1.y); g.atomic_add(a1 + 2, ap1.z);
+            g.atomic_add(a1 + 3, aq1.x); g.atomic_add(a1 + 4, aq1.y); g.atomic_add(a1 + 5, aq1.z); g.atomic_add(a1 + 6, aq1.w);
+        }
+        s[Y.amusc + m] += aact;
+    }
+    g.sync();
+}
+
+// =====================================================================================
+// joint torques: leaf -> root wrench accumulation and projection on the motion subspace
+// =====================================================================================
+DFX_HD void tau_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+    const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+    SV ft = sv_zero();
+    for (int k = P.child_start[i + 1] - 1; k >= P.child_start[i]; --k) ft += ld6(s + Y.ft + P.child_idx[k] * 6);
+    const SV f = ld6(s + Y.f + i * 6) + ft;
+    st6(s + Y.ft + i * 6, f);
+    const float* q = s + Y.q;
+    const float* qd = s + Y.qd;
+    const float* S = s + Y.S;
+    float* tau = s + Y.tau;
+    const float tke = P.target_ke[i], tkd = P.target_kd[i];
+    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+        const float qq = q[qs], qdv = qd[ds];
+        const float lower = P.limit_lower[qs], upper = P.limit_upper[qs];
+        float limit_f = 0.0f;
+        if (qq < lower) limit_f = P.limit_ke[i] * (lower - qq);
+        if (qq > upper) limit_f = P.limit_ke[i] * (upper - qq);
+        const float damping_f = (0.0f - P.limit_kd[i]) * qdv;
+        tau[ds] = 0.0f - sv_dot(ld6(S + ds * 6), f) - tke * (qq - P.target[qs]) - tkd * qdv + s[Y.act + ds] + limit_f + damping_f;
+    } else if (type == JOINT_BALL) {
+        for (int k = 0; k < 3; ++k)
+            tau[ds + k] = 0.0f - sv_dot(ld6(S + (ds + k) * 6), f) - qd[ds + k] * tkd - q[qs + k] * tke;
+    } else if (type == JOINT_FREE) {
+        tau[ds + 0] = 0.0f - f.w.x; tau[ds + 1] = 0.0f - f.w.y; tau[ds + 2] = 0.0f - f.w.z;
+        tau[ds + 3] = 0.0f - f.v.x; tau[ds + 4] = 0.0f - f.v.y; tau[ds + 5] = 0.0f - f.v.z;
+    }
+}
+
+template <class Grp>
+DFX_HD void tau_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    for (int lev = P.nlev - 1; lev >= 0; --lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int k = b + g.lane; k < e; k += Grp::G) tau_link_fwd(P, Y, s, P.level_links[k]);
+        g.sync();
+    }
+}
+
+// adjoint, root -> leaves.  `atau` (D) in, af[] becomes the adjoint of body_f_s; aS, aq, aqd, aact accumulate.
+DFX_HD void tau_link_adj(const Pack& P, const Layout& Y, float* s, const float* atau, int i) {
+    const int type = P.type[i], par = P.parent[i], qs = P.q_start[i], ds = P.qd_start[i];
+    SV af = sv_zero();
+    if (par >= 0) af = ld6(s + Y.af + par * 6);   // f_tot[parent] = f[parent] + sum f_tot[children]
+    const SV f = ld6(s + Y.ft + i * 6);
+    const float* q = s + Y.q;
+    const float* S = s + Y.S;
+    float* aS = s + Y.aS;
+    float* aq = s + Y.aq;
+    float* aqd = s + Y.aqd;
+    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+        const float at = atau[ds];
+        add6(aS + ds * 6, f * (-at));
+        af += ld6(S + ds * 6) * (-at);
+        const float qq = q[qs];
+        float dlim = 0.0f;
+        if (qq < P.limit_lower[qs]) dlim = -P.limit_ke[i];
+        if (qq > P.limit_upper[qs]) dlim = -P.limit_ke[i];
+        aq[qs] += (dlim - P.target_ke[i]) * at;
+        aqd[ds] += (0.0f - P.target_kd[i] - P.limit_kd[i]) * at;
+        s[Y.aact + ds] += at;
+    } else if (type == JOINT_BALL) {
+        for (int k = 0; k < 3; ++k) {
+            const float at = atau[ds + k];
+            add6(aS + (ds + k) * 6, f * (-at));
+            af += ld6(S + (ds + k) * 6) * (-at);
+            aqd[ds + k] += -P.target_kd[i] * at;
+            aq[qs + k] += -P.target_ke[i] * at;
+        }
+    } else if (type == JOINT_FREE) {
+        for (int k = 0; k < 6; ++k) add6(aS + (ds + k) * 6, f * (-atau[ds + k]));
+        af += SV{V3{-atau[ds], -atau[ds + 1], -atau[ds + 2]}, V3{-atau[ds + 3], -atau[ds + 4], -atau[ds + 5]}};
+    }
+    st6(s + Y.af + i * 6, af);
+}
+
+template <class Grp>
+DFX_HD void tau_adj(const Pack& P, const Layout& Y, float* s, const float* atau, const Grp& g) {
+    for (int lev = 0; lev < P.nlev; ++lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int k = b + g.lane; k < e; k += Grp::G) tau_link_adj(P, Y, s, atau, P.level_links[k]);
+        g.sync();
+    }
+}
+
+// =====================================================================================
+// joint-space inertia by composite rigid bodies, Cholesky, explicit inverse
+// =====================================================================================
+DFX_HD int sym_idx(int i, int j) {  // packed upper triangle of a symmetric 6x6, i <= j
+    return i * 6 - (i * (i - 1)) / 2 + (j - i);
+}
+// the 21 unique entries (packed upper triangle) of  I_s = Rb I_body Rb^T
+DFX_HD void inertia_sym21(const BodyInertia& B, float* o) {
+    const float uu = dot(B.u, B.u);
+    const float uv[3] = {B.u.x, B.u.y, B.u.z};
+    M3 TLb, K;  // body-frame top-left block and [u]x
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) TLb.m[i][j] = B.Ic.m[i][j] + B.m * ((i == j ? uu : 0.0f) - uv[i] * uv[j]);
+    K.m[0][0] = 0.f;    K.m[0][1] = -B.u.z; K.m[0][2] = B.u.y;
+    K.m[1][0] = B.u.z;  K.m[1][1] = 0.f;    K.m[1][2] = -B.u.x;
+    K.m[2][0] = -B.u.y; K.m[2][1] = B.u.x;  K.m[2][2] = 0.f;
+    const M3 TL = m3_mmt(m3_mm(B.R, TLb), B.R);
+    const M3 TR = m3_mmt(m3_mm(B.R, K), B.R);
+    const M3 BR = m3_mmt(B.R, B.R);
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            o[sym_idx(i, j)] = 0.5f * (TL.m[i][j] + TL.m[j][i]);
+            o[sym_idx(3 + i, 3 + j)] = B.m * 0.5f * (BR.m[i][j] + BR.m[j][i]);
+        }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o[sym_idx(i, 3 + j)] = B.m * TR.m[i][j];
+}
+DFX_HD SV sym21_apply(const float* o, SV x) {
+    const float xv[6] = {x.w.x, x.w.y, x.w.z, x.v.x, x.v.y, x.v.z};
+    float y[6];
+    for (int i = 0; i < 6; ++i) {
+        float acc = 0.0f;
+        for (int j = 0; j < 6; ++j) acc += o[i <= j ? sym_idx(i, j) : sym_idx(j, i)] * xv[j];
+        y[i] = acc;
+    }
+    return SV{V3{y[0], y[1], y[2]}, V3{y[3], y[4], y[5]}};
+}
+
+template <class Grp>
+DFX_HD void crba_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    const int D = P.D, L = P.L;
+    float* Ic = s + Y.Icmp;
+    float* F = s + Y.Icmp + L * 21;
+    float* H = s + Y.A;
+    float* Lm = s + Y.Lm;
+    DFX_FOR(i, L) inertia_sym21(body_inertia(P, s + Y.Xsm + i * 7, i), Ic + i * 21);
+    DFX_FOR(e, D * D) { H[e] = 0.0f; Lm[e] = 0.0f; }
+    g.sync();
+    // composite inertias, leaves -> root
+    for (int lev = P.nlev - 1; lev >= 0; --lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int it = g.lane; it < (e - b) * 21; it += Grp::G) {
+            const int i = P.level_links[b + it / 21], c = it % 21;
+            float acc = Ic[i * 21 + c];
+            for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) acc += Ic[P.child_idx[k] * 21 + c];
+            Ic[i * 21 + c] = acc;
+        }
+        g.sync();
+    }
+    DFX_FOR(d, D) st6(F + d * 6, sym21_apply(Ic + P.dof_link[d] * 21, ld6(s + Y.S + d * 6)));
+    g.sync();
+    DFX_FOR(d, D) {
+        const int l = P.dof_link[d];
+        const SV Fd = ld6(F + d * 6);
+        for (int k = P.anc_start[l]; k < P.anc_start[l + 1]; ++k) {
+            const int j = P.anc_dofs[k];
+            if (j > d) break;
+            const float h = sv_dot(Fd, ld6(s + Y.S + j * 6));
+            H[d * D + j] = h;
+            H[j * D + d] = h;
+        }
+    }
+    g.sync();
+}
+
+// Cholesky  L L^T = H + diag(armature)  (column by column), then A <- (L L^T)^-1 column-wise.
+template <class Grp>
+DFX_HD void chol_inverse(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    const int D = P.D;
+    float* A = s + Y.A;
+    float* Lm = s + Y.Lm;
+    for (int j = 0; j < D; ++j) {
+        float sj = A[j * D + j] + P.armature[j];
+        for (int k = 0; k < j; ++k) { const float r = Lm[j * D + k]; sj -= r * r; }
+        const float ljj = sqrtf(sj);
+        const float inv = 1.0f / ljj;
+        for (int i = j + 1 + g.lane; i < D; i += Grp::G) {
+            float si = A[i * D + j];
+            for (int k = 0; k < j; ++k) si -= Lm[i * D + k] * Lm[j * D + k];
+            Lm[i * D + j] = si * inv;
+        }
+        if (g.lane == j % Grp::G) Lm[j * D + j] = ljj;
+        g.sync();
+    }
+    DFX_FOR(c, D) {
+        // L y = e_c  (y_i = 0 for i < c)
+        for (int i = 0; i < D; ++i) {
+            float acc = (i == c) ? 1.0f : 0.0f;
+            for (int k = c; k < i; ++k) acc -= Lm[i * D + k] * A[k * D + c];
+            A[i * D + c] = (i < c) ? 0.0f : acc / Lm[i * D + i];
+        }
+        // L^T x = y
+        for (int i = D - 1; i >= 0; --i) {
+            float acc = A[i * D + c];
+            for (int k = i + 1; k < D; ++k) acc -= Lm[k * D + i] * A[k * D + c];
+            A[i * D + c] = acc / Lm[i * D + i];
+        }
+    }
+    g.sync();
+}
+
+// q'' = H^-1 tau
+template <class Grp>
+DFX_HD void solve_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    const int D = P.D;
+    DFX_FOR(i, D) {
+        float acc = 0.0f;
+        for (int j = 0; j < D; ++j) acc += s[Y.A + i * D + j] * s[Y.tau + j];
+        s[Y.qdd + i] = acc;
+    }
+    g.sync();
+}
+// atau = H^-1 aqdd (written over tau);  aH -= atau (x) qdd   (aH lives in the Lm slot during backward)
+template <class Grp>
+DFX_HD void solve_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    const int D = P.D;
+    DFX_FOR(i, D) {
+        float acc = 0.0f;
+        for (int j = 0; j < D; ++j) acc += s[Y.A + i * D + j] * s[Y.aqdd + j];
+        s[Y.tau + i] = acc;
+    }
+    g.sync();
+    DFX_FOR(e, D * D) {
+        const int i = e / D, j = e - i * D;
+        s[Y.Lm + e] -= s[Y.tau + i] * s[Y.qdd + j];
+    }
+    g.sync();
+}
+
+// adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), aH in the Lm slot
+template <class Grp>
+DFX_HD void crba_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    const int D = P.D, L = P.L;
+    const float* aH = s + Y.Lm;
+    // body inertia parameters: for each link l and each ancestor dof a:  z = sum_b aH[a][b] S_b ;
+    // cotangent S_a on  I_l z
+    DFX_FOR(l, L) {
+        const BodyInertia B = body_inertia(P, s + Y.Xsm + l * 7, l);
+        M3 aR = m3_zero();
+        V3 au = v3zero();
+        SV dummy = sv_zero();
+        for (int ka = P.anc_start[l]; ka < P.anc_start[l + 1]; ++ka) {
+            const int a = P.anc_dofs[ka];
+            SV z = sv_zero();
+            for (int kb = P.anc_start[l]; kb < P.anc_start[l + 1]; ++kb) {
+                const int b = P.anc_dofs[kb];
+                z += ld6(s + Y.S + b * 6) * aH[a * D + b];
+            }
+            inertia_apply_adj(B, z, ld6(s + Y.S + a * 6), aR, au, dummy);
+        }
+        float* o = s + Y.aIbar + l * 12;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) o[r * 3 + c] += aR.m[r][c];
+        add3(o + 9, au);
+    }
+    // motion subspace: aS_a += sum_{l in subtree(link(a))} I_l sum_{b in anc(l)} (aH[a][b] + aH[b][a]) S_b
+    DFX_FOR(a, D) {
+        const int la = P.dof_link[a];
+        SV acc = sv_zero();
+        for (int kl = P.sub_start[la]; kl < P.sub_start[la + 1]; ++kl) {
+            const int l = P.sub_links[kl];
+            const BodyInertia B = body_inertia(P, s + Y.Xsm + l * 7, l);
+            SV y = sv_zero();
+            for (int kb = P.anc_start[l]; kb < P.anc_start[l + 1]; ++kb) {
+                const int b = P.anc_dofs[kb];
+                y += ld6(s + Y.S + b * 6) * (aH[a * D + b] + aH[b * D + a]);
+            }
+            acc += inertia_apply(B, y);
+        }
+        add6(s + Y.aS + a * 6, acc);
+    }
+    g.sync();
+}
+
+// =====================================================================================
+// semi-implicit Euler
+// =====================================================================================
+DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, float* s, float dt, int i) {
+    const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+    float* q = s + Y.q;
+    float* qd = s + Y.qd;
+    const float* qdd = s + Y.qdd;
+    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+        const float qd_new = qd[ds] + qdd[ds] * dt;
+        q[qs] = q[qs] + qd_new * dt;
+        qd[ds] = qd_new;
+    } else if (type == JOINT_BALL) {
+        const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
+        const Q4 r = ld4(q + qs);
+        const Q4 drdt = qmul(Q4{w.x, w.y, w.z, 0.0f}, r) * 0.5f;
+        st4(q + qs, qnormalize(r + drdt * dt));
+        st3(qd + ds, w);
+    } else if (type == JOINT_FREE) {
+        const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
+        const V3 v = ld3(qd + ds + 3) + ld3(qdd + ds + 3) * dt;
+        const V3 p = ld3(q + qs);
+        const V3 dpdt = v + cross(w, p);
+        const Q4 r = ld4(q + qs + 3);
+        const Q4 drdt = qmul(Q4{w.x, w.y, w.z, 0.0f}, r) * 0.5f;
+        st3(q + qs, p + dpdt * dt);
+        st4(q + qs + 3, qnormalize(r + drdt * dt));
+        st3(qd + ds, w);
+        st3(qd + ds + 3, v);
+    }
+}
+
+template <class Grp>
+DFX_HD void integrate_fwd(const Pack& P, const Layout& Y, float* s, float dt, const Grp& g) {
+    DFX_FOR(i, P.L) integrate_link_fwd(P, Y, s, dt, i);
+    g.sync();
+}
+
+// adjoint: aq/aqd hold d/d(q', qd') on entry and d/d(q, qd) (direct part) on exit; aqdd is written.
+// q, qd, qdd in scratch are the substep INPUT values.
+DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, float* s, float dt, int i) {
+    const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+    const float* q = s + Y.q;
+    const float* qd = s + Y.qd;
+    const float* qdd = s + Y.qdd;
+    float* aq = s + Y.aq;
+    float* aqd = s + Y.aqd;
+    float* aqdd = s + Y.aqdd;
+    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+        const float aqdn = aqd[ds] + aq[qs] * dt;
+        aqd[ds] = aqdn;
+        aqdd[ds] = aqdn * dt;
+    } else if (type == JOINT_BALL) {
+        const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
+        const Q4 r = ld4(q + qs);
+        const Q4 W = Q4{w.x, w.y, w.z, 0.0f};
+        const Q4 rr = r + qmul(W, r) * (0.5f * dt);
+        const Q4 arr = qnormalize_adj(rr, ld4(aq + qs));
+        Q4 ar = arr, aW = qzero();
+        qmul_adj(W, r, arr * (0.5f * dt), aW, ar);
+        const V3 aw = ld3(aqd + ds) + qv(aW);
+        st4(aq + qs, ar);
+        st3(aqd + ds, aw);
+        st3(aqdd + ds, aw * dt);
+    } else if (type == JOINT_FREE) {
+        const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
+        const V3 p = ld3(q + qs);
+        const Q4 r = ld4(q + qs + 3);
+        const Q4 W = Q4{w.x, w.y, w.z, 0.0f};
+        const Q4 rr = r + qmul(W, r) * (0.5f * dt);
+        const Q4 arr = qnormalize_adj(rr, ld4(aq + qs + 3));
+        Q4 ar = arr, aW = qzero();
+        qmul_adj(W, r, arr * (0.5f * dt), aW, ar);
+        V3 aw = ld3(aqd + ds) + qv(aW);
+        V3 av = ld3(aqd + ds + 3);
+        V3 ap = ld3(aq + qs);
+        const V3 adpdt = ap * dt;
+        av += adpdt;
+        cross_adj(w, p, adpdt, aw, ap);
+        st3(aq + qs, ap);
+        st4(aq + qs + 3, ar);
+        st3(aqd + ds, aw);
+        st3(aqd + ds + 3, av);
+        st3(aqdd + ds, aw * dt);
+        st3(aqdd + ds + 3, av * dt);
+    }
+}
+
+template <class Grp>
+DFX_HD void integrate_adj(const Pack& P, const Layout& Y, float* s, float dt, const Grp& g) {
+    DFX_FOR(i, P.L) integrate_link_adj(P, Y, s, dt, i);
+    g.sync();
+}
+
+// =====================================================================================
+// one substep, forward and adjoint
+// =====================================================================================
+// forward dynamics up to q'' (everything the adjoint needs to re-create); scratch q, qd, act, musc set.
+template <class Grp>
+DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_mass, const Grp& g) {
+    kin_fwd(P, Y, s, g);
+    body_force_fwd(P, Y, s, g);
+    contact_fwd(P, Y, s, g);
+    muscle_fwd(P, Y, s, g);
+    tau_fwd(P, Y, s, g);
+    if (update_mass) {
+        crba_fwd(P, Y, s, g);
+        chol_inverse(P, Y, s, g);
+    }
+    solve_fwd(P, Y, s, g);
+}
+
+// adjoint of one substep.  Pre: scratch q, qd (substep input), act, musc, A = H^-1 of the segment;
+// aq, aqd = cotangents of the substep output.  Post: aq, aqd = cotangents of the substep input;
+// aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
+template <class Grp>
+DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool apply_crba, const Grp& g) {
+    kin_fwd(P, Y, s, g);
+    body_force_fwd(P, Y, s, g);
+    contact_fwd(P, Y, s, g);
+    muscle_fwd(P, Y, s, g);
+    tau_fwd(P, Y, s, g);
+    solve_fwd(P, Y, s, g);
+    zero_range(s + Y.aXsc, P.L * 7, g);
+    zero_range(s + Y.aXsm, P.L * 7, g);
+    zero_range(s + Y.aS, P.D * 6, g);
+    zero_range(s + Y.av, P.L * 6, g);
+    zero_range(s + Y.aa, P.L * 6, g);
+    zero_range(s + Y.aIbar, P.L * 12, g);
+    g.sync();
+    integrate_adj(P, Y, s, dt, g);
+    solve_adj(P, Y, s, g);                  // tau slot <- atau
+    if (apply_crba) crba_adj(P, Y, s, g);
+    tau_adj(P, Y, s, s + Y.tau, g);
+    muscle_adj(P, Y, s, g);
+    contact_adj(P, Y, s, g);
+    body_force_adj(P, Y, s, g);
+    kin_adj(P, Y, s, g);
+}
+
+}  // namespace dfx

@@ -1,0 +1,109 @@
+// dfx_step.h -- one environment's whole env-step (all substeps) forward and backward, for a
+// cooperative group owning the environment's scratch block.  Shared verbatim by the CUDA
+// kernels (dfx_kernels.cu) and the host emulation used by CPU-side unit tests.
+//
+// Tape (written by forward when taping, read by backward), all fp32:
+//   [substep][env][Q + D]     the (q, qd) ENTERING each substep         -- tile-contiguous per substep
+//   [segment][env][D * D]     H^-1 of each mass-matrix update
+// The reference instead keeps every State tensor of every substep alive (~3.7 KB/env/substep
+// for Ant); here the adjoint recomputes the substep from (q, qd).
+#pragma once
+
+#include "../../include/dfx.h"
+#include "dfx_pack_build.h"
+#include "dfx_phases.h"
+
+namespace dfx {
+
+struct StepArgs {
+    int N, substeps, mm_freq;
+    float dt_sub;
+    const float* q; const float* qd; const float* act; const float* musc;
+    float* q_out; float* qd_out;
+    float* tape;
+    DfxDerived derived; int has_derived;
+    // backward
+    const float* tape_in;
+    const float* gq_out; const float* gqd_out;
+    float* gq; float* gqd; float* gact; float* gmusc;
+    long long hinv_base;
+};
+
+template <class Grp>
+DFX_HD void dump_derived(const Pack& P, const Layout& Y, const float* s, const DfxDerived& d, int env, const Grp& g) {
+    const int L = P.L, D = P.D;
+    if (d.body_X_sc) DFX_FOR(i, L * 7) d.body_X_sc[(long long)env * L * 7 + i] = s[Y.Xsc + i];
+    if (d.body_X_sm) DFX_FOR(i, L * 7) d.body_X_sm[(long long)env * L * 7 + i] = s[Y.Xsm + i];
+    if (d.joint_S_s) DFX_FOR(i, D * 6) d.joint_S_s[(long long)env * D * 6 + i] = s[Y.S + i];
+    if (d.body_v_s) DFX_FOR(i, L * 6) d.body_v_s[(long long)env * L * 6 + i] = s[Y.v + i];
+    if (d.body_a_s) DFX_FOR(i, L * 6) d.body_a_s[(long long)env * L * 6 + i] = s[Y.a + i];
+    if (d.body_f_s) DFX_FOR(i, L * 6) d.body_f_s[(long long)env * L * 6 + i] = s[Y.f + i];
+    if (d.body_ft_s) DFX_FOR(i, L * 6) d.body_ft_s[(long long)env * L * 6 + i] = s[Y.ft + i] - s[Y.f + i];
+    if (d.joint_tau) DFX_FOR(i, D) d.joint_tau[(long long)env * D + i] = s[Y.tau + i];
+    if (d.joint_qdd) DFX_FOR(i, D) d.joint_qdd[(long long)env * D + i] = s[Y.qdd + i];
+}
+
+template <class Grp>
+DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp& g, int env, const StepArgs& a) {
+    const int Q = P.Q, D = P.D, M = P.M, QD = Q + D, DD = D * D;
+    DFX_FOR(i, Q) s[Y.q + i] = a.q[(long long)env * Q + i];
+    DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
+    DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
+    g.sync();
+    for (int sub = 0; sub < a.substeps; ++sub) {
+        const bool upd = (sub % a.mm_freq) == 0;
+        if (a.tape) {
+            float* t = a.tape + ((long long)sub * a.N + env) * QD;
+            DFX_FOR(i, QD) t[i] = s[Y.q + i];   // q and qd are adjacent in the scratch block
+        }
+        kin_fwd(P, Y, s, g);
+        body_force_fwd(P, Y, s, g);
+        contact_fwd(P, Y, s, g);
+        muscle_fwd(P, Y, s, g);
+        tau_fwd(P, Y, s, g);
+        if (upd) {
+            crba_fwd(P, Y, s, g);
+            if (a.has_derived && a.derived.H) DFX_FOR(e, DD) a.derived.H[(long long)env * DD + e] = s[Y.A + e];
+            g.sync();
+            chol_inverse(P, Y, s, g);
+            if (a.has_derived && a.derived.L) DFX_FOR(e, DD) a.derived.L[(long long)env * DD + e] = s[Y.Lm + e];
+            if (a.tape) {
+                float* t = a.tape + a.hinv_base + ((long long)(sub / a.mm_freq) * a.N + env) * DD;
+                DFX_FOR(e, DD) t[e] = s[Y.A + e];
+            }
+        }
+        solve_fwd(P, Y, s, g);
+        if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, g);
+        integrate_fwd(P, Y, s, a.dt_sub, g);
+    }
+    DFX_FOR(i, Q) a.q_out[(long long)env * Q + i] = s[Y.q + i];
+    DFX_FOR(i, D) a.qd_out[(long long)env * D + i] = s[Y.qd + i];
+}
+
+template <class Grp>
+DFX_HD void env_step_backward(const Pack& P, const Layout& Y, float* s, const Grp& g, int env, const StepArgs& a) {
+    const int Q = P.Q, D = P.D, M = P.M, QD = Q + D, DD = D * D;
+    DFX_FOR(i, D) { s[Y.act + i] = a.act[(long long)env * D + i]; s[Y.aact + i] = 0.0f; }
+    DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
+    DFX_FOR(i, Q) s[Y.aq + i] = a.gq_out ? a.gq_out[(long long)env * Q + i] : 0.0f;
+    DFX_FOR(i, D) s[Y.aqd + i] = a.gqd_out ? a.gqd_out[(long long)env * D + i] : 0.0f;
+    const int nseg = (a.substeps + a.mm_freq - 1) / a.mm_freq;
+    for (int seg = nseg - 1; seg >= 0; --seg) {
+        const int s0 = seg * a.mm_freq;
+        const int s1 = (s0 + a.mm_freq < a.substeps) ? s0 + a.mm_freq : a.substeps;
+        const float* th = a.tape_in + a.hinv_base + ((long long)seg * a.N + env) * DD;
+        DFX_FOR(e, DD) { s[Y.A + e] = th[e]; s[Y.Lm + e] = 0.0f; }
+        for (int sub = s1 - 1; sub >= s0; --sub) {
+            const float* t = a.tape_in + ((long long)sub * a.N + env) * QD;
+            DFX_FOR(i, QD) s[Y.q + i] = t[i];
+            g.sync();
+            substep_adj(P, Y, s, a.dt_sub, sub == s0, g);
+        }
+    }
+    if (a.gq) DFX_FOR(i, Q) a.gq[(long long)env * Q + i] = s[Y.aq + i];
+    if (a.gqd) DFX_FOR(i, D) a.gqd[(long long)env * D + i] = s[Y.aqd + i];
+    if (a.gact) DFX_FOR(i, D) a.gact[(long long)env * D + i] = s[Y.aact + i];
+    if (a.gmusc) DFX_FOR(i, M) a.gmusc[(long long)env * M + i] = s[Y.amusc + i];
+}
+
+}  // namespace dfx

@@ -1,0 +1,150 @@
+/* dfx.h -- C ABI of the B200-native differentiable articulated rigid-body step.
+ *
+ * This is the drop-in boundary underneath `dflex.sim.SemiImplicitIntegrator.forward`
+ * (reference NVlabs/DiffRL dflex/dflex/sim.py:2182).  In the reference that call fans out into
+ * 10-11 generated kernels per substep, each exported from one pybind module as
+ *     <kernel>_{cpu,cuda}_forward (int dim, torch::Tensor...)
+ *     <kernel>_{cpu,cuda}_backward(int dim, inputs..., outputs..., adj_inputs..., adj_outputs...)
+ * (reference dflex/dflex/adjoint.py:1247-1291: raw data_ptr() casts, default stream, no error
+ * returns, a null/empty adjoint tensor meaning "skip").  Here the whole env-step (all substeps)
+ * is ONE forward entry point and ONE backward entry point over plain device pointers:
+ *
+ *   dfx_step_forward   replaces  SimulateFunc.forward  (sim.py:2097-2123): substeps x
+ *                      { eval_rigid_fk :1681, eval_rigid_id :1845, eval_rigid_contacts_art :1137,
+ *                        eval_muscles :1245, eval_rigid_tau :1896, [eval_rigid_jacobian :1950,
+ *                        eval_rigid_mass :1999, eval_dense_gemm_batched x2 :2023,
+ *                        eval_dense_cholesky_batched :2031], eval_dense_solve_batched :2047,
+ *                        eval_rigid_integrate :2052 }
+ *   dfx_step_backward  replaces  SimulateFunc.backward (sim.py:2127-2154) / Tape.replay
+ *                      (adjoint.py:2153-2199): the *_backward twins of the kernels above.
+ *
+ * All pointers are DEVICE pointers unless stated otherwise; all calls are stream-ordered on
+ * `stream` (a cudaStream_t passed as void*), never synchronise the host, and return a
+ * cudaError_t value as int (0 == cudaSuccess).  Thread-compatible: one stream per caller.
+ * No torch types appear in any signature.
+ */
+#ifndef DFX_H_
+#define DFX_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Static description of ONE articulation (HOST pointers; copied during dfx_pack_create).
+ * Field names and layouts are those of the reference Model (dflex/dflex/model.py:1646-1879,
+ * collide() :424-515) restricted to a single environment, with link / shape indices made
+ * local to that environment.  All environments of a batch share this description. */
+typedef struct DfxModelDesc {
+    int link_count;      /* L */
+    int dof_count;       /* D  = len(joint_qd)  per env */
+    int coord_count;     /* Q  = len(joint_q)   per env */
+    int contact_count;   /* C */
+    int muscle_count;    /* M */
+    int waypoint_count;  /* W  = len(muscle_links) per env */
+    int shape_count;     /* rows of shape_materials */
+    int ground;          /* model.ground */
+    float gravity[3];
+
+    const int* joint_type;          /* [L]   0 prismatic, 1 revolute, 2 ball, 3 fixed, 4 free (model.py:35-39) */
+    const int* joint_parent;        /* [L]   local parent link or -1 */
+    const int* joint_q_start;       /* [L+1] with closing sentinel (model.py:1757) */
+    const int* joint_qd_start;      /* [L+1] */
+    const float* joint_X_pj;        /* [L,7] p then q(xyzw) */
+    const float* joint_X_cm;        /* [L,7] */
+    const float* joint_axis;        /* [L,3] */
+    const float* body_I_m;          /* [L,6,6] blockdiag(I_c, m*1) (util.py:340-349) */
+    const float* joint_target_ke;   /* [L] */
+    const float* joint_target_kd;   /* [L] */
+    const float* joint_limit_ke;    /* [L] */
+    const float* joint_limit_kd;    /* [L] */
+    const float* joint_target;      /* [Q] */
+    const float* joint_limit_lower; /* [Q] */
+    const float* joint_limit_upper; /* [Q] */
+    const float* joint_armature;    /* [D] */
+
+    const int* contact_body0;       /* [C] local link index */
+    const float* contact_point0;    /* [C,3] */
+    const float* contact_dist;      /* [C] */
+    const int* contact_material;    /* [C] local shape index into shape_materials */
+    const float* shape_materials;   /* [shape_count,4] ke, kd, kf, mu (model.py:964) */
+
+    const int* muscle_start;        /* [M+1] */
+    const int* muscle_links;        /* [W] local link index */
+    const float* muscle_points;     /* [W,3] */
+} DfxModelDesc;
+
+typedef struct dfx_pack dfx_pack_t;
+
+/* Optional per-substep derived state of the LAST substep of a forward call, in the reference's
+ * State layouts (model.py:360-388); any pointer may be NULL.  Device pointers, env-major. */
+typedef struct DfxDerived {
+    float* body_X_sc;  /* [N*L,7] */
+    float* body_X_sm;  /* [N*L,7] */
+    float* joint_S_s;  /* [N*D,6] */
+    float* body_v_s;   /* [N*L,6] */
+    float* body_a_s;   /* [N*L,6] */
+    float* body_f_s;   /* [N*L,6] */
+    float* body_ft_s;  /* [N*L,6] */
+    float* joint_tau;  /* [N*D]   */
+    float* joint_qdd;  /* [N*D]   */
+    float* H;          /* [N,D,D] joint-space inertia of the last mass-matrix update */
+    float* L;          /* [N,D,D] its Cholesky factor */
+} DfxDerived;
+
+enum {
+    DFX_QUERY_LINKS = 0,
+    DFX_QUERY_DOFS = 1,
+    DFX_QUERY_COORDS = 2,
+    DFX_QUERY_CONTACTS = 3,
+    DFX_QUERY_MUSCLES = 4,
+    DFX_QUERY_FWD_SCRATCH_FLOATS = 5, /* shared-memory floats per environment, forward */
+    DFX_QUERY_BWD_SCRATCH_FLOATS = 6, /* shared-memory floats per environment, backward */
+    DFX_QUERY_TREE_DEPTH = 7
+};
+
+/* Build the device-resident pack for CUDA device `device` (>= 0).  Returns NULL on failure and
+ * writes a message into err (if err != NULL). */
+dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int err_len);
+void dfx_pack_destroy(dfx_pack_t* pack);
+int dfx_pack_query(const dfx_pack_t* pack, int what);
+
+/* Update the pack's gravity / ground flag (envs assign model.gravity and model.ground after
+ * finalize, reference envs/ant.py:132-133). */
+int dfx_pack_set_gravity(dfx_pack_t* pack, float gx, float gy, float gz, int ground);
+
+/* Number of floats of tape one forward call writes for `num_envs` environments:
+ *   substeps * N * (Q + D)                      the (q, qd) entering every substep
+ * + ceil(substeps / mm_freq) * N * D * D        H^-1 of every mass-matrix update           */
+long long dfx_tape_floats(const dfx_pack_t* pack, int num_envs, int substeps, int mm_freq);
+
+/* One env-step: `substeps` semi-implicit substeps of dt/substeps with the actuation held
+ * constant (sim.py:2104-2113); the joint-space inertia is refactorised when i % mm_freq == 0.
+ * dt is a double because the reference divides the Python float dt by substeps before the
+ * value is narrowed to fp32 at the kernel boundary (sim.py:2113).
+ *   q [N*Q], qd [N*D], act [N*D], musc [N*M] (NULL when M == 0)   inputs (not modified)
+ *   q_out [N*Q], qd_out [N*D]                                      outputs (may alias the inputs)
+ *   tape     NULL => no-grad mode (dflex.config.no_grad, sim.py:2201-2207)
+ *   derived  NULL or a struct of optional dumps                                              */
+int dfx_step_forward(const dfx_pack_t* pack, int num_envs, int substeps, int mm_freq, double dt,
+                     const float* q, const float* qd, const float* act, const float* musc,
+                     float* q_out, float* qd_out, float* tape, const DfxDerived* derived,
+                     void* stream);
+
+/* Adjoint of dfx_step_forward.  gq_out/gqd_out are the cotangents of (q_out, qd_out) (NULL == 0);
+ * gq, gqd, gact, gmusc receive (are overwritten with) the cotangents of the inputs; any of
+ * them may be NULL to skip the write (the reference's "empty tensor => skip", adjoint.h:336-346). */
+int dfx_step_backward(const dfx_pack_t* pack, int num_envs, int substeps, int mm_freq, double dt,
+                      const float* act, const float* musc, const float* tape,
+                      const float* gq_out, const float* gqd_out,
+                      float* gq, float* gqd, float* gact, float* gmusc, void* stream);
+
+/* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
+int dfx_set_group_size(int lanes);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+long long dfx_launch_count(void);
+const char* dfx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFX_H_ */

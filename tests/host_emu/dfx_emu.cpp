@@ -1,0 +1,90 @@
+// dfx_emu.cpp -- HOST EMULATION of the device code, for CPU-side unit tests only.
+//
+// Compiles the very same phase / step headers the CUDA kernels are built from
+// (diffrl_b200/csrc/dfx_{math,phases,step}.h) with g++, one "lane" per environment, so that the
+// arithmetic and the hand-derived adjoints can be checked against the reference's golden
+// vectors in a container that has no GPU.  It is test infrastructure: nothing in the product
+// (diffrl_b200/) loads it, and the product fails loudly when the CUDA library is missing.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../diffrl_b200/csrc/dfx_step.h"
+
+using namespace dfx;
+
+struct EmuPack {
+    PackHost host;
+    Pack pack;
+};
+
+extern "C" {
+
+EmuPack* emu_pack_create(const DfxModelDesc* desc, char* err, int err_len) {
+    EmuPack* p = new EmuPack();
+    std::string msg;
+    if (!build_pack(*desc, p->host, msg)) {
+        if (err && err_len > 0) { strncpy(err, msg.c_str(), err_len - 1); err[err_len - 1] = 0; }
+        delete p;
+        return nullptr;
+    }
+    p->pack = p->host.bind(p->host.ints.data(), p->host.floats.data());
+    return p;
+}
+void emu_pack_destroy(EmuPack* p) { delete p; }
+int emu_pack_query(const EmuPack* p, int what) {
+    switch (what) {
+        case DFX_QUERY_LINKS: return p->pack.L;
+        case DFX_QUERY_DOFS: return p->pack.D;
+        case DFX_QUERY_COORDS: return p->pack.Q;
+        case DFX_QUERY_CONTACTS: return p->pack.C;
+        case DFX_QUERY_MUSCLES: return p->pack.M;
+        case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
+        case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
+        case DFX_QUERY_TREE_DEPTH: return p->pack.nlev;
+    }
+    return -1;
+}
+int emu_pack_set_gravity(EmuPack* p, float gx, float gy, float gz, int ground) {
+    p->pack.gx = gx; p->pack.gy = gy; p->pack.gz = gz;
+    p->pack.ground = (ground && p->pack.C > 0) ? 1 : 0;
+    return 0;
+}
+long long emu_tape_floats(const EmuPack* p, int n, int substeps, int mm_freq) {
+    return tape_geom(p->pack.Q, p->pack.D, n, substeps, mm_freq).total;
+}
+
+int emu_step_forward(const EmuPack* p, int n, int substeps, int mm_freq, double dt,
+                     const float* q, const float* qd, const float* act, const float* musc,
+                     float* q_out, float* qd_out, float* tape, const DfxDerived* derived) {
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
+    if (derived) { a.derived = *derived; a.has_derived = 1; }
+    a.hinv_base = tape_geom(p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
+    std::vector<float> scratch(p->host.layout.bwd_size + 16, 0.0f);
+    GroupSerial g{0};
+    for (int env = 0; env < n; ++env) env_step_forward(p->pack, p->host.layout, scratch.data(), g, env, a);
+    return 0;
+}
+
+int emu_step_backward(const EmuPack* p, int n, int substeps, int mm_freq, double dt,
+                      const float* act, const float* musc, const float* tape,
+                      const float* gq_out, const float* gqd_out,
+                      float* gq, float* gqd, float* gact, float* gmusc) {
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
+    a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
+    a.hinv_base = tape_geom(p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
+    std::vector<float> scratch(p->host.layout.bwd_size + 16, 0.0f);
+    GroupSerial g{0};
+    for (int env = 0; env < n; ++env) env_step_backward(p->pack, p->host.layout, scratch.data(), g, env, a);
+    return 0;
+}
+
+}  // extern "C"
