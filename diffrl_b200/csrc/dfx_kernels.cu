@@ -1,0 +1,256 @@
+// dfx_kernels.cu -- sm_100a kernels and the C ABI (include/dfx.h) of the differentiable
+// articulated rigid-body step.
+//
+// Execution model: a cooperative group of G lanes (8, 16 or 32; a sub-warp tile) owns one
+// environment for the whole env-step; the environment's working set (transforms, spatial
+// vectors, H^-1, adjoint accumulators: dfx_pack.h Layout) lives in a private shared-memory block,
+// the model description is staged once per CTA into shared memory, and the only global traffic is
+//   forward : q, qd, act [, musc] in   ->  q', qd' out  (+ the (q, qd) / H^-1 tape)
+//   backward: cotangents of q', qd' + tape in  ->  cotangents of q, qd, act [, musc] out.
+// Environments are env-major contiguous in global memory (the reference's State layout), so a
+// group's loads are contiguous 60-120 B rows and a CTA's rows for one substep of the tape form
+// one contiguous tile.  There is no dense contraction on this path: no tensor cores.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <string>
+
+#include "dfx_step.h"
+
+namespace dfx {
+
+template <int G_>
+struct GroupCuda {
+    static constexpr int G = G_;
+    int lane;
+    unsigned mask;
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
+};
+
+constexpr int kThreads = 128;
+
+// Copy the pack's arrays into shared memory once per CTA and rebind the pointers.
+struct PackBlob {
+    const int* ints;
+    const float* floats;
+    int n_ints, n_floats;
+    // offsets of each pointer field (same order as PackHost::bind)
+    int int_off[17];
+    int float_off[17];
+};
+
+__device__ __forceinline__ Pack bind_pack(const Pack& header, const PackBlob& b, const int* ib, const float* fb) {
+    Pack p = header;
+    int ii = 0, fi = 0;
+    p.type = ib + b.int_off[ii++]; p.parent = ib + b.int_off[ii++]; p.q_start = ib + b.int_off[ii++];
+    p.qd_start = ib + b.int_off[ii++]; p.level_start = ib + b.int_off[ii++]; p.level_links = ib + b.int_off[ii++];
+    p.child_start = ib + b.int_off[ii++]; p.child_idx = ib + b.int_off[ii++]; p.anc_start = ib + b.int_off[ii++];
+    p.anc_dofs = ib + b.int_off[ii++]; p.sub_start = ib + b.int_off[ii++]; p.sub_links = ib + b.int_off[ii++];
+    p.dof_link = ib + b.int_off[ii++]; p.cbody_start = ib + b.int_off[ii++]; p.cbody = ib + b.int_off[ii++];
+    p.mstart = ib + b.int_off[ii++]; p.mlinks = ib + b.int_off[ii++];
+    p.X_pj = fb + b.float_off[fi++]; p.X_cm = fb + b.float_off[fi++]; p.axis = fb + b.float_off[fi++];
+    p.I_c = fb + b.float_off[fi++]; p.mass = fb + b.float_off[fi++]; p.target_ke = fb + b.float_off[fi++];
+    p.target_kd = fb + b.float_off[fi++]; p.limit_ke = fb + b.float_off[fi++]; p.limit_kd = fb + b.float_off[fi++];
+    p.target = fb + b.float_off[fi++]; p.limit_lower = fb + b.float_off[fi++]; p.limit_upper = fb + b.float_off[fi++];
+    p.armature = fb + b.float_off[fi++]; p.cpoint = fb + b.float_off[fi++]; p.cdist = fb + b.float_off[fi++];
+    p.cmat = fb + b.float_off[fi++]; p.mpoints = fb + b.float_off[fi++];
+    return p;
+}
+
+struct KernelArgs {
+    Pack header;
+    PackBlob blob;
+    Layout layout;
+    StepArgs step;
+    int scratch_stride;   // floats per environment
+    int pack_smem_floats; // floats reserved at the start of dynamic smem for the staged pack
+};
+
+template <int G, bool BACKWARD>
+__global__ void __launch_bounds__(kThreads) dfx_step_kernel(const __grid_constant__ KernelArgs ka) {
+    extern __shared__ __align__(16) float smem[];
+    // ---- stage the model description
+    float* fpack = smem;
+    int* ipack = reinterpret_cast<int*>(smem + ((ka.blob.n_floats + 3) & ~3));
+    for (int i = threadIdx.x; i < ka.blob.n_floats; i += kThreads) fpack[i] = ka.blob.floats[i];
+    for (int i = threadIdx.x; i < ka.blob.n_ints; i += kThreads) ipack[i] = ka.blob.ints[i];
+    __syncthreads();
+    const Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
+
+    constexpr int kEnvsPerCta = kThreads / G;
+    const int local = threadIdx.x / G;
+    const int env = blockIdx.x * kEnvsPerCta + local;
+    if (env >= ka.step.N) return;
+    const int lane_in_warp = threadIdx.x & 31;
+    GroupCuda<G> g;
+    g.lane = threadIdx.x % G;
+    g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_in_warp / G) * G));
+    float* s = smem + ka.pack_smem_floats + (size_t)local * ka.scratch_stride;
+    if (BACKWARD) env_step_backward(P, ka.layout, s, g, env, ka.step);
+    else env_step_forward(P, ka.layout, s, g, env, ka.step);
+}
+
+}  // namespace dfx
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+using namespace dfx;
+
+struct dfx_pack {
+    PackHost host;
+    int device;
+    int* d_ints;
+    float* d_floats;
+    Pack header;
+    PackBlob blob;
+};
+
+static std::atomic<long long> g_launches{0};
+static int g_group = 0;
+
+static void set_err(char* err, int n, const std::string& m) {
+    if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
+}
+
+extern "C" {
+
+const char* dfx_version(void) { return "diffrl_b200 dfx 0.1 (sm_100a)"; }
+long long dfx_launch_count(void) { return g_launches.load(); }
+int dfx_set_group_size(int lanes) {
+    if (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32) return 1;
+    g_group = lanes;
+    return 0;
+}
+
+dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int err_len) {
+    if (!desc) { set_err(err, err_len, "null DfxModelDesc"); return nullptr; }
+    dfx_pack* p = new dfx_pack();
+    std::string msg;
+    if (!build_pack(*desc, p->host, msg)) { set_err(err, err_len, msg); delete p; return nullptr; }
+    if (p->host.int_off.size() != 17 || p->host.float_off.size() != 17) { set_err(err, err_len, "internal: pack field count"); delete p; return nullptr; }
+    p->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_ints, p->host.ints.size() * sizeof(int) + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_floats, p->host.floats.size() * sizeof(float) + 16);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_ints, p->host.ints.data(), p->host.ints.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_floats, p->host.floats.data(), p->host.floats.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_err(err, err_len, std::string("CUDA: ") + cudaGetErrorString(e)); delete p; return nullptr; }
+    p->header = p->host.header;
+    p->blob.ints = p->d_ints; p->blob.floats = p->d_floats;
+    p->blob.n_ints = (int)p->host.ints.size(); p->blob.n_floats = (int)p->host.floats.size();
+    for (int i = 0; i < 17; ++i) { p->blob.int_off[i] = (int)p->host.int_off[i]; p->blob.float_off[i] = (int)p->host.float_off[i]; }
+    return p;
+}
+
+void dfx_pack_destroy(dfx_pack_t* p) {
+    if (!p) return;
+    cudaFree(p->d_ints);
+    cudaFree(p->d_floats);
+    delete p;
+}
+
+int dfx_pack_query(const dfx_pack_t* p, int what) {
+    switch (what) {
+        case DFX_QUERY_LINKS: return p->header.L;
+        case DFX_QUERY_DOFS: return p->header.D;
+        case DFX_QUERY_COORDS: return p->header.Q;
+        case DFX_QUERY_CONTACTS: return p->header.C;
+        case DFX_QUERY_MUSCLES: return p->header.M;
+        case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
+        case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
+        case DFX_QUERY_TREE_DEPTH: return p->header.nlev;
+    }
+    return -1;
+}
+
+int dfx_pack_set_gravity(dfx_pack_t* p, float gx, float gy, float gz, int ground) {
+    p->header.gx = gx; p->header.gy = gy; p->header.gz = gz;
+    p->header.ground = (ground && p->header.C > 0) ? 1 : 0;
+    return 0;
+}
+
+long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq) {
+    return tape_geom(p->header.Q, p->header.D, n, substeps, mm_freq).total;
+}
+
+}  // extern "C"
+
+template <int G, bool BWD>
+static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t stream) {
+    KernelArgs ka;
+    ka.header = p->header;
+    ka.blob = p->blob;
+    ka.layout = p->host.layout;
+    ka.step = step;
+    const int per_env = BWD ? p->host.layout.bwd_size : p->host.layout.fwd_size;
+    ka.scratch_stride = (per_env + 1) | 1;   // odd stride: spreads the groups of a warp over banks
+    const int pack_bytes = (((p->blob.n_floats + 3) & ~3) + ((p->blob.n_ints + 3) & ~3)) * 4;
+    ka.pack_smem_floats = pack_bytes / 4;
+    constexpr int envs_per_cta = kThreads / G;
+    const size_t smem = (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float);
+    auto kern = dfx_step_kernel<G, BWD>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int grid = (step.N + envs_per_cta - 1) / envs_per_cta;
+    kern<<<grid, kThreads, smem, stream>>>(ka);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+static int pick_group(const dfx_pack* p) {
+    if (g_group) return g_group;
+    const int widest = p->header.D > p->header.L ? p->header.D : p->header.L;
+    return widest <= 16 ? 16 : 32;
+}
+
+extern "C" {
+
+int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
+                     const float* q, const float* qd, const float* act, const float* musc,
+                     float* q_out, float* qd_out, float* tape, const DfxDerived* derived, void* stream) {
+    if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0) return (int)cudaErrorInvalidValue;
+    if (!q || !qd || !act || !q_out || !qd_out || (p->header.M > 0 && !musc)) return (int)cudaErrorInvalidValue;
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
+    if (derived) { a.derived = *derived; a.has_derived = 1; }
+    a.hinv_base = tape_geom(p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pick_group(p)) {
+        case 8: return (int)launch<8, false>(p, a, st);
+        case 16: return (int)launch<16, false>(p, a, st);
+        default: return (int)launch<32, false>(p, a, st);
+    }
+}
+
+int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
+                      const float* act, const float* musc, const float* tape,
+                      const float* gq_out, const float* gqd_out,
+                      float* gq, float* gqd, float* gact, float* gmusc, void* stream) {
+    if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0 || !tape || !act) return (int)cudaErrorInvalidValue;
+    if (p->header.M > 0 && !musc) return (int)cudaErrorInvalidValue;
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
+    a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
+    a.hinv_base = tape_geom(p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pick_group(p)) {
+        case 8: return (int)launch<8, true>(p, a, st);
+        case 16: return (int)launch<16, true>(p, a, st);
+        default: return (int)launch<32, true>(p, a, st);
+    }
+}
+
+}  // extern "C"

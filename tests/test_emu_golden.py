@@ -1,0 +1,68 @@
+"""CPU-side check of the device code's arithmetic: the host emulation (tests/host_emu, the same
+phase/step headers the CUDA kernels compile) against golden vectors produced by the unmodified
+reference (oracle/make_golden.py).  Forward tolerance is the north-star's 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import ENVS
+from emu_util import EmuSim, load_golden
+
+FWD_RTOL = 1e-5     # BASELINE.json north_star: state trajectories within 1e-5 relative
+GRAD_RTOL = 5e-5
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+@pytest.mark.parametrize("name", ENVS)
+def test_forward_and_adjoint_match_reference(name):
+    d, model = load_golden(name)
+    N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    sim = EmuSim(model, N)
+    for k in range(int(d["meta/num_cases"])):
+        p = "case%d/" % k
+        musc = d[p + "musc"] if (p + "musc") in d.files else None
+        q, qd, tape, _ = sim.forward(d[p + "q0"], d[p + "qd0"], d[p + "act"], musc, S, mm, dt)
+        assert rel(q, d[p + "traj_q"][-1]) < FWD_RTOL, (name, k)
+        assert rel(qd, d[p + "traj_qd"][-1]) < FWD_RTOL, (name, k)
+        # the tape holds the state entering every substep == the reference's per-substep trajectory
+        QD = sim.desc.Q + sim.desc.D
+        t = tape[: S * N * QD].reshape(S, N, QD)
+        # (velocities right after a start from rest are ~0, and the fp32 solve of H q'' = tau is only
+        #  good to cond(H) * eps ~ 1e-5 relative in the reference too -- hence the absolute floor)
+        for s in (1, S // 2, S - 1):
+            assert rel(t[s, :, : sim.desc.Q], d[p + "traj_q"][s - 1]) < FWD_RTOL
+            ref_qd = d[p + "traj_qd"][s - 1]
+            assert np.abs(t[s, :, sim.desc.Q:].ravel() - ref_qd).max() < FWD_RTOL * (1.0 + np.abs(ref_qd).max())
+        gq, gqd, gact, gm = sim.backward(d[p + "act"], musc, tape, d[p + "gq_out"], d[p + "gqd_out"], S, mm, dt)
+        assert rel(gq, d[p + "grad_q"]) < GRAD_RTOL, (name, k)
+        assert rel(gqd, d[p + "grad_qd"]) < GRAD_RTOL, (name, k)
+        assert rel(gact, d[p + "grad_act"]) < GRAD_RTOL, (name, k)
+        if gm is not None:
+            assert rel(gm, d[p + "grad_musc"]) < GRAD_RTOL, (name, k)
+
+
+@pytest.mark.parametrize("name", ENVS)
+def test_single_substep_derived_state(name):
+    """Every intermediate of the first substep against the reference State tensors."""
+    d, model = load_golden(name)
+    N, S, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), float(d["meta/dt"])
+    sim = EmuSim(model, N)
+    p = "case%d/" % (int(d["meta/num_cases"]) - 1)
+    musc = d[p + "musc"] if (p + "musc") in d.files else None
+    _, _, _, dv = sim.forward(d[p + "q0"], d[p + "qd0"], d[p + "act"], musc, 1, 1, dt / S, tape=False, derived=True)
+    for f in ("body_X_sc", "body_X_sm", "joint_S_s", "body_v_s", "body_a_s", "body_f_s", "body_ft_s", "joint_tau", "H", "L"):
+        assert rel(dv[f], d[p + "first/" + f]) < 2e-5, (name, f)
+    assert rel(dv["joint_qdd"], d[p + "first/joint_qdd"]) < 2e-4, name   # conditioned by H
+
+
+def test_heterogeneous_batch_is_rejected():
+    from diffrl_b200.modelpack import articulation_from_model
+    d, model = load_golden("AntEnv")
+    model = dict(model)
+    model["joint_axis"] = model["joint_axis"].copy()
+    model["joint_axis"][-1, 0] += 0.5
+    with pytest.raises(ValueError):
+        articulation_from_model(model, 2)
