@@ -29,7 +29,7 @@ struct GroupCuda {
     __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
 };
 
-constexpr int kThreads = 128;
+constexpr int kMaxThreads = 128;
 
 // Copy the pack's arrays into shared memory once per CTA and rebind the pointers.
 struct PackBlob {
@@ -69,17 +69,17 @@ struct KernelArgs {
 };
 
 template <int G, bool BACKWARD>
-__global__ void __launch_bounds__(kThreads) dfx_step_kernel(const __grid_constant__ KernelArgs ka) {
+__global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_constant__ KernelArgs ka) {
     extern __shared__ __align__(16) float smem[];
     // ---- stage the model description
     float* fpack = smem;
     int* ipack = reinterpret_cast<int*>(smem + ((ka.blob.n_floats + 3) & ~3));
-    for (int i = threadIdx.x; i < ka.blob.n_floats; i += kThreads) fpack[i] = ka.blob.floats[i];
-    for (int i = threadIdx.x; i < ka.blob.n_ints; i += kThreads) ipack[i] = ka.blob.ints[i];
+    for (int i = threadIdx.x; i < ka.blob.n_floats; i += blockDim.x) fpack[i] = ka.blob.floats[i];
+    for (int i = threadIdx.x; i < ka.blob.n_ints; i += blockDim.x) ipack[i] = ka.blob.ints[i];
     __syncthreads();
     const Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
 
-    constexpr int kEnvsPerCta = kThreads / G;
+    const int kEnvsPerCta = blockDim.x / G;
     const int local = threadIdx.x / G;
     const int env = blockIdx.x * kEnvsPerCta + local;
     if (env >= ka.step.N) return;
@@ -189,8 +189,15 @@ static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t 
     ka.scratch_stride = (per_env + 1) | 1;   // odd stride: spreads the groups of a warp over banks
     const int pack_bytes = (((p->blob.n_floats + 3) & ~3) + ((p->blob.n_ints + 3) & ~3)) * 4;
     ka.pack_smem_floats = pack_bytes / 4;
-    constexpr int envs_per_cta = kThreads / G;
+    // environments per CTA: as many as fit 128 threads and ~100 KB of shared memory (>= 2 CTAs/SM),
+    // but never less than one warp's worth of groups
+    int envs_per_cta = kMaxThreads / G;
+    const int min_envs = 32 / G > 0 ? 32 / G : 1;
+    while (envs_per_cta > min_envs &&
+           (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float) > 100 * 1024)
+        envs_per_cta /= 2;
     const size_t smem = (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = dfx_step_kernel<G, BWD>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -199,7 +206,7 @@ static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t 
         configured = smem;
     }
     const int grid = (step.N + envs_per_cta - 1) / envs_per_cta;
-    kern<<<grid, kThreads, smem, stream>>>(ka);
+    kern<<<grid, envs_per_cta * G, smem, stream>>>(ka);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -1,0 +1,89 @@
+"""Aggregate an ncu report's per-SASS-instruction counters by CUDA source line / function.
+
+usage: python tools/ncu_by_line.py <report.ncu-rep> <lib.so> <kernel-substring e.g. 'ILi16ELb0'> [top]
+Needs the .so compiled with -lineinfo.  (ncu's own CSV export of the CUDA view carries no metrics.)
+"""
+import csv, io, os, re, subprocess, sys, tempfile, collections
+
+rep, lib, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+tmp = tempfile.mkdtemp()
+subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
+cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+# ---- offset -> (file, line) for the chosen kernel
+off2line, cur, inside = {}, None, False
+for ln in dis.splitlines():
+    if ln.startswith("//---") and ".text." in ln:
+        inside = ksub in ln
+        continue
+    if not inside:
+        continue
+    m = re.match(r'\s*//## File "(.*)", line (\d+)', ln)
+    if m:
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
+    if m:
+        off2line[int(m.group(1), 16)] = cur
+# ---- ncu per-instruction rows
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+want = {"ILi8ELb0": "(int)8, (bool)0", "ILi16ELb0": "(int)16, (bool)0", "ILi32ELb0": "(int)32, (bool)0",
+        "ILi8ELb1": "(int)8, (bool)1", "ILi16ELb1": "(int)16, (bool)1", "ILi32ELb1": "(int)32, (bool)1"}[ksub]
+i = 0
+sect = None
+while i < len(rows):
+    if rows[i] and rows[i][0] == "Kernel Name" and want in rows[i][1]:
+        sect = i
+        break
+    i += 1
+assert sect is not None, "kernel not in report"
+hdr = rows[sect + 1]
+ia, ie, isamp, ith = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+stall_cols = [c for c in hdr if c.startswith("stall_") and "Not Issued" not in c]
+body = []
+for r in rows[sect + 2:]:
+    if not r or r[0] == "Kernel Name":
+        break
+    body.append(r)
+base = int(body[0][ia], 16)
+# ---- function ranges per file
+def func_table(path):
+    tbl = []
+    for n, ln in enumerate(open(path), 1):
+        m = re.match(r"^(?:template.*\n)?(?:DFX_HD|inline|static|__device__|__global__)[^;(]*?\b(\w+)\(", ln)
+        if m and not ln.startswith(" "):
+            tbl.append((n, m.group(1)))
+    return tbl
+root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffrl_b200", "csrc")
+ftab = {f: func_table(os.path.join(root, f)) for f in os.listdir(root)}
+def func_of(file, line):
+    best = "?"
+    for n, name in ftab.get(file, []):
+        if n <= line:
+            best = name
+        else:
+            break
+    return best
+by_line, by_func = collections.Counter(), collections.Counter()
+samp_line, samp_func, thr_func = collections.Counter(), collections.Counter(), collections.Counter()
+stall_func = collections.defaultdict(collections.Counter)
+tot = tots = 0
+for r in body:
+    off = int(r[ia], 16) - base
+    loc = off2line.get(off) or ("?", 0)
+    n, s, th = float(r[ie] or 0), float(r[isamp] or 0), float(r[ith] or 0)
+    fn = func_of(*loc)
+    by_line[loc] += n; by_func[fn] += n; samp_line[loc] += s; samp_func[fn] += s; thr_func[fn] += th
+    for c in stall_cols:
+        stall_func[fn][c] += float(r[hdr.index(c)] or 0)
+    tot += n; tots += s
+print("kernel %s: %.3g warp-instructions, %d samples" % (want, tot, tots))
+print("\n== by function: %inst  %samples  lanes/inst  top stalls")
+for fn, n in by_func.most_common(30):
+    st = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(1, samp_func[fn])) for k, v in stall_func[fn].most_common(4))
+    print("%6.2f%% %6.2f%%  %5.1f  %-26s %s" % (100 * n / tot, 100 * samp_func[fn] / max(1, tots), thr_func[fn] / max(1, n), fn, st))
+print("\n== by line: %inst  %samples")
+for loc, n in by_line.most_common(top):
+    print("%6.2f%% %6.2f%%  %s:%d" % (100 * n / tot, 100 * samp_line[loc] / max(1, tots), loc[0], loc[1]))
