@@ -449,7 +449,7 @@ def model_from_articulation(arrays, num_envs, device, ground=True, gravity=(0.0,
     m.contact_material = tile_i("contact_material", S)
     m.muscle_start = tile_i("muscle_start", W, sentinel=True)
     m.muscle_links = tile_i("muscle_links", L)
-    m.muscle_params = torch.zeros((M * n, 5), **f32)
+    m.muscle_params = tile_f("muscle_params") if "muscle_params" in arrays else torch.zeros((M * n, 5), **f32)
     m.muscle_activation = torch.zeros((M * n,), **f32)
     m.articulation_joint_start = torch.arange(0, (n + 1) * L, L, **i32)
     m.articulation_dof_start = torch.arange(0, n * D, D, **i32)

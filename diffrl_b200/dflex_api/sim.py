@@ -24,7 +24,16 @@ def _engine_for(model):
     from ..modelpack import ArticulationDesc, articulation_from_model  # noqa: F401
     if model._engine is None:
         n = int(model.articulation_count)
-        model._engine = ArticulationEngine.from_model(model, model.adapter, n)
+        arrays = getattr(model, "_articulation_arrays", None)
+        if arrays is not None:
+            # tiled from one articulation: the per-env description is already at hand
+            import numpy as np
+            one = {k: np.asarray(v) for k, v in arrays.items()}
+            one["ground"] = bool(model.ground)
+            desc, _ = articulation_from_model(one, 1)
+            model._engine = ArticulationEngine(desc, n, model.adapter)
+        else:
+            model._engine = ArticulationEngine.from_model(model, model.adapter, n)
         model._engine_key = None
     g = model.gravity
     key = (id(g), g._version, bool(model.ground))

@@ -1,0 +1,338 @@
+"""Concrete differentiable environments: Ant, Humanoid, SNU humanoid (muscle-actuated), CartPole
+swing-up, Hopper, HalfCheetah.
+
+Interface mirrors of the reference ``envs/{ant,humanoid,snu_humanoid,cartpole_swing_up,hopper,cheetah}.py``:
+same class names, constructor signatures, observation layouts, rewards, termination rules, reset
+distributions and constants (cited per class); obs / reward / gradient parity against the
+reference's own rollouts is tested in tests/test_gpu_envs.py.  The simulation step itself is the
+fused kernel behind ``df.sim.SemiImplicitIntegrator``.
+"""
+import math
+
+import numpy as np
+import torch
+
+import diffrl_b200.dflex_api as df
+
+from . import torch_ops as tu
+from .base import DFlexEnv
+
+
+class _FreeRootWalker(DFlexEnv):
+    """Shared pieces of the three free-floating walkers (torso pose/velocity features, heading and
+    up-vector projections, start-pose reset)."""
+
+    nan_guard = False
+    target_x = 10000.0
+
+    def _init_common(self, start_height, start_rot):
+        n, dev = self.num_envs, self.device
+        self.start_rot = start_rot
+        self.start_rotation = tu.to_torch(start_rot, device=dev)
+        unit = lambda v: tu.to_torch(v, device=dev).repeat((n, 1))
+        self.x_unit_tensor, self.y_unit_tensor, self.z_unit_tensor = unit([1, 0, 0]), unit([0, 1, 0]), unit([0, 0, 1])
+        self.up_vec = self.y_unit_tensor.clone()
+        self.heading_vec = self.x_unit_tensor.clone()
+        self.inv_start_rot = tu.quat_conjugate(self.start_rotation).repeat((n, 1))
+        self.basis_vec0 = self.heading_vec.clone()
+        self.basis_vec1 = self.up_vec.clone()
+        self.targets = tu.to_torch([self.target_x, 0.0, 0.0], device=dev).repeat((n, 1))
+        self.env_dist = 0.0
+        self.start_pos = tu.to_torch([[0.0, start_height, 0.0]] * n, device=dev)
+
+    def _torso_features(self):
+        q = self.state.joint_q.view(self.num_envs, -1)
+        qd = self.state.joint_qd.view(self.num_envs, -1)
+        torso_pos, torso_rot = q[:, 0:3], q[:, 3:7]
+        ang_vel = qd[:, 0:3]
+        # spatial twist at the world origin -> velocity of the torso origin (ant.py:272-273)
+        lin_vel = qd[:, 3:6] - torch.cross(torso_pos, ang_vel, dim=-1)
+        to_target = self.targets + self.start_pos - torso_pos
+        to_target[:, 1] = 0.0
+        target_dirs = tu.normalize(to_target)
+        torso_quat = tu.quat_mul(torso_rot, self.inv_start_rot)
+        up_vec = tu.quat_rotate(torso_quat, self.basis_vec1)
+        heading_vec = tu.quat_rotate(torso_quat, self.basis_vec0)
+        heading_proj = (heading_vec * target_dirs).sum(dim=-1).unsqueeze(-1)
+        return q, qd, torso_pos, torso_rot, lin_vel, ang_vel, up_vec[:, 1:2], heading_proj
+
+    def _reset_state(self, env_ids):
+        q = self.state.joint_q.view(self.num_envs, -1)
+        qd = self.state.joint_qd.view(self.num_envs, -1)
+        q[env_ids, 0:3] = self.start_pos[env_ids, :].clone()
+        q[env_ids, 3:7] = self.start_rotation.clone()
+        q[env_ids, 7:] = self.start_joint_q.clone()
+        qd[env_ids, :] = 0.0
+        if self.stochastic_init:
+            k, dev = len(env_ids), self.device
+            q[env_ids, 0:3] = q[env_ids, 0:3] + 0.1 * (torch.rand(size=(k, 3), device=dev) - 0.5) * 2.0
+            angle = (torch.rand(k, device=dev) - 0.5) * np.pi / 12.0
+            axis = torch.nn.functional.normalize(torch.rand((k, 3), device=dev) - 0.5)
+            q[env_ids, 3:7] = tu.quat_mul(q[env_ids, 3:7], tu.quat_from_angle_axis(angle, axis))
+            if self.randomize_joints:
+                q[env_ids, 7:] = q[env_ids, 7:] + 0.2 * (torch.rand(size=(k, self.num_joint_q - 7), device=dev) - 0.5) * 2.0
+            qd[env_ids, :] = 0.5 * (torch.rand(size=(k, self.num_joint_qd), device=dev) - 0.5)
+
+    randomize_joints = True
+
+
+class AntEnv(_FreeRootWalker):
+    """reference envs/ant.py: 37 obs, 8 actions, 16 substeps, termination height 0.27."""
+
+    def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
+                 stochastic_init=False, MM_caching_frequency=1, early_termination=True):
+        super().__init__(num_envs, 37, 8, episode_length, MM_caching_frequency, seed, no_grad, render, device)
+        self.stochastic_init, self.early_termination = stochastic_init, early_termination
+        self.dt, self.sim_substeps = 1.0 / 60.0, 16
+        self.sim_dt, self.ground = self.dt, True
+        self.num_joint_q, self.num_joint_qd = 15, 14
+        self._init_common(0.75, df.quat_from_axis_angle((1.0, 0.0, 0.0), -math.pi * 0.5))
+        self.start_joint_q = tu.to_torch([0.0, 1.0, 0.0, -1.0, 0.0, -1.0, 0.0, 1.0], device=device)
+        self.start_joint_target = self.start_joint_q.clone()
+        self._build_model("AntEnv")
+        self.termination_height, self.action_strength = 0.27, 200.0
+        self.action_penalty, self.joint_vel_obs_scaling = 0.0, 0.1
+
+    def _apply_actions(self, actions):
+        self.state.joint_act.view(self.num_envs, -1)[:, 6:] = actions * self.action_strength
+
+    def calculateObservations(self):
+        q, qd, pos, rot, lin_vel, ang_vel, up, heading = self._torso_features()
+        self.obs_buf = torch.cat([pos[:, 1:2], rot, lin_vel, ang_vel, q[:, 7:], self.joint_vel_obs_scaling * qd[:, 6:],
+                                  up, heading, self.actions.clone()], dim=-1)
+
+    def calculateReward(self):
+        o = self.obs_buf
+        self.rew_buf = o[:, 5] + 0.1 * o[:, 27] + o[:, 28] + (o[:, 0] - self.termination_height) + \
+            torch.sum(self.actions ** 2, dim=-1) * self.action_penalty
+        if self.early_termination:
+            self.reset_buf = torch.where(o[:, 0] < self.termination_height, torch.ones_like(self.reset_buf), self.reset_buf)
+        self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
+
+
+class HumanoidEnv(_FreeRootWalker):
+    """reference envs/humanoid.py: 76 obs, 21 actions, 48 substeps, termination height 0.74."""
+
+    nan_guard = True
+    target_x = 200.0
+    MOTOR_STRENGTHS = [200, 200, 200, 200, 200, 600, 400, 100, 100, 200, 200, 600, 400, 100, 100, 100, 100, 200, 100, 100, 200]
+
+    def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
+                 stochastic_init=False, MM_caching_frequency=1):
+        super().__init__(num_envs, 76, 21, episode_length, MM_caching_frequency, seed, no_grad, render, device)
+        self.stochastic_init = stochastic_init
+        self.dt, self.sim_substeps = 1.0 / 60.0, 48
+        self.sim_dt, self.ground = self.dt, True
+        self.num_joint_q, self.num_joint_qd = 28, 27
+        self._init_common(1.35, df.quat_from_axis_angle((1.0, 0.0, 0.0), -math.pi * 0.5))
+        arrays = self._build_model("HumanoidEnv")
+        self.start_joint_q = tu.to_torch(arrays["joint_q"][7:28], device=device)
+        self.start_joint_target = self.start_joint_q.clone()
+        self.termination_height, self.termination_tolerance = 0.74, 0.1
+        self.motor_strengths = tu.to_torch(self.MOTOR_STRENGTHS, device=device).repeat((num_envs, 1))
+        self.motor_scale, self.action_penalty = 0.35, -0.002
+        self.joint_vel_obs_scaling, self.height_rew_scale = 0.1, 10.0
+
+    def _apply_actions(self, actions):
+        self.state.joint_act.view(self.num_envs, -1)[:, 6:] = actions * self.motor_scale * self.motor_strengths
+
+    def calculateObservations(self):
+        q, qd, pos, rot, lin_vel, ang_vel, up, heading = self._torso_features()
+        self.obs_buf = torch.cat([pos[:, 1:2], rot, lin_vel, ang_vel, q[:, 7:], self.joint_vel_obs_scaling * qd[:, 6:],
+                                  up, heading, self.actions.clone()], dim=-1)
+
+    def _height_reward(self, h):
+        r = torch.clip(h - (self.termination_height + self.termination_tolerance), -1.0, self.termination_tolerance)
+        r = torch.where(r < 0.0, -200.0 * r * r, r)
+        return torch.where(r > 0.0, self.height_rew_scale * r, r)
+
+    def calculateReward(self):
+        o = self.obs_buf
+        self.rew_buf = o[:, 5] + 0.1 * o[:, 53] + o[:, 54] + self._height_reward(o[:, 0]) + \
+            torch.sum(self.actions ** 2, dim=-1) * self.action_penalty
+        self.reset_buf = torch.where(o[:, 0] < self.termination_height, torch.ones_like(self.reset_buf), self.reset_buf)
+        self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
+        self.reset_buf = torch.where(self._invalid_state_mask(), torch.ones_like(self.reset_buf), self.reset_buf)
+
+
+class SNUHumanoidEnv(_FreeRootWalker):
+    """reference envs/snu_humanoid.py (lower-body SNU skeleton, 152 muscle-tendon units): 53 obs, 152
+    actions in [0, 1] after the affine map, 48 substeps, termination height 0.46."""
+
+    nan_guard = True
+    randomize_joints = False
+
+    def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
+                 stochastic_init=False, MM_caching_frequency=1):
+        self.mtu_actuations = True
+        self.num_joint_q, self.num_joint_qd = 29, 24
+        self.num_dof, self.num_muscles, self.str_scale = 22, 152, 0.6
+        super().__init__(num_envs, 53, self.num_muscles, episode_length, MM_caching_frequency, seed, no_grad, render, device)
+        self.stochastic_init = stochastic_init
+        self.inv_control_freq = 1
+        self.dt, self.sim_substeps = 1.0 / 60.0, 48
+        self.sim_dt, self.ground = self.dt, True
+        self._init_common(1.0, df.quat_from_axis_angle((0.0, 1.0, 0.0), math.pi * 0.5))
+        arrays = self._build_model("SNUHumanoidEnv")
+        self.start_joint_q = tu.to_torch(arrays["joint_q"][7:29], device=device)
+        self.start_joint_target = self.start_joint_q.clone()
+        # str_scale is applied twice in the reference (snu_humanoid.py:176-180)
+        f0 = arrays["muscle_params"][:, 0].astype(np.float64)
+        self.muscle_strengths = tu.to_torch(self.str_scale * (self.str_scale * f0), device=device).repeat(num_envs)
+        self.termination_height, self.termination_tolerance = 0.46, 0.05
+        self.height_rew_scale, self.action_strength = 4.0, 100.0
+        self.action_penalty, self.joint_vel_obs_scaling = -0.001, 0.1
+
+    def _preprocess_actions(self, actions):
+        return actions * 0.5 + 0.5
+
+    def _apply_actions(self, actions):
+        self.model.muscle_activation = actions.view(-1) * self.muscle_strengths
+
+    def calculateObservations(self):
+        q, qd, pos, rot, lin_vel, ang_vel, up, heading = self._torso_features()
+        self.obs_buf = torch.cat([pos[:, 1:2], rot, lin_vel, ang_vel, q[:, 7:], self.joint_vel_obs_scaling * qd[:, 6:],
+                                  up, heading], dim=-1)
+
+    def calculateReward(self):
+        o = self.obs_buf
+        act_penalty = torch.sum(torch.abs(self.actions), dim=-1) * self.action_penalty
+        self.rew_buf = o[:, 5] + 0.1 * o[:, 51] + o[:, 52] + act_penalty
+        self.reset_buf = torch.where(o[:, 0] < self.termination_height, torch.ones_like(self.reset_buf), self.reset_buf)
+        self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
+        invalid = self._invalid_state_mask()
+        self.reset_buf = torch.where(invalid, torch.ones_like(self.reset_buf), self.reset_buf)
+        self.rew_buf[invalid] = 0.0
+
+
+class CartPoleSwingUpEnv(DFlexEnv):
+    """reference envs/cartpole_swing_up.py: 5 obs, 1 action, 4 substeps, no ground."""
+
+    clone_actions = False
+
+    def __init__(self, render=False, device="cuda:0", num_envs=1024, seed=0, episode_length=240, no_grad=True,
+                 stochastic_init=False, MM_caching_frequency=1, early_termination=False):
+        super().__init__(num_envs, 5, 1, episode_length, MM_caching_frequency, seed, no_grad, render, device)
+        self.stochastic_init, self.early_termination = stochastic_init, early_termination
+        self.dt, self.sim_substeps = 1.0 / 60.0, 4
+        self.sim_dt, self.ground = self.dt, False
+        self.num_joint_q = self.num_joint_qd = 2
+        self._build_model("CartPoleSwingUpEnv")
+        self.start_joint_q = self.state.joint_q.clone()
+        self.start_joint_qd = self.state.joint_qd.clone()
+        self.action_strength = 1000.0
+        self.pole_angle_penalty, self.pole_velocity_penalty = 1.0, 0.1
+        self.cart_position_penalty, self.cart_velocity_penalty, self.cart_action_penalty = 0.05, 0.1, 0.0
+
+    def _apply_actions(self, actions):
+        self.state.joint_act.view(self.num_envs, -1)[:, 0:1] = actions * self.action_strength
+
+    def _reset_state(self, env_ids):
+        q = self.state.joint_q.view(self.num_envs, -1)
+        qd = self.state.joint_qd.view(self.num_envs, -1)
+        q[env_ids, :] = self.start_joint_q.view(-1, self.num_joint_q)[env_ids, :].clone()
+        qd[env_ids, :] = self.start_joint_qd.view(-1, self.num_joint_qd)[env_ids, :].clone()
+        if self.stochastic_init:
+            k, dev = len(env_ids), self.device
+            q[env_ids, :] = q[env_ids, :] + np.pi * (torch.rand(size=(k, self.num_joint_q), device=dev) - 0.5)
+            qd[env_ids, :] = qd[env_ids, :] + 0.5 * (torch.rand(size=(k, self.num_joint_qd), device=dev) - 0.5)
+
+    def clear_grad(self, checkpoint=None):
+        with torch.no_grad():
+            q, qd, act = self.state.joint_q.clone(), self.state.joint_qd.clone(), self.state.joint_act.clone()
+            self.state = self.model.state()
+            self.state.joint_q, self.state.joint_qd, self.state.joint_act = q, qd, act
+
+    def calculateObservations(self):
+        q = self.state.joint_q.view(self.num_envs, -1)
+        qd = self.state.joint_qd.view(self.num_envs, -1)
+        theta = q[:, 1:2]
+        self.obs_buf = torch.cat([q[:, 0:1], qd[:, 0:1], torch.sin(theta), torch.cos(theta), qd[:, 1:2]], dim=-1)
+
+    def calculateReward(self):
+        q = self.state.joint_q.view(self.num_envs, -1)
+        qd = self.state.joint_qd.view(self.num_envs, -1)
+        theta = tu.normalize_angle(q[:, 1])
+        self.rew_buf = -torch.pow(theta, 2.0) * self.pole_angle_penalty - torch.pow(qd[:, 1], 2.0) * self.pole_velocity_penalty \
+            - torch.pow(q[:, 0], 2.0) * self.cart_position_penalty - torch.pow(qd[:, 0], 2.0) * self.cart_velocity_penalty \
+            - torch.sum(self.actions ** 2, dim=-1) * self.cart_action_penalty
+        self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
+
+
+class _PlanarHopper(DFlexEnv):
+    """Planar (x, z, pitch) rooted chains: Hopper and HalfCheetah share reset and observation code."""
+
+    init_noise = (0.05, 0.1, 0.05, 0.05 * 2.0)   # pos, pitch span, joints, velocity span
+
+    def _init_planar(self, asset, start_height, n_joint):
+        n, dev = self.num_envs, self.device
+        self.dt, self.sim_substeps = 1.0 / 60.0, 16
+        self.sim_dt, self.ground = self.dt, True
+        self.num_joint_q = self.num_joint_qd = 3 + n_joint
+        self.start_rotation = torch.tensor([0.0], device=dev)
+        self.start_pos = tu.to_torch([[0.0, start_height]] * n, device=dev)
+        self.start_joint_q = tu.to_torch([0.0] * n_joint, device=dev)
+        self.start_joint_target = self.start_joint_q.clone()
+        self._build_model(asset)
+
+    def _apply_actions(self, actions):
+        self.state.joint_act.view(self.num_envs, -1)[:, 3:] = actions * self.action_strength
+
+    def _reset_state(self, env_ids):
+        q = self.state.joint_q.view(self.num_envs, -1)
+        qd = self.state.joint_qd.view(self.num_envs, -1)
+        q[env_ids, 0:2] = self.start_pos[env_ids, :].clone()
+        q[env_ids, 2] = self.start_rotation.clone()
+        q[env_ids, 3:] = self.start_joint_q.clone()
+        qd[env_ids, :] = 0.0
+        if self.stochastic_init:
+            k, dev = len(env_ids), self.device
+            a_pos, a_rot, a_joint, a_vel = self.init_noise
+            q[env_ids, 0:2] = q[env_ids, 0:2] + a_pos * (torch.rand(size=(k, 2), device=dev) - 0.5) * 2.0
+            q[env_ids, 2] = (torch.rand(k, device=dev) - 0.5) * a_rot
+            q[env_ids, 3:] = q[env_ids, 3:] + a_joint * (torch.rand(size=(k, self.num_joint_q - 3), device=dev) - 0.5) * 2.0
+            qd[env_ids, :] = a_vel * (torch.rand(size=(k, self.num_joint_qd), device=dev) - 0.5)
+
+    def calculateObservations(self):
+        self.obs_buf = torch.cat([self.state.joint_q.view(self.num_envs, -1)[:, 1:], self.state.joint_qd.view(self.num_envs, -1)], dim=-1)
+
+
+class HopperEnv(_PlanarHopper):
+    """reference envs/hopper.py: 11 obs, 3 actions."""
+
+    def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
+                 stochastic_init=False, MM_caching_frequency=1, early_termination=True):
+        super().__init__(num_envs, 11, 3, episode_length, MM_caching_frequency, seed, no_grad, render, device)
+        self.stochastic_init, self.early_termination = stochastic_init, early_termination
+        self._init_planar("HopperEnv", 0.0, 3)
+        self.termination_height, self.termination_angle = -0.45, np.pi / 6.0
+        self.termination_height_tolerance, self.termination_angle_tolerance = 0.15, 0.05
+        self.height_rew_scale, self.action_strength, self.action_penalty = 1.0, 200.0, -1e-1
+
+    def calculateReward(self):
+        o = self.obs_buf
+        h = torch.clip(o[:, 0] - (self.termination_height + self.termination_height_tolerance), -1.0, 0.3)
+        h = torch.where(h < 0.0, -200.0 * h * h, h)
+        h = torch.where(h > 0.0, self.height_rew_scale * h, h)
+        angle_reward = 1.0 * (-o[:, 1] ** 2 / (self.termination_angle ** 2) + 1.0)
+        self.rew_buf = o[:, 5] + h + angle_reward + torch.sum(self.actions ** 2, dim=-1) * self.action_penalty
+        self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
+        if self.early_termination:
+            self.reset_buf = torch.where(o[:, 0] < self.termination_height, torch.ones_like(self.reset_buf), self.reset_buf)
+
+
+class CheetahEnv(_PlanarHopper):
+    """reference envs/cheetah.py: 17 obs, 6 actions, no early termination."""
+
+    init_noise = (0.1, 0.2, 0.1, 0.5)
+
+    def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
+                 stochastic_init=False, MM_caching_frequency=1, early_termination=False):
+        super().__init__(num_envs, 17, 6, episode_length, MM_caching_frequency, seed, no_grad, render, device)
+        self.stochastic_init, self.early_termination = stochastic_init, early_termination
+        self._init_planar("CheetahEnv", -0.2, 6)
+        self.action_strength, self.action_penalty = 200.0, -0.1
+
+    def calculateReward(self):
+        self.rew_buf = self.obs_buf[:, 8] + torch.sum(self.actions ** 2, dim=-1) * self.action_penalty
+        self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
