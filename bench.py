@@ -218,6 +218,11 @@ def run_ours(args):
     for _ in range(args.warmup):
         kernel_rollout()
     barrier()
+    if args.ncu_range:
+        torch.cuda.profiler.start()
+        kernel_rollout()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     launches0 = lib.dfx_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     with ClockSampler(local) as clocks:
@@ -344,6 +349,8 @@ def main():
     ap.add_argument("--num-envs", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="wrap ONE kernel-path step and ONE e2e step in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

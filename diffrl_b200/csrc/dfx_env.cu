@@ -1,0 +1,185 @@
+// dfx_env.cu -- fused observation / reward / termination epilogue of the free-root walker envs
+// (Ant, Humanoid, SNU humanoid) and its adjoint: SURVEY.md section 8f row 1.
+//
+// In the reference these are ~35 small PyTorch ops per env.step() plus ~60 autograd ops in backward
+// (envs/ant.py:266-307, envs/humanoid.py:314-368, envs/snu_humanoid.py:378-432): launch-bound once the
+// simulation step itself takes a few hundred microseconds.  Here: one thread per environment, one
+// launch forward, one launch backward, straight from / to the env-major (q, qd, actions) rows.
+#include <cuda_runtime.h>
+
+#include "../../include/dfx.h"
+#include "dfx_math.h"
+
+using namespace dfx;
+
+namespace {
+
+__device__ __forceinline__ void walker_features(const DfxWalkerParams& p, const float* q, const float* qd,
+                                                V3& pos, Q4& rot, V3& ang, V3& lin, V3& tt, float& tn, V3& tdir,
+                                                Q4& tq, V3& up, V3& heading) {
+    pos = ld3(q);
+    rot = ld4(q + 3);
+    ang = ld3(qd);
+    lin = ld3(qd + 3) - cross(pos, ang);   // twist at the world origin -> velocity of the torso origin
+    tt = V3{p.target[0] - pos.x, 0.0f, p.target[2] - pos.z};
+    tn = fmaxf(sqrtf(dot(tt, tt)), 1e-9f);
+    tdir = tt * (1.0f / tn);
+    tq = qmul(rot, ld4(p.inv_start_rot));
+    up = qrot(tq, ld3(p.basis_up));
+    heading = qrot(tq, ld3(p.basis_heading));
+}
+
+__device__ __forceinline__ float height_reward(const DfxWalkerParams& p, float h, float* dh) {
+    if (p.height_mode == 0) { *dh = 1.0f; return h - p.termination_height; }
+    if (p.height_mode == 2) { *dh = 0.0f; return 0.0f; }
+    // clip(h - (term + tol), -1, tol); r<0 -> -200 r^2 ; r>0 -> scale*r        (humanoid.py:348-351)
+    float x = h - (p.termination_height + p.termination_tolerance);
+    float r = fminf(fmaxf(x, -1.0f), p.termination_tolerance);
+    float dr = (x >= -1.0f && x <= p.termination_tolerance) ? 1.0f : 0.0f;   // torch.clip: gradient 1 inside, incl. the ends
+    if (r < 0.0f) { *dh = -400.0f * r * dr; return -200.0f * r * r; }
+    if (r > 0.0f) { *dh = p.height_rew_scale * dr; return p.height_rew_scale * r; }
+    *dh = dr;
+    return r;
+}
+
+__global__ void walker_forward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                      const float* __restrict__ actions, const long long* __restrict__ progress,
+                                      float* __restrict__ obs, float* __restrict__ rew, long long* __restrict__ reset) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float* qe = q + (size_t)e * p.num_q;
+    const float* qde = qd + (size_t)e * p.num_qd;
+    const float* ae = actions + (size_t)e * p.num_act;
+    V3 pos, ang, lin, tt, tdir, up, heading;
+    Q4 rot, tq;
+    float tn;
+    walker_features(p, qe, qde, pos, rot, ang, lin, tt, tn, tdir, tq, up, heading);
+    float* o = obs + (size_t)e * p.num_obs;
+    int k = 0;
+    o[k++] = pos.y;
+    o[k++] = rot.x; o[k++] = rot.y; o[k++] = rot.z; o[k++] = rot.w;
+    o[k++] = lin.x; o[k++] = lin.y; o[k++] = lin.z;
+    o[k++] = ang.x; o[k++] = ang.y; o[k++] = ang.z;
+    bool bad = false;
+    for (int i = 7; i < p.num_q; ++i) o[k++] = qe[i];
+    for (int i = 6; i < p.num_qd; ++i) o[k++] = p.joint_vel_scale * qde[i];
+    const float up_y = up.y, hproj = dot(heading, tdir);
+    o[k++] = up_y;
+    o[k++] = hproj;
+    float act_sq = 0.0f, act_abs = 0.0f;
+    for (int i = 0; i < p.num_act; ++i) {
+        const float a = ae[i];
+        if (p.obs_has_actions) o[k++] = a;
+        act_sq += a * a;
+        act_abs += fabsf(a);
+    }
+    if (!rew) return;
+    float dh;
+    const float hr = height_reward(p, pos.y, &dh);
+    float r = lin.x + 0.1f * up_y + hproj;
+    if (p.height_mode != 2) r += hr;
+    r += (p.action_penalty_abs ? act_abs : act_sq) * p.action_penalty;
+    long long rs = 0;
+    if (p.early_termination && pos.y < p.termination_height) rs = 1;
+    if (progress[e] > (long long)p.episode_length - 1) rs = 1;
+    if (p.check_invalid) {
+        for (int i = 0; i < p.num_q; ++i) bad |= !isfinite(qe[i]) || fabsf(qe[i]) > 1e6f;
+        for (int i = 0; i < p.num_qd; ++i) bad |= !isfinite(qde[i]) || fabsf(qde[i]) > 1e6f;
+        for (int i = 0; i < p.num_obs; ++i) bad |= !isfinite(o[i]);
+        if (bad) { rs = 1; if (p.zero_reward_on_invalid) r = 0.0f; }
+    }
+    rew[e] = r;
+    reset[e] = rs;
+}
+
+__global__ void walker_backward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                       const float* __restrict__ actions, const float* __restrict__ g_obs,
+                                       const float* __restrict__ g_rew, float* __restrict__ gq, float* __restrict__ gqd,
+                                       float* __restrict__ gact) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float* qe = q + (size_t)e * p.num_q;
+    const float* qde = qd + (size_t)e * p.num_qd;
+    const float* ae = actions + (size_t)e * p.num_act;
+    V3 pos, ang, lin, tt, tdir, up, heading;
+    Q4 rot, tq;
+    float tn;
+    walker_features(p, qe, qde, pos, rot, ang, lin, tt, tn, tdir, tq, up, heading);
+    const float* go = g_obs ? g_obs + (size_t)e * p.num_obs : nullptr;
+    float gr = g_rew ? g_rew[e] : 0.0f;
+    if (p.check_invalid && p.zero_reward_on_invalid && g_rew) {
+        bool bad = false;
+        for (int i = 0; i < p.num_q; ++i) bad |= !isfinite(qe[i]) || fabsf(qe[i]) > 1e6f;
+        for (int i = 0; i < p.num_qd; ++i) bad |= !isfinite(qde[i]) || fabsf(qde[i]) > 1e6f;
+        if (bad) gr = 0.0f;
+    }
+    float dh;
+    height_reward(p, pos.y, &dh);
+    int k = 0;
+    auto G = [&](int idx) { return go ? go[idx] : 0.0f; };
+    // cotangents of the features
+    float a_posy = G(0) + (p.height_mode != 2 ? gr * dh : 0.0f);
+    Q4 a_rot = Q4{G(1), G(2), G(3), G(4)};
+    V3 a_lin = V3{G(5) + gr, G(6), G(7)};
+    V3 a_ang = V3{G(8), G(9), G(10)};
+    k = 11;
+    float* gqe = gq + (size_t)e * p.num_q;
+    float* gqde = gqd + (size_t)e * p.num_qd;
+    for (int i = 7; i < p.num_q; ++i) gqe[i] = G(k++);
+    for (int i = 6; i < p.num_qd; ++i) gqde[i] = p.joint_vel_scale * G(k++);
+    const float a_upy = G(k) + 0.1f * gr; ++k;
+    const float a_h = G(k) + gr; ++k;
+    if (gact) {
+        float* gae = gact + (size_t)e * p.num_act;
+        for (int i = 0; i < p.num_act; ++i) {
+            const float a = ae[i];
+            float g = p.obs_has_actions ? G(k + i) : 0.0f;
+            g += gr * p.action_penalty * (p.action_penalty_abs ? (a < 0.0f ? -1.0f : (a > 0.0f ? 1.0f : 0.0f)) : 2.0f * a);
+            gae[i] = g;
+        }
+    }
+    // hproj = heading . tdir
+    V3 a_heading = tdir * a_h;
+    V3 a_tdir = heading * a_h;
+    // tdir = tt / tn, tn = max(|tt|, eps)
+    V3 a_tt = a_tdir * (1.0f / tn);
+    if (sqrtf(dot(tt, tt)) > 1e-9f) a_tt -= tdir * (dot(a_tdir, tdir) / tn);
+    V3 a_pos = V3{-a_tt.x, a_posy, -a_tt.z};
+    // up = R(tq) b1 ; heading = R(tq) b0
+    Q4 a_tq = qrot_adj_q(tq, ld3(p.basis_up), V3{0.0f, a_upy, 0.0f});
+    a_tq += qrot_adj_q(tq, ld3(p.basis_heading), a_heading);
+    // tq = rot * inv_start
+    a_rot += qmul_adj_a(ld4(p.inv_start_rot), a_tq);
+    // lin = v - pos x ang
+    V3 a_v = a_lin;
+    V3 nl = -a_lin;
+    cross_adj(pos, ang, nl, a_pos, a_ang);
+    gqe[0] = a_pos.x; gqe[1] = a_pos.y; gqe[2] = a_pos.z;
+    gqe[3] = a_rot.x; gqe[4] = a_rot.y; gqe[5] = a_rot.z; gqe[6] = a_rot.w;
+    gqde[0] = a_ang.x; gqde[1] = a_ang.y; gqde[2] = a_ang.z;
+    gqde[3] = a_v.x; gqde[4] = a_v.y; gqde[5] = a_v.z;
+}
+
+}  // namespace
+
+extern long long dfx_count_launch(void);
+
+extern "C" {
+
+int dfx_walker_obs_forward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                           const long long* progress, float* obs, float* rew, long long* reset, void* stream) {
+    if (!p || n <= 0 || !q || !qd || !actions || !obs || (rew && (!reset || !progress))) return (int)cudaErrorInvalidValue;
+    walker_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, progress, obs, rew, reset);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                            const float* g_obs, const float* g_rew, float* gq, float* gqd, float* gact, void* stream) {
+    if (!p || n <= 0 || !q || !qd || !actions || !gq || !gqd) return (int)cudaErrorInvalidValue;
+    walker_backward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, g_obs, g_rew, gq, gqd, gact);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

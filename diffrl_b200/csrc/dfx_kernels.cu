@@ -109,6 +109,7 @@ struct dfx_pack {
 };
 
 static std::atomic<long long> g_launches{0};
+long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
 
 static void set_err(char* err, int n, const std::string& m) {
@@ -161,6 +162,7 @@ int dfx_pack_query(const dfx_pack_t* p, int what) {
         case DFX_QUERY_MUSCLES: return p->header.M;
         case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
         case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
+        case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
         case DFX_QUERY_TREE_DEPTH: return p->header.nlev;
     }
     return -1;
@@ -173,7 +175,7 @@ int dfx_pack_set_gravity(dfx_pack_t* p, float gx, float gy, float gz, int ground
 }
 
 long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq) {
-    return tape_geom(p->header.Q, p->header.D, n, substeps, mm_freq).total;
+    return tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).total;
 }
 
 }  // extern "C"
@@ -230,7 +232,7 @@ int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, doub
     a.dt_sub = (float)(dt / (double)substeps);
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
-    a.hinv_base = tape_geom(p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_group(p)) {
         case 8: return (int)launch<8, false>(p, a, st);
@@ -251,7 +253,7 @@ int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, dou
     a.dt_sub = (float)(dt / (double)substeps);
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
-    a.hinv_base = tape_geom(p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_group(p)) {
         case 8: return (int)launch<8, true>(p, a, st);

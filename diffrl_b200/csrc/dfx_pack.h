@@ -75,6 +75,7 @@ struct Layout {
     int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
     int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
     int fwd_size;
+    int tape_row;  // floats of the contiguous [q, qd, X_sc, X_sm, S, v, a, f_tot, qdd] block
     // adjoint
     int aq, aqd, aqdd, aact, amusc;
     int aXsc, aXsm, aS, av, aa, af, aIbar /* (L,12): dL/dR (9) + dL/du (3) */, pX;
@@ -87,9 +88,13 @@ inline Layout make_layout(int L, int D, int Q, int C, int M) {
     Layout y;
     int o = 0;
     auto take = [&](int n) { int r = o; o += n; return r; };
-    y.q = take(Q); y.qd = take(D); y.act = take(D); y.musc = take(M); y.tau = take(D); y.qdd = take(D);
+    // [q .. qdd] is one contiguous block: it is what forward writes to the tape per substep and what the
+    // adjoint reads back instead of re-running the forward dynamics (tape_row floats)
+    y.q = take(Q); y.qd = take(D);
     y.Xsc = take(L * 7); y.Xsm = take(L * 7); y.S = take(D * 6); y.v = take(L * 6); y.a = take(L * 6);
-    y.f = take(L * 6); y.ft = take(L * 6);
+    y.ft = take(L * 6); y.qdd = take(D);
+    y.tape_row = o;
+    y.act = take(D); y.musc = take(M); y.tau = take(D); y.f = take(L * 6);
     y.A = take(D * D); y.Lm = take(D * D);
     y.Icmp = take(L * 21 + D * 6);
     // the contact staging buffer aliases nothing in forward; in backward it needs 13 floats/contact

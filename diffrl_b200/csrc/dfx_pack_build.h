@@ -200,13 +200,13 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
 
 // tape geometry shared by forward / backward / host emulation
 struct TapeGeom {
-    int N, S, nseg, QD, DD;
+    int N, S, nseg, QD /* floats per (substep, env) row */, DD;
     long long hinv_base;  // float offset of the H^-1 blocks
     long long total;
 };
-inline TapeGeom tape_geom(int Q, int D, int N, int substeps, int mm_freq) {
+inline TapeGeom tape_geom(int L, int Q, int D, int N, int substeps, int mm_freq) {
     TapeGeom t;
-    t.N = N; t.S = substeps; t.QD = Q + D; t.DD = D * D;
+    t.N = N; t.S = substeps; t.QD = make_layout(L, D, Q, 0, 0).tape_row; t.DD = D * D;
     t.nseg = (substeps + mm_freq - 1) / mm_freq;
     t.hinv_base = (long long)substeps * N * t.QD;
     t.total = t.hinv_base + (long long)t.nseg * N * t.DD;

@@ -890,17 +890,11 @@ DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_m
     solve_fwd(P, Y, s, g);
 }
 
-// adjoint of one substep.  Pre: scratch q, qd (substep input), act, musc, A = H^-1 of the segment;
-// aq, aqd = cotangents of the substep output.  Post: aq, aqd = cotangents of the substep input;
+// adjoint of one substep.  Pre: scratch [q .. qdd] = the substep's taped block (entering q, qd and the
+// forward intermediates), act, musc, A = H^-1 of the segment; aq, aqd = cotangents of the substep output.  Post: aq, aqd = cotangents of the substep input;
 // aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
 template <class Grp>
 DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool apply_crba, const Grp& g) {
-    kin_fwd(P, Y, s, g);
-    body_force_fwd(P, Y, s, g);
-    contact_fwd(P, Y, s, g);
-    muscle_fwd(P, Y, s, g);
-    tau_fwd(P, Y, s, g);
-    solve_fwd(P, Y, s, g);
     zero_range(s + Y.aXsc, P.L * 7, g);
     zero_range(s + Y.aXsm, P.L * 7, g);
     zero_range(s + Y.aS, P.D * 6, g);

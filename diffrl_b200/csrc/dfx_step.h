@@ -3,10 +3,12 @@
 // kernels (dfx_kernels.cu) and the host emulation used by CPU-side unit tests.
 //
 // Tape (written by forward when taping, read by backward), all fp32:
-//   [substep][env][Q + D]     the (q, qd) ENTERING each substep         -- tile-contiguous per substep
+//   [substep][env][tape_row]  per substep: the (q, qd) ENTERING it and the forward intermediates the adjoint
+//                             needs -- X_sc, X_sm, S, v, a, total link wrenches, q'' (32 L + 8 D + Q floats)
 //   [segment][env][D * D]     H^-1 of each mass-matrix update
-// The reference instead keeps every State tensor of every substep alive (~3.7 KB/env/substep
-// for Ant); here the adjoint recomputes the substep from (q, qd).
+// The path is FP32-issue bound with HBM idle, so the adjoint trades bandwidth for instructions: it reads these
+// rows back (coalesced, tile-contiguous per substep) instead of re-running the forward dynamics.  Ant: 1.7 KB
+// per env-substep vs the reference's ~3.7 KB (it keeps every State tensor alive).
 #pragma once
 
 #include "../../include/dfx.h"
@@ -45,17 +47,13 @@ DFX_HD void dump_derived(const Pack& P, const Layout& Y, const float* s, const D
 
 template <class Grp>
 DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp& g, int env, const StepArgs& a) {
-    const int Q = P.Q, D = P.D, M = P.M, QD = Q + D, DD = D * D;
+    const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
     DFX_FOR(i, Q) s[Y.q + i] = a.q[(long long)env * Q + i];
     DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
     DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
-        if (a.tape) {
-            float* t = a.tape + ((long long)sub * a.N + env) * QD;
-            DFX_FOR(i, QD) t[i] = s[Y.q + i];   // q and qd are adjacent in the scratch block
-        }
         kin_fwd(P, Y, s, g);
         body_force_fwd(P, Y, s, g);
         contact_fwd(P, Y, s, g);
@@ -73,7 +71,12 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
             }
         }
         solve_fwd(P, Y, s, g);
+        if (a.tape) {   // q, qd still hold the values that ENTERED this substep
+            float* t = a.tape + ((long long)sub * a.N + env) * QD;
+            DFX_FOR(i, QD) t[i] = s[Y.q + i];
+        }
         if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, g);
+        g.sync();   // the tape / dump copies above read q, qd, which integrate_fwd overwrites in place
         integrate_fwd(P, Y, s, a.dt_sub, g);
     }
     DFX_FOR(i, Q) a.q_out[(long long)env * Q + i] = s[Y.q + i];
@@ -82,7 +85,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
 
 template <class Grp>
 DFX_HD void env_step_backward(const Pack& P, const Layout& Y, float* s, const Grp& g, int env, const StepArgs& a) {
-    const int Q = P.Q, D = P.D, M = P.M, QD = Q + D, DD = D * D;
+    const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
     DFX_FOR(i, D) { s[Y.act + i] = a.act[(long long)env * D + i]; s[Y.aact + i] = 0.0f; }
     DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
     DFX_FOR(i, Q) s[Y.aq + i] = a.gq_out ? a.gq_out[(long long)env * Q + i] : 0.0f;

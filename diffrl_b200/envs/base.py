@@ -119,6 +119,9 @@ class DFlexEnv:
 
     nan_guard = False
     clone_actions = True
+    # True: terminated environments are re-initialised with a mask (torch.where) instead of the reference's
+    # reset_buf.nonzero() + indexed writes, so env.step() never synchronises the host with the GPU.
+    sync_free_reset = True
 
     def step(self, actions):
         actions = actions.view((self.num_envs, self.num_actions))
@@ -132,15 +135,21 @@ class DFlexEnv:
         self.reset_buf = torch.zeros_like(self.reset_buf)
         self.progress_buf += 1
         self.num_frames += 1
-        self.calculateObservations()
-        self.calculateReward()
-        env_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        self._observe_and_reward()
         if not self.no_grad:
             self.obs_buf_before_reset = self.obs_buf.clone()
             self.extras = {"obs_before_reset": self.obs_buf_before_reset, "episode_end": self.termination_buf}
-        if len(env_ids) > 0:
-            self.reset(env_ids)
+        if self.sync_free_reset and hasattr(self, "_reset_masked"):
+            self._reset_masked(self.reset_buf)
+        else:
+            env_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+            if len(env_ids) > 0:
+                self.reset(env_ids)
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _observe_and_reward(self):
+        self.calculateObservations()
+        self.calculateReward()
 
     def _preprocess_actions(self, actions):
         return actions

@@ -7,6 +7,7 @@ distributions and constants (cited per class); obs / reward / gradient parity ag
 reference's own rollouts is tested in tests/test_gpu_envs.py.  The simulation step itself is the
 fused kernel behind ``df.sim.SemiImplicitIntegrator``.
 """
+import ctypes
 import math
 
 import numpy as np
@@ -39,6 +40,73 @@ class _FreeRootWalker(DFlexEnv):
         self.targets = tu.to_torch([self.target_x, 0.0, 0.0], device=dev).repeat((n, 1))
         self.env_dist = 0.0
         self.start_pos = tu.to_torch([[0.0, start_height, 0.0]] * n, device=dev)
+
+    # ---- fused epilogue -------------------------------------------------------------------------
+    def _walker_params(self):
+        from ..env_ops import DfxWalkerParams
+        p = DfxWalkerParams()
+        p.num_q, p.num_qd, p.num_act, p.num_obs = self.num_joint_q, self.num_joint_qd, self.num_actions, self.num_observations
+        p.obs_has_actions = int(self.obs_has_actions)
+        p.height_mode, p.action_penalty_abs = int(self.height_mode), int(self.action_penalty_abs)
+        p.early_termination = int(getattr(self, "early_termination", True))
+        p.check_invalid, p.zero_reward_on_invalid = int(self.check_invalid), int(self.zero_reward_on_invalid)
+        p.episode_length = int(self.episode_length)
+        p.joint_vel_scale = float(self.joint_vel_obs_scaling)
+        p.termination_height = float(self.termination_height)
+        p.termination_tolerance = float(getattr(self, "termination_tolerance", 0.0))
+        p.height_rew_scale = float(getattr(self, "height_rew_scale", 1.0))
+        p.action_penalty = float(self.action_penalty)
+        tgt = (self.targets[0] + self.start_pos[0]).tolist()
+        p.target = (ctypes.c_float * 3)(*tgt)
+        p.inv_start_rot = (ctypes.c_float * 4)(*self.inv_start_rot[0].tolist())
+        p.basis_heading = (ctypes.c_float * 3)(*self.basis_vec0[0].tolist())
+        p.basis_up = (ctypes.c_float * 3)(*self.basis_vec1[0].tolist())
+        return p
+
+    obs_has_actions, height_mode, action_penalty_abs = True, 0, False
+    check_invalid, zero_reward_on_invalid = False, False
+    fused_epilogue = True
+
+    def _fused(self, want_reward):
+        from ..env_ops import WalkerObsFunction
+        if getattr(self, "_wparams", None) is None:
+            self._wparams = self._walker_params()
+        return WalkerObsFunction.apply(self._wparams, self.num_envs, want_reward, self.progress_buf,
+                                       self.state.joint_q, self.state.joint_qd, self.actions)
+
+    def _observe_and_reward(self):
+        if self.fused_epilogue and torch.device(self.device).type == "cuda":
+            self.obs_buf, self.rew_buf, self.reset_buf = self._fused(True)
+        else:
+            self.calculateObservations()
+            self.calculateReward()
+
+    def _reset_masked(self, reset_buf):
+        """Re-initialise terminated environments without reading reset_buf on the host."""
+        n = self.num_envs
+        mask = reset_buf.bool().unsqueeze(-1)
+        q = self.state.joint_q.view(n, -1)
+        qd = self.state.joint_qd.view(n, -1)
+        if getattr(self, "_start_q_full", None) is None:
+            self._start_q_full = torch.cat([self.start_pos, self.start_rotation.expand(n, 4),
+                                            self.start_joint_q.expand(n, -1)], dim=-1).contiguous()
+            self._zero_qd, self._zero_act = torch.zeros_like(qd), torch.zeros_like(self.actions)
+        start_q, start_qd = self._start_q_full, self._zero_qd
+        if self.stochastic_init:
+            dev = self.device
+            start_q = start_q.clone()
+            start_q[:, 0:3] = start_q[:, 0:3] + 0.1 * (torch.rand(size=(n, 3), device=dev) - 0.5) * 2.0
+            angle = (torch.rand(n, device=dev) - 0.5) * np.pi / 12.0
+            axis = torch.nn.functional.normalize(torch.rand((n, 3), device=dev) - 0.5)
+            start_q[:, 3:7] = tu.quat_mul(start_q[:, 3:7], tu.quat_from_angle_axis(angle, axis))
+            if self.randomize_joints:
+                start_q[:, 7:] = start_q[:, 7:] + 0.2 * (torch.rand(size=(n, self.num_joint_q - 7), device=dev) - 0.5) * 2.0
+            start_qd = 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
+        self.state.joint_q = torch.where(mask, start_q, q).view(-1)
+        self.state.joint_qd = torch.where(mask, start_qd, qd).view(-1)
+        self.actions = torch.where(mask, self._zero_act, self.actions)
+        self.progress_buf = torch.where(reset_buf.bool(), torch.zeros_like(self.progress_buf), self.progress_buf)
+        self.calculateObservations()
 
     def _torso_features(self):
         q = self.state.joint_q.view(self.num_envs, -1)
@@ -97,6 +165,9 @@ class AntEnv(_FreeRootWalker):
         self.state.joint_act.view(self.num_envs, -1)[:, 6:] = actions * self.action_strength
 
     def calculateObservations(self):
+        if self.fused_epilogue and torch.device(self.device).type == "cuda":
+            self.obs_buf = self._fused(False)
+            return
         q, qd, pos, rot, lin_vel, ang_vel, up, heading = self._torso_features()
         self.obs_buf = torch.cat([pos[:, 1:2], rot, lin_vel, ang_vel, q[:, 7:], self.joint_vel_obs_scaling * qd[:, 6:],
                                   up, heading, self.actions.clone()], dim=-1)
@@ -115,6 +186,7 @@ class HumanoidEnv(_FreeRootWalker):
 
     nan_guard = True
     target_x = 200.0
+    height_mode, check_invalid = 1, True
     MOTOR_STRENGTHS = [200, 200, 200, 200, 200, 600, 400, 100, 100, 200, 200, 600, 400, 100, 100, 100, 100, 200, 100, 100, 200]
 
     def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
@@ -137,6 +209,9 @@ class HumanoidEnv(_FreeRootWalker):
         self.state.joint_act.view(self.num_envs, -1)[:, 6:] = actions * self.motor_scale * self.motor_strengths
 
     def calculateObservations(self):
+        if self.fused_epilogue and torch.device(self.device).type == "cuda":
+            self.obs_buf = self._fused(False)
+            return
         q, qd, pos, rot, lin_vel, ang_vel, up, heading = self._torso_features()
         self.obs_buf = torch.cat([pos[:, 1:2], rot, lin_vel, ang_vel, q[:, 7:], self.joint_vel_obs_scaling * qd[:, 6:],
                                   up, heading, self.actions.clone()], dim=-1)
@@ -161,6 +236,8 @@ class SNUHumanoidEnv(_FreeRootWalker):
 
     nan_guard = True
     randomize_joints = False
+    obs_has_actions, height_mode, action_penalty_abs = False, 2, True
+    check_invalid, zero_reward_on_invalid = True, True
 
     def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
                  stochastic_init=False, MM_caching_frequency=1):
@@ -190,6 +267,9 @@ class SNUHumanoidEnv(_FreeRootWalker):
         self.model.muscle_activation = actions.view(-1) * self.muscle_strengths
 
     def calculateObservations(self):
+        if self.fused_epilogue and torch.device(self.device).type == "cuda":
+            self.obs_buf = self._fused(False)
+            return
         q, qd, pos, rot, lin_vel, ang_vel, up, heading = self._torso_features()
         self.obs_buf = torch.cat([pos[:, 1:2], rot, lin_vel, ang_vel, q[:, 7:], self.joint_vel_obs_scaling * qd[:, 6:],
                                   up, heading], dim=-1)

@@ -99,7 +99,8 @@ enum {
     DFX_QUERY_MUSCLES = 4,
     DFX_QUERY_FWD_SCRATCH_FLOATS = 5, /* shared-memory floats per environment, forward */
     DFX_QUERY_BWD_SCRATCH_FLOATS = 6, /* shared-memory floats per environment, backward */
-    DFX_QUERY_TREE_DEPTH = 7
+    DFX_QUERY_TREE_DEPTH = 7,
+    DFX_QUERY_TAPE_ROW_FLOATS = 8     /* floats per (substep, environment) tape row */
 };
 
 /* Build the device-resident pack for CUDA device `device` (>= 0).  Returns NULL on failure and
@@ -113,7 +114,8 @@ int dfx_pack_query(const dfx_pack_t* pack, int what);
 int dfx_pack_set_gravity(dfx_pack_t* pack, float gx, float gy, float gz, int ground);
 
 /* Number of floats of tape one forward call writes for `num_envs` environments:
- *   substeps * N * (Q + D)                      the (q, qd) entering every substep
+ *   substeps * N * (Q + 8 D + 32 L)             per substep: the (q, qd) entering it + the forward
+ *                                               intermediates the adjoint reads back instead of recomputing
  * + ceil(substeps / mm_freq) * N * D * D        H^-1 of every mass-matrix update           */
 long long dfx_tape_floats(const dfx_pack_t* pack, int num_envs, int substeps, int mm_freq);
 
@@ -137,6 +139,32 @@ int dfx_step_backward(const dfx_pack_t* pack, int num_envs, int substeps, int mm
                       const float* act, const float* musc, const float* tape,
                       const float* gq_out, const float* gqd_out,
                       float* gq, float* gqd, float* gact, float* gmusc, void* stream);
+
+/* ---- fused env epilogue: observation + reward + termination flags of the free-root
+ * walker envs and its adjoint, replacing ~35 PyTorch ops per env.step (reference envs/ant.py:266-307,
+ * envs/humanoid.py:314-368, envs/snu_humanoid.py:378-432).  One thread per environment. */
+typedef struct DfxWalkerParams {
+    int num_q, num_qd, num_act, num_obs;
+    int obs_has_actions;        /* Ant, Humanoid: observation ends with the actions; SNU: no */
+    int height_mode;            /* 0: h - termination_height (Ant); 1: clipped quadratic (Humanoid); 2: none (SNU) */
+    int action_penalty_abs;     /* 0: sum a^2 ; 1: sum |a| (SNU) */
+    int early_termination;      /* reset when h < termination_height */
+    int check_invalid;          /* reset on NaN / Inf / |x| > 1e6 (Humanoid, SNU) */
+    int zero_reward_on_invalid; /* SNU */
+    int episode_length;
+    float joint_vel_scale, termination_height, termination_tolerance, height_rew_scale, action_penalty;
+    float target[3];            /* targets + start_pos */
+    float inv_start_rot[4];
+    float basis_heading[3], basis_up[3];
+} DfxWalkerParams;
+
+/* q [n*num_q], qd [n*num_qd], actions [n*num_act], progress [n] (int64) -> obs [n*num_obs], and when rew != NULL
+ * rew [n], reset [n] (int64, 0/1). */
+int dfx_walker_obs_forward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                           const long long* progress, float* obs, float* rew, long long* reset, void* stream);
+/* cotangents g_obs [n*num_obs] (NULL == 0), g_rew [n] (NULL == 0) -> gq, gqd (overwritten), gact (NULL: skip). */
+int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                            const float* g_obs, const float* g_rew, float* gq, float* gqd, float* gact, void* stream);
 
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);

@@ -41,6 +41,7 @@ int emu_pack_query(const EmuPack* p, int what) {
         case DFX_QUERY_MUSCLES: return p->pack.M;
         case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
         case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
+        case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
         case DFX_QUERY_TREE_DEPTH: return p->pack.nlev;
     }
     return -1;
@@ -51,7 +52,7 @@ int emu_pack_set_gravity(EmuPack* p, float gx, float gy, float gz, int ground) {
     return 0;
 }
 long long emu_tape_floats(const EmuPack* p, int n, int substeps, int mm_freq) {
-    return tape_geom(p->pack.Q, p->pack.D, n, substeps, mm_freq).total;
+    return tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).total;
 }
 
 int emu_step_forward(const EmuPack* p, int n, int substeps, int mm_freq, double dt,
@@ -63,7 +64,7 @@ int emu_step_forward(const EmuPack* p, int n, int substeps, int mm_freq, double 
     a.dt_sub = (float)(dt / (double)substeps);
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
-    a.hinv_base = tape_geom(p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
     std::vector<float> scratch(p->host.layout.bwd_size + 16, 0.0f);
     GroupSerial g{0};
     for (int env = 0; env < n; ++env) env_step_forward(p->pack, p->host.layout, scratch.data(), g, env, a);
@@ -80,7 +81,7 @@ int emu_step_backward(const EmuPack* p, int n, int substeps, int mm_freq, double
     a.dt_sub = (float)(dt / (double)substeps);
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
-    a.hinv_base = tape_geom(p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
     std::vector<float> scratch(p->host.layout.bwd_size + 16, 0.0f);
     GroupSerial g{0};
     for (int env = 0; env < n; ++env) env_step_backward(p->pack, p->host.layout, scratch.data(), g, env, a);

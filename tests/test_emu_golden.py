@@ -27,14 +27,14 @@ def test_forward_and_adjoint_match_reference(name):
         assert rel(q, d[p + "traj_q"][-1]) < fwd_rtol(name), (name, k)
         assert rel(qd, d[p + "traj_qd"][-1]) < fwd_rtol(name), (name, k)
         # the tape holds the state entering every substep == the reference's per-substep trajectory
-        QD = sim.desc.Q + sim.desc.D
+        QD = sim.lib.emu_pack_query(sim.pack, 8)      # DFX_QUERY_TAPE_ROW_FLOATS; a row starts with (q, qd)
         t = tape[: S * N * QD].reshape(S, N, QD)
         # (velocities right after a start from rest are ~0, and the fp32 solve of H q'' = tau is only
         #  good to cond(H) * eps ~ 1e-5 relative in the reference too -- hence the absolute floor)
         for s in (1, S // 2, S - 1):
             assert rel(t[s, :, : sim.desc.Q], d[p + "traj_q"][s - 1]) < fwd_rtol(name)
             ref_qd = d[p + "traj_qd"][s - 1]
-            assert np.abs(t[s, :, sim.desc.Q:].ravel() - ref_qd).max() < fwd_rtol(name) * (1.0 + np.abs(ref_qd).max())
+            assert np.abs(t[s, :, sim.desc.Q:sim.desc.Q + sim.desc.D].ravel() - ref_qd).max() < fwd_rtol(name) * (1.0 + np.abs(ref_qd).max())
         gq, gqd, gact, gm = sim.backward(d[p + "act"], musc, tape, d[p + "gq_out"], d[p + "gqd_out"], S, mm, dt)
         assert rel(gq, d[p + "grad_q"]) < GRAD_RTOL, (name, k)
         assert rel(gqd, d[p + "grad_qd"]) < GRAD_RTOL, (name, k)

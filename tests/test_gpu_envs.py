@@ -74,3 +74,52 @@ def test_derived_state_fields_on_demand():
     env.step(torch.zeros(2, 8, device="cuda:0"))
     X = env.state.body_X_sc
     assert X.shape == (18, 7) and torch.isfinite(X).all()
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv"])
+def test_fused_epilogue_equals_torch_ops(name):
+    """The fused obs/reward/reset kernel and its adjoint against the plain PyTorch formulation."""
+    import torch
+    import diffrl_b200.envs as envs
+    n = 64
+    outs = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name])
+        env.fused_epilogue = fused
+        env.sync_free_reset = fused
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        g = torch.Generator(device="cuda:0").manual_seed(3)
+        acts = [(torch.rand((n, env.num_actions), generator=g, device="cuda:0") * 2 - 1).requires_grad_() for _ in range(4)]
+        loss, obs_l, rew_l = 0.0, [], []
+        w = torch.linspace(0.5, 1.5, env.num_obs, device="cuda:0")
+        for a in acts:
+            obs, rew, done, _ = env.step(a)
+            loss = loss + rew.sum() + (obs * w).sum() * 1e-2
+            obs_l.append(obs.detach()); rew_l.append(rew.detach())
+        loss.backward()
+        outs.append((torch.stack(obs_l), torch.stack(rew_l), torch.stack([a.grad for a in acts])))
+    (o1, r1, g1), (o2, r2, g2) = outs
+    assert torch.allclose(o1, o2, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(r1, r2, rtol=1e-5, atol=1e-4)
+    assert (g1 - g2).abs().max() <= 1e-4 * g2.abs().max() + 1e-6
+
+
+def test_masked_reset_equals_indexed_reset():
+    import torch
+    import diffrl_b200.envs as envs
+    n = 32
+    res = []
+    for masked in (True, False):
+        env = envs.AntEnv(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=16, episode_length=3)
+        env.sync_free_reset = masked
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        g = torch.Generator(device="cuda:0").manual_seed(5)
+        traj = []
+        for t in range(5):     # episode_length 3 forces resets at t = 2
+            obs, rew, done, _ = env.step(torch.rand((n, 8), generator=g, device="cuda:0") * 2 - 1)
+            traj.append((obs.detach().clone(), done.clone(), env.progress_buf.clone(), env.state.joint_q.detach().clone()))
+        res.append(traj)
+    for a, b in zip(*res):
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[3], b[3], atol=1e-6)

@@ -89,8 +89,9 @@ def test_full_size_properties_ant_4096():
     qp, qdp, _, _ = eng.forward(t(q0[perm]), t(qd0[perm]), t(act[perm]), None, c["S"], c["mm"], c["dt"], want_tape=False)
     Q, D = o.desc.Q, o.desc.D
     assert torch.equal(qp.view(N, Q), q.view(N, Q)[torch.tensor(perm, device="cuda:0")])       # envs are independent
-    first = tape[: N * (Q + D)].view(N, Q + D)
-    assert torch.equal(first[:, :Q].reshape(-1), t(q0)) and torch.equal(first[:, Q:].reshape(-1), t(qd0))
+    row = eng.lib.dfx_pack_query(eng.pack, 8)   # DFX_QUERY_TAPE_ROW_FLOATS
+    first = tape[: N * row].view(N, row)
+    assert torch.equal(first[:, :Q].reshape(-1), t(q0)) and torch.equal(first[:, Q:Q + D].reshape(-1), t(qd0))
     # one 16-substep call with the mass matrix refreshed every 8 == two chained 8-substep calls
     qa, qda, _, _ = eng.forward(t(q0), t(qd0), t(act), None, 16, 8, c["dt"], want_tape=False)
     qb, qdb, _, _ = eng.forward(t(q0), t(qd0), t(act), None, 8, 8, c["dt"] / 2, want_tape=False)
