@@ -26,7 +26,18 @@ struct GroupCuda {
     int lane;
     unsigned mask;
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    bool psync;
+    __device__ __forceinline__ void phase_sync() const { if (psync) __syncthreads(); }
     __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
+    // cp.async (LDGSTS) 16-byte copies, one commit group per row
+    __device__ __forceinline__ void copy_row_async(float* dst, const float* src, int n) const {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        for (int i = lane * 4; i < n; i += G_ * 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ void copy_wait_but_one() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 };
 
 constexpr int kMaxThreads = 128;
@@ -81,11 +92,14 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
 
     const int kEnvsPerCta = blockDim.x / G;
     const int local = threadIdx.x / G;
-    const int env = blockIdx.x * kEnvsPerCta + local;
-    if (env >= ka.step.N) return;
+    // groups past the end redo the last environment (identical values are stored twice) so that every
+    // thread of the CTA reaches the CTA-wide phase barriers
+    int env = blockIdx.x * kEnvsPerCta + local;
+    if (env >= ka.step.N) env = ka.step.N - 1;
     const int lane_in_warp = threadIdx.x & 31;
     GroupCuda<G> g;
     g.lane = threadIdx.x % G;
+    g.psync = (ka.step.flags & 2) != 0;
     g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_in_warp / G) * G));
     float* s = smem + ka.pack_smem_floats + (size_t)local * ka.scratch_stride;
     if (BACKWARD) env_step_backward(P, ka.layout, s, g, env, ka.step);
@@ -111,6 +125,7 @@ struct dfx_pack {
 static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
+static int g_flags = 3;
 
 static void set_err(char* err, int n, const std::string& m) {
     if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
@@ -120,6 +135,7 @@ extern "C" {
 
 const char* dfx_version(void) { return "diffrl_b200 dfx 0.1 (sm_100a)"; }
 long long dfx_launch_count(void) { return g_launches.load(); }
+int dfx_set_flags(int flags) { g_flags = flags; return 0; }
 int dfx_set_group_size(int lanes) {
     if (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32) return 1;
     g_group = lanes;
@@ -188,18 +204,27 @@ static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t 
     ka.layout = p->host.layout;
     ka.step = step;
     const int per_env = BWD ? p->host.layout.bwd_size : p->host.layout.fwd_size;
-    ka.scratch_stride = (per_env + 1) | 1;   // odd stride: spreads the groups of a warp over banks
+    // multiple of 4 floats (16-byte cp.async rows) that is not a multiple of 32 (bank spreading between groups)
+    ka.scratch_stride = (per_env + 3) & ~3;
+    if (ka.scratch_stride % 32 == 0) ka.scratch_stride += 4;
     const int pack_bytes = (((p->blob.n_floats + 3) & ~3) + ((p->blob.n_ints + 3) & ~3)) * 4;
     ka.pack_smem_floats = pack_bytes / 4;
-    // environments per CTA: as many as fit 128 threads and ~100 KB of shared memory (>= 2 CTAs/SM),
-    // but never less than one warp's worth of groups
-    int envs_per_cta = kMaxThreads / G;
-    const int min_envs = 32 / G > 0 ? 32 / G : 1;
-    while (envs_per_cta > min_envs &&
-           (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float) > 100 * 1024)
-        envs_per_cta /= 2;
+    // environments per CTA: the candidate (128, 64 or 32 threads) that keeps the most environments resident
+    // per SM under the shared-memory (227 KB) and register (64 K) budgets; ties go to the larger CTA
+    const int regs_per_thread = BWD ? 128 : 96;
+    int envs_per_cta = 0, best = -1;
+    for (int threads = kMaxThreads; threads >= 32 && threads >= G; threads /= 2) {
+        const int e = threads / G;
+        const size_t bytes = (size_t)pack_bytes + (size_t)e * ka.scratch_stride * sizeof(float) + 1024;
+        if (bytes > 227 * 1024) continue;
+        int ctas = (int)((227 * 1024) / bytes);
+        const int by_regs = 65536 / (regs_per_thread * threads);
+        if (by_regs < ctas) ctas = by_regs;
+        if (ctas > 32) ctas = 32;
+        if (ctas * e > best) { best = ctas * e; envs_per_cta = e; }
+    }
+    if (envs_per_cta == 0) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float);
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = dfx_step_kernel<G, BWD>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -233,6 +258,7 @@ int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, doub
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
     a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    a.flags = g_flags;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_group(p)) {
         case 8: return (int)launch<8, false>(p, a, st);
@@ -254,6 +280,7 @@ int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, dou
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
     a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    a.flags = g_flags;
     cudaStream_t st = (cudaStream_t)stream;
     switch (pick_group(p)) {
         case 8: return (int)launch<8, true>(p, a, st);

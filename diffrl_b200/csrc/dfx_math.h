@@ -170,6 +170,8 @@ DFX_HD void xf_mul_adj_a(Xf a, Xf b, Xf r, Xf& aa) {
     aa.q += qrot_adj_q(a.q, b.p, r.p);
     aa.q += qmul_adj_a(b.q, r.q);
 }
+// adjoint w.r.t. the second factor only
+DFX_HD Xf xf_mul_adj_b(Xf a, Xf r) { return Xf{qrot_inv(a.q, r.p), qmul_adj_b(a.q, r.q)}; }
 DFX_HD Xf& operator+=(Xf& a, Xf b) {
     a.p += b.p;
     a.q += b.q;

@@ -68,9 +68,9 @@ struct Pack {
 // backward kernels additionally [fwd_size, bwd_size).
 struct Layout {
     // primal
-    int q, qd, act, musc, tau, qdd;
+    int q, qd, act, musc, tau, qdd, Xl, vj;
     int Xsc, Xsm, S, v, a, f, ft;
-    int cw;    // contact wrenches (C,6) forward; (C,13) adjoint staging in backward
+    int cw;    // contact wrenches (C,6), forward only
     int A;     // H, then H^-1 (D,D)
     int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
     int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
@@ -84,6 +84,17 @@ struct Layout {
 
 inline int dfx_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// the same layout with the taped block [q .. qdd] relocated by `shift` floats (double buffering)
+inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+Layout shifted_tape_block(Layout y, int shift) {
+    y.q += shift; y.qd += shift; y.Xsc += shift; y.Xsm += shift; y.S += shift; y.v += shift; y.a += shift;
+    y.ft += shift; y.qdd += shift;
+    return y;
+}
+
 inline Layout make_layout(int L, int D, int Q, int C, int M) {
     Layout y;
     int o = 0;
@@ -93,15 +104,18 @@ inline Layout make_layout(int L, int D, int Q, int C, int M) {
     y.q = take(Q); y.qd = take(D);
     y.Xsc = take(L * 7); y.Xsm = take(L * 7); y.S = take(D * 6); y.v = take(L * 6); y.a = take(L * 6);
     y.ft = take(L * 6); y.qdd = take(D);
+    o = dfx_round_up(o, 4);          // rows are copied with 16-byte transactions
     y.tape_row = o;
-    y.act = take(D); y.musc = take(M); y.tau = take(D); y.f = take(L * 6);
+    y.act = take(D); y.musc = take(M); y.tau = take(D);
+    y.Xl = take(L * 7); y.vj = take(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
     y.A = take(D * D); y.Lm = take(D * D);
+    // ---- from here on the forward-only and the adjoint-only fields share the same region
+    const int shared_end = o;
     y.Icmp = take(L * 21 + D * 6);
-    // the contact staging buffer aliases nothing in forward; in backward it needs 13 floats/contact
-    y.cw = take(C * 6);
+    y.f = take(L * 6);
+    y.cw = take(C * 6);              // contact wrenches staged for the deterministic per-body gather
     y.fwd_size = o;
-    // backward: widen the contact buffer in place (it is the last forward field)
-    o = y.cw + C * 13;
+    o = shared_end;
     y.aq = take(Q); y.aqd = take(D); y.aqdd = take(D); y.aact = take(D); y.amusc = take(M);
     y.aXsc = take(L * 7); y.aXsm = take(L * 7); y.aS = take(D * 6); y.av = take(L * 6); y.aa = take(L * 6);
     y.af = take(L * 6); y.aIbar = take(L * 12); y.pX = take(L * 7);

@@ -30,7 +30,12 @@ struct GroupSerial {  // host / single-lane execution
     static constexpr int G = 1;
     int lane;
     DFX_HD void sync() const {}
+    DFX_HD void phase_sync() const {}
     DFX_HD void atomic_add(float* p, float v) const { *p += v; }
+    // asynchronous global -> scratch row copy (16-byte aligned, n a multiple of 4 floats)
+    DFX_HD void copy_row_async(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
+    DFX_HD void copy_wait_all() const {}
+    DFX_HD void copy_wait_but_one() const {}
 };
 
 #define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
@@ -41,37 +46,55 @@ DFX_HD void zero_range(float* p, int n, const Grp& g) {
 }
 
 // =====================================================================================
-// kinematics: transforms, motion subspace, velocity and bias acceleration, root -> leaves
+// kinematics: transforms, motion subspace, velocity and bias acceleration.
+// Organised as PARALLEL per-link passes plus THIN tree recursions, so that the level-serial part of
+// the work is one transform product / a few vector adds per level instead of the whole per-link body:
+//   K1 (parallel)   X_l = X_pj X_jc(q)                                  joint-local transform
+//   K2 (root->leaf) X_sc = X_sc[parent] X_l
+//   K3 (parallel)   X_sm = X_sc X_cm ; X_sj = X_sc[parent] X_pj ; S ; v_j = S qd
+//   K4 (root->leaf) v = v[parent] + v_j ; a = a[parent] + v x v_j
+// Scratch: Y.Xl (L,7) and Y.vj (L,6).
 // =====================================================================================
-DFX_HD void kin_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
-    const int par = P.parent[i], type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
-    Xf Xp = xf_ident();
-    SV vp = sv_zero(), ap = sv_zero();
-    if (par >= 0) {
-        Xp = ld7(s + Y.Xsc + par * 7);
-        vp = ld6(s + Y.v + par * 6);
-        ap = ld6(s + Y.a + par * 6);
-    }
+DFX_HD Xf joint_transform(const Pack& P, const float* q, int i) {
+    const int type = P.type[i], qs = P.q_start[i];
+    Xf Xjc = xf_ident();
+    if (type == JOINT_PRISMATIC) Xjc.p = ld3(P.axis + i * 3) * q[qs];
+    else if (type == JOINT_REVOLUTE) Xjc.q = q_from_axis_angle(ld3(P.axis + i * 3), q[qs]);
+    else if (type == JOINT_BALL) Xjc.q = ld4(q + qs);
+    else if (type == JOINT_FREE) { Xjc.p = ld3(q + qs); Xjc.q = ld4(q + qs + 3); }
+    return Xjc;
+}
+
+DFX_HD void kin_local_fwd(const Pack& P, const Layout& Y, float* s, int i) {   // K1
+    st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
+}
+
+DFX_HD void kin_chain_fwd(const Pack& P, const Layout& Y, float* s, int i) {   // K2
+    const int par = P.parent[i];
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
+    // derivative along |q| (q is not assumed unit) agrees
+    st7(s + Y.Xsc + i * 7, xf_mul(Xp, ld7(s + Y.Xl + i * 7)));
+}
+
+DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, float* s, int i) {  // K3
+    const int par = P.parent[i], type = P.type[i], ds = P.qd_start[i];
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     const Xf Xsj = xf_mul(Xp, ld7(P.X_pj + i * 7));
     const V3 axis = ld3(P.axis + i * 3);
-    const float* q = s + Y.q;
     const float* qd = s + Y.qd;
     float* S = s + Y.S;
-    Xf Xjc = xf_ident();
     SV vj = sv_zero();
     if (type == JOINT_PRISMATIC) {
-        Xjc.p = axis * q[qs];
         SV Sk = SV{v3zero(), qrot(Xsj.q, axis)};
         st6(S + ds * 6, Sk);
         vj = Sk * qd[ds];
     } else if (type == JOINT_REVOLUTE) {
-        Xjc.q = q_from_axis_angle(axis, q[qs]);
         V3 w = qrot(Xsj.q, axis);
         SV Sk = SV{w, cross(Xsj.p, w)};
         st6(S + ds * 6, Sk);
         vj = Sk * qd[ds];
     } else if (type == JOINT_BALL) {
-        Xjc.q = ld4(q + qs);
         for (int k = 0; k < 3; ++k) {
             V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
             V3 w = qrot(Xsj.q, e);
@@ -80,133 +103,158 @@ DFX_HD void kin_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
             vj = (k == 0) ? Sk * qd[ds] : vj + Sk * qd[ds + k];
         }
     } else if (type == JOINT_FREE) {
-        Xjc.p = ld3(q + qs);
-        Xjc.q = ld4(q + qs + 3);
         for (int k = 0; k < 6; ++k)
             for (int c = 0; c < 6; ++c) S[(ds + k) * 6 + c] = (k == c) ? 1.0f : 0.0f;
         vj = ld6(qd + ds);
     }
-    // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
-    // derivative along |q| (q is not assumed unit) agrees
-    const Xf Xsc = xf_mul(Xp, xf_mul(ld7(P.X_pj + i * 7), Xjc));
-    const Xf Xsm = xf_mul(Xsc, ld7(P.X_cm + i * 7));
+    st6(s + Y.vj + i * 6, vj);
+    st7(s + Y.Xsm + i * 7, xf_mul(ld7(s + Y.Xsc + i * 7), ld7(P.X_cm + i * 7)));
+}
+
+DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, float* s, int i) {  // K4
+    const int par = P.parent[i];
+    SV vp = sv_zero(), ap = sv_zero();
+    if (par >= 0) { vp = ld6(s + Y.v + par * 6); ap = ld6(s + Y.a + par * 6); }
+    const SV vj = ld6(s + Y.vj + i * 6);
     const SV v = vp + vj;
-    const SV a = ap + sv_cross(v, vj);
-    st7(s + Y.Xsc + i * 7, Xsc);
-    st7(s + Y.Xsm + i * 7, Xsm);
     st6(s + Y.v + i * 6, v);
-    st6(s + Y.a + i * 6, a);
+    st6(s + Y.a + i * 6, ap + sv_cross(v, vj));
 }
 
 template <class Grp>
 DFX_HD void kin_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
+    g.sync();
     for (int lev = 0; lev < P.nlev; ++lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) kin_link_fwd(P, Y, s, P.level_links[k]);
+        for (int k = b + g.lane; k < e; k += Grp::G) kin_chain_fwd(P, Y, s, P.level_links[k]);
+        g.sync();
+    }
+    DFX_FOR(i, P.L) kin_motion_fwd(P, Y, s, i);
+    g.sync();
+    for (int lev = 0; lev < P.nlev; ++lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int k = b + g.lane; k < e; k += Grp::G) kin_velocity_fwd(P, Y, s, P.level_links[k]);
         g.sync();
     }
 }
 
-// Adjoint of kin_link_fwd.  On entry aXsc[i], aXsm[i], aS[dofs of i], av[i], aa[i] hold the adjoints
-// from everything downstream EXCEPT the children's kinematics, which are gathered here from the
-// children's slots (av[c], aa[c] = totals pushed to the parent, pX[c] = adjoint of the parent
-// transform).  Leaves first.
-DFX_HD void kin_link_adj(const Pack& P, const Layout& Y, float* s, int i) {
-    const int par = P.parent[i], type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
-    Xf aXsc = ld7(s + Y.aXsc + i * 7);
-    SV av = ld6(s + Y.av + i * 6);
-    SV aa = ld6(s + Y.aa + i * 6);
+// ---- adjoint.  On entry aXsc[i], aXsm[i], aS[dofs of i], av[i], aa[i] hold the cotangents from everything
+// downstream of the kinematics.  Passes (leaves -> root recursions are thin):
+//   A1 (parallel)   aXsc += adj(X_sm = X_sc X_cm) ; recompute X_l, v_j
+//   A2 (leaf->root) av, aa totals (children gathered), adjoint of a = a_p + v x v_j  -> avj (in the vj slot)
+//   A3 (parallel)   adjoint of v_j = S qd and of S(X_sj): aS, aqd, aX_sj (kept in the pX slot)
+//   A4 (leaf->root) aXsc totals (children's pushes gathered); push of this link to its parent -> pX
+//   A5 (parallel)   adjoint of X_l = X_pj X_jc(q) -> aq
+DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, float* s, int i) {    // A1
+    float* aX = s + Y.aXsc + i * 7;
+    Xf acc = ld7(aX);
+    xf_mul_adj_a(ld7(s + Y.Xsc + i * 7), ld7(P.X_cm + i * 7), ld7(s + Y.aXsm + i * 7), acc);
+    st7(aX, acc);
+    st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
+    const int type = P.type[i], ds = P.qd_start[i];
+    const float* qd = s + Y.qd;
+    const float* S = s + Y.S;
+    SV vj = sv_zero();
+    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) vj = ld6(S + ds * 6) * qd[ds];
+    else if (type == JOINT_BALL) { for (int k = 0; k < 3; ++k) vj += ld6(S + (ds + k) * 6) * qd[ds + k]; }
+    else if (type == JOINT_FREE) vj = ld6(qd + ds);
+    st6(s + Y.vj + i * 6, vj);
+}
+
+DFX_HD void kin_adj_velocity(const Pack& P, const Layout& Y, float* s, int i) {  // A2
+    SV av = ld6(s + Y.av + i * 6), aa = ld6(s + Y.aa + i * 6);
     for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) {
         const int c = P.child_idx[k];
-        aXsc += ld7(s + Y.pX + c * 7);
         av += ld6(s + Y.av + c * 6);
         aa += ld6(s + Y.aa + c * 6);
     }
-    // ---- recompute the primal pieces
-    Xf Xp = xf_ident();
-    if (par >= 0) Xp = ld7(s + Y.Xsc + par * 7);
-    const Xf Xpj = ld7(P.X_pj + i * 7);
-    const Xf Xsj = xf_mul(Xp, Xpj);
+    SV avj = sv_zero();
+    sv_cross_adj(ld6(s + Y.v + i * 6), ld6(s + Y.vj + i * 6), aa, av, avj);   // a = a_p + v x v_j
+    avj += av;                                                                // v = v_p + v_j
+    st6(s + Y.av + i * 6, av);   // == cotangent pushed to v[parent]
+    st6(s + Y.aa + i * 6, aa);
+    st6(s + Y.vj + i * 6, avj);
+}
+
+DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, float* s, int i) {    // A3
+    const int par = P.parent[i], type = P.type[i], ds = P.qd_start[i];
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    const Xf Xsj = xf_mul(Xp, ld7(P.X_pj + i * 7));
     const V3 axis = ld3(P.axis + i * 3);
-    const float* q = s + Y.q;
+    const SV avj = ld6(s + Y.vj + i * 6);
     const float* qd = s + Y.qd;
     const float* S = s + Y.S;
-    float* aq = s + Y.aq;
-    float* aqd = s + Y.aqd;
     const float* aS = s + Y.aS;
-    Xf Xjc = xf_ident();
-    SV vj = sv_zero();
+    float* aqd = s + Y.aqd;
+    Xf aXsj = xf_zero();
     if (type == JOINT_PRISMATIC) {
-        Xjc.p = axis * q[qs];
-        vj = ld6(S + ds * 6) * qd[ds];
-    } else if (type == JOINT_REVOLUTE) {
-        Xjc.q = q_from_axis_angle(axis, q[qs]);
-        vj = ld6(S + ds * 6) * qd[ds];
-    } else if (type == JOINT_BALL) {
-        Xjc.q = ld4(q + qs);
-        for (int k = 0; k < 3; ++k) vj += ld6(S + (ds + k) * 6) * qd[ds + k];
-    } else if (type == JOINT_FREE) {
-        Xjc.p = ld3(q + qs);
-        Xjc.q = ld4(q + qs + 3);
-        vj = ld6(qd + ds);
-    }
-    const Xf Xsc = ld7(s + Y.Xsc + i * 7);
-    const SV v = ld6(s + Y.v + i * 6);
-    // ---- reverse
-    // a = ap + v x vj
-    SV avj = sv_zero();
-    sv_cross_adj(v, vj, aa, av, avj);
-    // v = vp + vj
-    avj += av;
-    // Xsm = Xsc * Xcm
-    xf_mul_adj_a(Xsc, ld7(P.X_cm + i * 7), ld7(s + Y.aXsm + i * 7), aXsc);
-    // Xsc = Xp * (Xpj * Xjc)
-    Xf aXsj = xf_zero(), aXjc = xf_zero(), aXp = xf_zero(), aXpjc = xf_zero();
-    xf_mul_adj(Xp, xf_mul(Xpj, Xjc), aXsc, aXp, aXpjc);
-    {
-        Xf unused = xf_zero();
-        xf_mul_adj(Xpj, Xjc, aXpjc, unused, aXjc);
-    }
-    if (type == JOINT_PRISMATIC) {
-        SV Sk = ld6(S + ds * 6);
-        SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
-        aqd[ds] += sv_dot(Sk, avj);
+        const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
+        aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
         aXsj.q += qrot_adj_q(Xsj.q, axis, aSk.v);   // S.v = R axis
-        aq[qs] += dot(axis, aXjc.p);
     } else if (type == JOINT_REVOLUTE) {
-        SV Sk = ld6(S + ds * 6);
-        SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
-        aqd[ds] += sv_dot(Sk, avj);
+        const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
+        aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
         xf_twist_adj_t(Xsj, SV{axis, v3zero()}, aSk, aXsj);
-        aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
     } else if (type == JOINT_BALL) {
         for (int k = 0; k < 3; ++k) {
-            SV Sk = ld6(S + (ds + k) * 6);
-            SV aSk = ld6(aS + (ds + k) * 6) + avj * qd[ds + k];
-            aqd[ds + k] += sv_dot(Sk, avj);
+            const SV aSk = ld6(aS + (ds + k) * 6) + avj * qd[ds + k];
+            aqd[ds + k] += sv_dot(ld6(S + (ds + k) * 6), avj);
             V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
             xf_twist_adj_t(Xsj, SV{e, v3zero()}, aSk, aXsj);
         }
-        add4(aq + qs, aXjc.q);
     } else if (type == JOINT_FREE) {
         add6(aqd + ds, avj);
-        add3(aq + qs, aXjc.p);
-        add4(aq + qs + 3, aXjc.q);
     }
-    // Xsj = Xp * Xpj ; push to the parent through this link's slots
-    xf_mul_adj_a(Xp, Xpj, aXsj, aXp);
+    st7(s + Y.pX + i * 7, aXsj);
+}
+
+DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, float* s, int i) {     // A4
+    const int par = P.parent[i];
+    Xf aXsc = ld7(s + Y.aXsc + i * 7);
+    for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) aXsc += ld7(s + Y.pX + P.child_idx[k] * 7);
+    st7(s + Y.aXsc + i * 7, aXsc);                       // total, consumed by A5
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    Xf aXp = xf_zero();
+    xf_mul_adj_a(Xp, ld7(s + Y.Xl + i * 7), aXsc, aXp);                   // X_sc = X_p X_l
+    xf_mul_adj_a(Xp, ld7(P.X_pj + i * 7), ld7(s + Y.pX + i * 7), aXp);    // X_sj = X_p X_pj
     st7(s + Y.pX + i * 7, aXp);
-    st6(s + Y.av + i * 6, av);   // == adjoint of v[parent] contributed by this subtree
-    st6(s + Y.aa + i * 6, aa);
+}
+
+DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, float* s, int i) {     // A5
+    const int par = P.parent[i], type = P.type[i], qs = P.q_start[i];
+    if (type == JOINT_FIXED) return;
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    const Xf Xpj = ld7(P.X_pj + i * 7);
+    const float* q = s + Y.q;
+    float* aq = s + Y.aq;
+    const Xf aXl = xf_mul_adj_b(Xp, ld7(s + Y.aXsc + i * 7));   // X_sc = X_p X_l
+    const Xf aXjc = xf_mul_adj_b(Xpj, aXl);                      // X_l = X_pj X_jc
+    const V3 axis = ld3(P.axis + i * 3);
+    if (type == JOINT_PRISMATIC) aq[qs] += dot(axis, aXjc.p);
+    else if (type == JOINT_REVOLUTE) aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
+    else if (type == JOINT_BALL) add4(aq + qs, aXjc.q);
+    else if (type == JOINT_FREE) { add3(aq + qs, aXjc.p); add4(aq + qs + 3, aXjc.q); }
 }
 
 template <class Grp>
 DFX_HD void kin_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    DFX_FOR(i, P.L) kin_adj_local(P, Y, s, i);
+    g.sync();
     for (int lev = P.nlev - 1; lev >= 0; --lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) kin_link_adj(P, Y, s, P.level_links[k]);
+        for (int k = b + g.lane; k < e; k += Grp::G) kin_adj_velocity(P, Y, s, P.level_links[k]);
         g.sync();
     }
+    DFX_FOR(i, P.L) kin_adj_motion(P, Y, s, i);
+    g.sync();
+    for (int lev = P.nlev - 1; lev >= 0; --lev) {
+        const int b = P.level_start[lev], e = P.level_start[lev + 1];
+        for (int k = b + g.lane; k < e; k += Grp::G) kin_adj_chain(P, Y, s, P.level_links[k]);
+        g.sync();
+    }
+    DFX_FOR(i, P.L) kin_adj_joint(P, Y, s, i);
+    g.sync();
 }
 
 // =====================================================================================
@@ -358,22 +406,21 @@ DFX_HD void contact_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) 
     g.sync();
 }
 
-// adjoint for one contact: cotangent r = af[body]; writes 13 floats (aXsc 7, av 6) to the staging row
-DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k) {
+// adjoint for one contact: cotangent r = af[body]; accumulates into aXsc[body], av[body] with shared-memory
+// atomics (only penetrating contacts do any work; the summation order, hence the last bits of the
+// GRADIENT, may vary between runs -- the forward pass stays deterministic)
+template <class Grp>
+DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, const Grp& g) {
     const int b = P.cbody[k];
     const Xf X = ld7(s + Y.Xsc + b * 7);
     const SV vs = ld6(s + Y.v + b * 6);
-    const float ke = P.cmat[k * 4 + 0], kd = P.cmat[k * 4 + 1], kf = P.cmat[k * 4 + 2], mu = P.cmat[k * 4 + 3];
     const V3 pt = ld3(P.cpoint + k * 3);
     V3 p = xf_point(X, pt);
     p.y -= P.cdist[k];
-    const V3 dpdt = vs.v + cross(vs.w, p);
     const float c = p.y;
-    float* out = s + Y.cw + k * 13;
-    if (c >= 0.0f) {
-        for (int j = 0; j < 13; ++j) out[j] = 0.0f;
-        return;
-    }
+    if (c >= 0.0f) return;
+    const float ke = P.cmat[k * 4 + 0], kd = P.cmat[k * 4 + 1], kf = P.cmat[k * 4 + 2], mu = P.cmat[k * 4 + 3];
+    const V3 dpdt = vs.v + cross(vs.w, p);
     const SV r = ld6(s + Y.af + b * 6);
     const float vn = dpdt.y;
     const V3 vt = V3{dpdt.x, 0.0f, dpdt.z};
@@ -413,28 +460,22 @@ DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k) {
     adpdt.y += avn;
     ap.y += ac;
     // dpdt = v + w x p
-    SV avs = sv_zero();
-    avs.v += adpdt;
-    cross_adj(vs.w, p, adpdt, avs.w, ap);
+    V3 aw = v3zero();
+    cross_adj(vs.w, p, adpdt, aw, ap);
     // p = X.p + R(X.q) pt - n d
-    Xf aX;
-    aX.p = ap;
-    aX.q = qrot_adj_q(X.q, pt, ap);
-    st7(out, aX);
-    st6(out + 7, avs);
+    const Q4 aq = qrot_adj_q(X.q, pt, ap);
+    float* ax = s + Y.aXsc + b * 7;
+    float* avp = s + Y.av + b * 6;
+    g.atomic_add(ax + 0, ap.x); g.atomic_add(ax + 1, ap.y); g.atomic_add(ax + 2, ap.z);
+    g.atomic_add(ax + 3, aq.x); g.atomic_add(ax + 4, aq.y); g.atomic_add(ax + 5, aq.z); g.atomic_add(ax + 6, aq.w);
+    g.atomic_add(avp + 0, aw.x); g.atomic_add(avp + 1, aw.y); g.atomic_add(avp + 2, aw.z);
+    g.atomic_add(avp + 3, adpdt.x); g.atomic_add(avp + 4, adpdt.y); g.atomic_add(avp + 5, adpdt.z);
 }
 
 template <class Grp>
 DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     if (!P.ground) return;
-    DFX_FOR(k, P.C) contact_point_adj(P, Y, s, k);
-    g.sync();
-    DFX_FOR(it, P.L * 13) {
-        const int i = it / 13, c = it - i * 13;
-        float acc = 0.0f;
-        for (int k = P.cbody_start[i]; k < P.cbody_start[i + 1]; ++k) acc += s[Y.cw + k * 13 + c];
-        if (c < 7) s[Y.aXsc + i * 7 + c] += acc; else s[Y.av + i * 6 + (c - 7)] += acc;
-    }
+    DFX_FOR(k, P.C) contact_point_adj(P, Y, s, k, g);
     g.sync();
 }
 
@@ -511,12 +552,16 @@ DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 // =====================================================================================
 // joint torques: leaf -> root wrench accumulation and projection on the motion subspace
 // =====================================================================================
-DFX_HD void tau_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
-    const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+// T1 (leaf->root, thin): f_tot[i] = f[i] + sum f_tot[children]   T2 (parallel): project on S, add PD / limits
+DFX_HD void tau_accum_fwd(const Pack& P, const Layout& Y, float* s, int i) {
     SV ft = sv_zero();
     for (int k = P.child_start[i + 1] - 1; k >= P.child_start[i]; --k) ft += ld6(s + Y.ft + P.child_idx[k] * 6);
-    const SV f = ld6(s + Y.f + i * 6) + ft;
-    st6(s + Y.ft + i * 6, f);
+    st6(s + Y.ft + i * 6, ld6(s + Y.f + i * 6) + ft);
+}
+
+DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+    const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
+    const SV f = ld6(s + Y.ft + i * 6);
     const float* q = s + Y.q;
     const float* qd = s + Y.qd;
     const float* S = s + Y.S;
@@ -543,16 +588,18 @@ template <class Grp>
 DFX_HD void tau_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     for (int lev = P.nlev - 1; lev >= 0; --lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) tau_link_fwd(P, Y, s, P.level_links[k]);
+        for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_fwd(P, Y, s, P.level_links[k]);
         g.sync();
     }
+    DFX_FOR(i, P.L) tau_project_fwd(P, Y, s, i);
+    g.sync();
 }
 
-// adjoint, root -> leaves.  `atau` (D) in, af[] becomes the adjoint of body_f_s; aS, aq, aqd, aact accumulate.
-DFX_HD void tau_link_adj(const Pack& P, const Layout& Y, float* s, const float* atau, int i) {
-    const int type = P.type[i], par = P.parent[i], qs = P.q_start[i], ds = P.qd_start[i];
+// adjoint: `atau` (D) in; af[] becomes the adjoint of body_f_s; aS, aq, aqd, aact accumulate.
+// T2' (parallel): per-link contribution to a(f_tot) + aS, aq, aqd, aact ;  T1' (root->leaf, thin): af[i] += af[parent]
+DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, float* s, const float* atau, int i) {
+    const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
     SV af = sv_zero();
-    if (par >= 0) af = ld6(s + Y.af + par * 6);   // f_tot[parent] = f[parent] + sum f_tot[children]
     const SV f = ld6(s + Y.ft + i * 6);
     const float* q = s + Y.q;
     const float* S = s + Y.S;
@@ -585,11 +632,18 @@ DFX_HD void tau_link_adj(const Pack& P, const Layout& Y, float* s, const float* 
     st6(s + Y.af + i * 6, af);
 }
 
+DFX_HD void tau_accum_adj(const Pack& P, const Layout& Y, float* s, int i) {
+    const int par = P.parent[i];
+    if (par >= 0) add6(s + Y.af + i * 6, ld6(s + Y.af + par * 6));   // f_tot[parent] = f[parent] + sum f_tot[children]
+}
+
 template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, float* s, const float* atau, const Grp& g) {
-    for (int lev = 0; lev < P.nlev; ++lev) {
+    DFX_FOR(i, P.L) tau_project_adj(P, Y, s, atau, i);
+    g.sync();
+    for (int lev = 1; lev < P.nlev; ++lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) tau_link_adj(P, Y, s, atau, P.level_links[k]);
+        for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_adj(P, Y, s, P.level_links[k]);
         g.sync();
     }
 }
@@ -902,14 +956,21 @@ DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool
     zero_range(s + Y.aa, P.L * 6, g);
     zero_range(s + Y.aIbar, P.L * 12, g);
     g.sync();
+    // phase_sync(): CTA-wide barrier that keeps the warps of a CTA inside the same phase, so that the
+    // instruction working set per SM is one or two phases (~10 KB each) instead of the whole 140 KB body
     integrate_adj(P, Y, s, dt, g);
     solve_adj(P, Y, s, g);                  // tau slot <- atau
+    g.phase_sync();
     if (apply_crba) crba_adj(P, Y, s, g);
     tau_adj(P, Y, s, s + Y.tau, g);
+    g.phase_sync();
     muscle_adj(P, Y, s, g);
     contact_adj(P, Y, s, g);
+    g.phase_sync();
     body_force_adj(P, Y, s, g);
+    g.phase_sync();
     kin_adj(P, Y, s, g);
+    g.phase_sync();
 }
 
 }  // namespace dfx

@@ -29,6 +29,7 @@ struct StepArgs {
     const float* gq_out; const float* gqd_out;
     float* gq; float* gqd; float* gact; float* gmusc;
     long long hinv_base;
+    int flags;   // bit 1: CTA-wide phase barriers
 };
 
 template <class Grp>
@@ -55,10 +56,14 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
         kin_fwd(P, Y, s, g);
+        g.phase_sync();
         body_force_fwd(P, Y, s, g);
+        g.phase_sync();
         contact_fwd(P, Y, s, g);
         muscle_fwd(P, Y, s, g);
+        g.phase_sync();
         tau_fwd(P, Y, s, g);
+        g.phase_sync();
         if (upd) {
             crba_fwd(P, Y, s, g);
             if (a.has_derived && a.derived.H) DFX_FOR(e, DD) a.derived.H[(long long)env * DD + e] = s[Y.A + e];
@@ -76,7 +81,8 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
             DFX_FOR(i, QD) t[i] = s[Y.q + i];
         }
         if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, g);
-        g.sync();   // the tape / dump copies above read q, qd, which integrate_fwd overwrites in place
+        g.phase_sync();   // (also orders the tape / dump copies above before integrate_fwd overwrites q, qd)
+        g.sync();
         integrate_fwd(P, Y, s, a.dt_sub, g);
     }
     DFX_FOR(i, Q) a.q_out[(long long)env * Q + i] = s[Y.q + i];
@@ -90,18 +96,18 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, float* s, const Gr
     DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
     DFX_FOR(i, Q) s[Y.aq + i] = a.gq_out ? a.gq_out[(long long)env * Q + i] : 0.0f;
     DFX_FOR(i, D) s[Y.aqd + i] = a.gqd_out ? a.gqd_out[(long long)env * D + i] : 0.0f;
-    const int nseg = (a.substeps + a.mm_freq - 1) / a.mm_freq;
-    for (int seg = nseg - 1; seg >= 0; --seg) {
+    for (int sub = a.substeps - 1; sub >= 0; --sub) {
+        const int seg = sub / a.mm_freq;
         const int s0 = seg * a.mm_freq;
-        const int s1 = (s0 + a.mm_freq < a.substeps) ? s0 + a.mm_freq : a.substeps;
-        const float* th = a.tape_in + a.hinv_base + ((long long)seg * a.N + env) * DD;
-        DFX_FOR(e, DD) { s[Y.A + e] = th[e]; s[Y.Lm + e] = 0.0f; }
-        for (int sub = s1 - 1; sub >= s0; --sub) {
-            const float* t = a.tape_in + ((long long)sub * a.N + env) * QD;
-            DFX_FOR(i, QD) s[Y.q + i] = t[i];
-            g.sync();
-            substep_adj(P, Y, s, a.dt_sub, sub == s0, g);
+        const bool seg_last = (sub == a.substeps - 1) || ((sub + 1) % a.mm_freq == 0);   // first visited of its segment
+        g.copy_row_async(s + Y.q, a.tape_in + ((long long)sub * a.N + env) * QD, QD);
+        if (seg_last) {
+            const float* th = a.tape_in + a.hinv_base + ((long long)seg * a.N + env) * DD;
+            DFX_FOR(e, DD) { s[Y.A + e] = th[e]; s[Y.Lm + e] = 0.0f; }
         }
+        g.copy_wait_all();
+        g.sync();
+        substep_adj(P, Y, s, a.dt_sub, sub == s0, g);
     }
     if (a.gq) DFX_FOR(i, Q) a.gq[(long long)env * Q + i] = s[Y.aq + i];
     if (a.gqd) DFX_FOR(i, D) a.gqd[(long long)env * D + i] = s[Y.aqd + i];

@@ -168,6 +168,8 @@ int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, con
 
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
+/* Tuning flags (default 3): bit 1 = CTA-wide phase barriers (instruction-cache locality). */
+int dfx_set_flags(int flags);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 long long dfx_launch_count(void);
 const char* dfx_version(void);

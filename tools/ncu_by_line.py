@@ -9,8 +9,10 @@ rep, lib, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+dis = ""
+for f in sorted(os.listdir(tmp)):
+    if f.endswith(".cubin"):
+        dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
 # ---- offset -> (file, line) for the chosen kernel
 off2line, cur, inside = {}, None, False
 for ln in dis.splitlines():
