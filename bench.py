@@ -40,10 +40,15 @@ CPU_SAMPLE = {"AntEnv": (64, 24), "HumanoidEnv": (16, 8), "SNUHumanoidEnv": (8, 
               "HopperEnv": (64, 32), "CheetahEnv": (64, 32)}
 
 
-def algorithmic_bytes(Q, D, A, substeps):
-    """state-only tape, fp32.  Returns (forward, backward) bytes per env-step."""
-    fwd = 4 * (Q + D + A) + 4 * (Q + D) + 4 * substeps * (Q + D)
-    bwd = 4 * substeps * (Q + D) + 4 * (Q + D) + 4 * A + 4 * (Q + D + A)
+def algorithmic_bytes(Q, D, A, substeps, row=None, nseg=1):
+    """Bytes one env-step MUST move per environment, fp32.  With row=None: SURVEY.md section 8d's figure for a
+    state-only tape (row = Q + D).  With the kernels' actual tape row (q, qd + the forward intermediates the
+    adjoint reads back instead of recomputing) and the D*D H^-1 block per mass-matrix
+    update: the design's own algorithmic traffic.  Returns (forward, backward)."""
+    row = (Q + D) if row is None else row
+    hinv = 0 if row == Q + D else nseg * D * D
+    fwd = 4 * (Q + D + A) + 4 * (Q + D) + 4 * (substeps * row + hinv)
+    bwd = 4 * (substeps * row + hinv) + 4 * (Q + D) + 4 * A + 4 * (Q + D + A)
     return fwd, bwd
 
 
@@ -128,27 +133,52 @@ def cpu_reference_arm(env_name, budget_steps=None):
             "seconds": tf + tb}
 
 
+def _cpu_worker(env_name, reps, out_q):
+    """One host process of the reference arm: `reps` timed samples on one core."""
+    try:
+        secs = [cpu_reference_arm(env_name)["seconds"] for _ in range(reps)]
+        out_q.put(secs)
+    except Exception as exc:  # pragma: no cover
+        out_q.put(exc)
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path on this box's host cores.  Its kernels are a serial
+    loop (adjoint.py:1271-1279), so "all the host threads it can use" = P independent single-threaded
+    processes, each running the same bounded sample concurrently (environments are independent)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     env = args.env
     n, steps = CPU_SAMPLE[env]
-    times = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_reference_arm(env)
-        if base["value"] is None:
-            print(json.dumps({"impl": "reference", "unavailable": base["sample"]}))
+    probe = cpu_reference_arm(env) if args.warmup > 0 else None
+    if probe is not None and probe["value"] is None:
+        print(json.dumps({"impl": "reference", "unavailable": probe["sample"]}))
+        return
+    procs = max(1, min(args.cpu_procs or (os.cpu_count() or 1), 64))
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    workers = [ctx.Process(target=_cpu_worker, args=(env, args.steps, out_q)) for _ in range(procs)]
+    for w in workers:
+        w.start()
+    results = [out_q.get() for _ in workers]
+    for w in workers:
+        w.join()
+    for r in results:
+        if isinstance(r, Exception):
+            print(json.dumps({"impl": "reference", "unavailable": "worker failed: %r" % (r,)}))
             return
-        if i >= args.warmup:
-            times.append(base["seconds"])
-    value = n * steps * len(times) / sum(times)
-    base["value"] = value
+    per_step = [max(r[i] for r in results) for i in range(args.steps)]   # all workers run step i concurrently
+    times = per_step
+    value = procs * n * steps * len(times) / sum(times)
+    base = {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "reference",
+            "sample": "%s: %d single-threaded processes x (%d envs x %d env-steps forward+adjoint) on the reference's own "
+                      "generated CPU kernels (oracle/_ref/kernels.so); host has %d cores" % (env, procs, n, steps, os.cpu_count())}
     line = {"impl": "reference", "metric": "differentiable env-steps/s (fwd+bwd)", "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s reference dflex CPU path, bounded sample %d envs x %d env-steps per step" % (env, n, steps)},
+            "config": {"workload": "%s reference dflex CPU path, bounded sample: %d processes x %d envs x %d env-steps per step" % (env, procs, n, steps)},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -303,7 +333,9 @@ def run_ours(args):
     value = total_env_steps / (kernel_ms * 1e-3)
     e2e_value = world * N * T * e2e_steps / (e2e_ms * 1e-3)
     peaks, peak_kind = measured_peaks()
-    b_fwd, b_bwd = algorithmic_bytes(Q, D, A, S)
+    row = lib.dfx_pack_query(eng.pack, 8)   # DFX_QUERY_TAPE_ROW_FLOATS
+    b_fwd, b_bwd = algorithmic_bytes(Q, D, A, S, row=row, nseg=(S + mm - 1) // mm)
+    s_fwd, s_bwd = algorithmic_bytes(Q, D, A, S)
     achieved = N * b_bwd / (bwd_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -329,7 +361,11 @@ def run_ours(args):
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                      "kernel": "dfx_step_kernel<G,BWD=1> (adjoint of one env-step)",
                      "algorithmic_bytes_per_launch": N * b_bwd,
-                     "note": "fused path is FP32-issue/latency bound, not HBM bound; see profiles/ and DESIGN.md section 5"},
+                     "survey_8d_state_only_bytes_per_launch": N * s_bwd,
+                     "forward_kernel": {"achieved": N * b_fwd / (fwd_ms * 1e-3) / 1e9, "algorithmic_bytes_per_launch": N * b_fwd},
+                     "note": "algorithmic bytes = this design's tape rows (q, qd + forward intermediates, 4*row B per env-substep) "
+                             "+ H^-1 blocks + state I/O; the fused path is FP32-issue/latency bound, not HBM bound "
+                             "(profiles/r01_ant_full.md, DESIGN.md section 3)"},
         "clocks": clocks.summary(),
     }
     if cpu is not None:
@@ -349,6 +385,7 @@ def main():
     ap.add_argument("--num-envs", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: host processes (default: all cores, max 64)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="wrap ONE kernel-path step and ONE e2e step in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     args = ap.parse_args()

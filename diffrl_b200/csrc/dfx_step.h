@@ -52,6 +52,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
     DFX_FOR(i, Q) s[Y.q + i] = a.q[(long long)env * Q + i];
     DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
     DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
+    for (int i = Y.qdd + D + g.lane; i < Y.q + Y.tape_row; i += Grp::G) s[i] = 0.0f;   // row padding
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
