@@ -317,13 +317,42 @@ def run_ours(args):
         e2e_rollout()
     e3[1].record()
     barrier()
-    e2e_ms = e3[0].elapsed_time(e3[1])
+    eager_ms = e3[0].elapsed_time(e3[1])
+
+    # the same rollout through the package's graphed-rollout API (one CUDA graph per rollout: H2D actions,
+    # horizon x env.step, loss.backward, D2H loss + action gradients)
+    e2e_ms, e2e_api = eager_ms, "envs.%s.step -> dflex.sim.SemiImplicitIntegrator.forward -> autograd (eager)" % env_name
+    if args.e2e != "eager" and hasattr(env, "_reset_masked"):
+        from diffrl_b200.rollout import GraphedRollout
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        roll = GraphedRollout(env, T)
+
+        def graphed_rollout():
+            env.clear_grad()
+            env.reset()
+            loss_h, grad_h = roll(host_actions, sync=False)
+            if world > 1:
+                comm[: T * env.num_actions] = roll.actions.grad.mean(dim=1).reshape(-1)
+                dist.all_reduce(comm)
+            torch.cuda.current_stream().synchronize()
+            return float(loss_h)
+
+        for _ in range(max(1, args.warmup // 2)):
+            graphed_rollout()
+        barrier()
+        e3[0].record()
+        for _ in range(e2e_steps):
+            graphed_rollout()
+        e3[1].record()
+        barrier()
+        e2e_ms = e3[0].elapsed_time(e3[1])
+        e2e_api = "diffrl_b200.rollout.GraphedRollout(envs.%s): one CUDA graph = H2D actions + %d x env.step + backward + D2H" % (env_name, T)
 
     # ------------------------------------------------------------ reduce over ranks (max time)
-    times = torch.tensor([kernel_ms, e2e_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([kernel_ms, e2e_ms, eager_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    kernel_ms, e2e_ms = times.tolist()
+    kernel_ms, e2e_ms, eager_ms = times.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -353,8 +382,9 @@ def run_ours(args):
                    "cache": "per-rollout tape %.0f MB > 126 MB L2 (inputs larger than L2)" % (T * eng.tape_floats(S, mm) * 4 / 1e6),
                    "group_lanes": "auto"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(host_actions.numel() * 4),
-                "d2h_bytes_per_step": int(host_grad.numel() * 4 + 4), "api": "envs.%s.step -> dflex.sim.SemiImplicitIntegrator.forward -> autograd" % env_name,
-                "ms_per_step": e2e_ms / e2e_steps},
+                "d2h_bytes_per_step": int(host_grad.numel() * 4 + 4), "api": e2e_api,
+                "ms_per_step": e2e_ms / e2e_steps,
+                "eager_env_step_loop": {"value": world * N * T * e2e_steps / (eager_ms * 1e-3), "ms_per_step": eager_ms / e2e_steps}},
         "gpu_launches": int(launches),
         "kernel_ms": {"forward_env_step": fwd_ms, "backward_env_step": bwd_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -385,6 +415,7 @@ def main():
     ap.add_argument("--num-envs", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e", default="graph", choices=["graph", "eager"])
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: host processes (default: all cores, max 64)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="wrap ONE kernel-path step and ONE e2e step in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")

@@ -1,0 +1,103 @@
+"""CUDA-graphed differentiable rollouts.
+
+``env.step`` is launch-bound once the simulation kernels take a few hundred microseconds: a 32-step SHAC
+rollout issues ~1 500 small launches (sim step, fused epilogue, masked reset, autograd bookkeeping) from
+Python.  ``GraphedRollout`` captures ``horizon`` env-steps, the loss and its backward pass into ONE CUDA
+graph (the env layer is sync-free: masked resets, no ``nonzero()``), including the host->device copy of
+the actions and the device->host copies of the loss and the action gradients, and replays it:
+
+    roll = GraphedRollout(env, horizon=32)
+    loss, grad_actions = roll(host_actions)        # host_actions: pinned [horizon, num_envs, num_actions]
+
+Each call starts from the env's current state (``env.state.joint_q/qd``, ``progress_buf``, last actions)
+and leaves the env at the end of the rollout with the graph cut (as ``env.clear_grad()`` would), so
+consecutive calls chain like SHAC's short-horizon windows (reference algorithms/shac.py:169-292).
+"""
+import torch
+
+
+class GraphedRollout:
+    def __init__(self, env, horizon, reward_weight=None, warmup=2):
+        if torch.device(env.device).type != "cuda":
+            raise RuntimeError("GraphedRollout needs a CUDA environment")
+        if env.no_grad:
+            raise RuntimeError("GraphedRollout differentiates the rollout: construct the env with no_grad=False")
+        if not getattr(env, "sync_free_reset", False) or not hasattr(env, "_reset_masked"):
+            raise RuntimeError("%s resets through reset_buf.nonzero(), which cannot be captured" % type(env).__name__)
+        self.env, self.T = env, int(horizon)
+        dev = torch.device(env.device)
+        n, a = env.num_envs, env.num_actions
+        self.device = dev
+        # static inputs
+        self.actions = torch.zeros((self.T, n, a), device=dev, requires_grad=True)
+        self.q0 = env.state.joint_q.detach().clone()
+        self.qd0 = env.state.joint_qd.detach().clone()
+        self.progress0 = env.progress_buf.clone()
+        self.prev_actions = env.actions.detach().clone()
+        self.weight = None if reward_weight is None else reward_weight.to(dev)
+        # pinned host mirrors of the outputs
+        self.host_grad = torch.empty((self.T, n, a), dtype=torch.float32).pin_memory()
+        self.host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        self.host_actions = torch.empty((self.T, n, a), dtype=torch.float32).pin_memory()
+        self.graph = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.actions.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        torch.cuda.synchronize(dev)
+
+    def _body(self):
+        env = self.env
+        with torch.no_grad():
+            self.actions.copy_(self.host_actions, non_blocking=True)
+        # start from the static state buffers, graph cut (== env.clear_grad() on those values)
+        env.state = env.model.state()
+        env.state.joint_q = self.q0.clone()
+        env.state.joint_qd = self.qd0.clone()
+        env.progress_buf = self.progress0.clone()
+        env.actions = self.prev_actions.clone()
+        env.calculateObservations()
+        loss = torch.zeros((), device=self.device)
+        obs_l, rew_l, done_l = [], [], []
+        for t in range(self.T):
+            obs, rew, done, _ = env.step(self.actions[t])
+            loss = loss + (rew.sum() if self.weight is None else (rew * self.weight).sum())
+            obs_l.append(obs); rew_l.append(rew); done_l.append(done)
+        self.actions.grad = None
+        loss.backward()
+        self.obs, self.rew, self.done = torch.stack(obs_l).detach(), torch.stack(rew_l).detach(), torch.stack(done_l)
+        self.loss = loss.detach()
+        self.final_q = env.state.joint_q.detach()
+        self.final_qd = env.state.joint_qd.detach()
+        self.final_progress = env.progress_buf
+        self.final_actions = env.actions.detach()
+        self.host_grad.copy_(self.actions.grad, non_blocking=True)
+        self.host_loss.copy_(self.loss, non_blocking=True)
+
+    def __call__(self, host_actions=None, sync=True):
+        """Replay the captured rollout.  ``host_actions``: [T, N, A] tensor (ideally pinned); None re-uses the
+        previous buffer contents.  Returns (loss, grad_actions) as host tensors (valid after the sync)."""
+        env = self.env
+        if host_actions is not None:
+            self.host_actions.copy_(host_actions)
+        with torch.no_grad():
+            # chain from where the env currently is
+            self.q0.copy_(env.state.joint_q.detach().view(-1))
+            self.qd0.copy_(env.state.joint_qd.detach().view(-1))
+            self.progress0.copy_(env.progress_buf)
+            self.prev_actions.copy_(env.actions.detach())
+        self.graph.replay()
+        # leave the env at the end of the rollout, detached
+        env.state = env.model.state()
+        env.state.joint_q, env.state.joint_qd = self.final_q, self.final_qd
+        env.progress_buf, env.actions = self.final_progress, self.final_actions
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return self.host_loss, self.host_grad

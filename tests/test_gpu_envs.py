@@ -123,3 +123,40 @@ def test_masked_reset_equals_indexed_reset():
     for a, b in zip(*res):
         assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
         assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[3], b[3], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv"])
+def test_graphed_rollout_equals_eager(name):
+    """One CUDA graph for horizon env-steps + backward reproduces the eager rollout (loss, action gradients,
+    final state) and chains across calls."""
+    import torch
+    import diffrl_b200.envs as envs
+    from diffrl_b200.rollout import GraphedRollout
+    n, T = 48, 6
+    g = torch.Generator().manual_seed(2)
+    acts = [torch.rand((T, n, 8 if name == "AntEnv" else 21), generator=g) * 2 - 1 for _ in range(2)]
+
+    def make():
+        env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=9)
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        return env
+
+    env = make()
+    eager = []
+    for a in acts:                      # two chained windows, eager
+        env.initialize_trajectory()
+        a_dev = a.to("cuda:0").requires_grad_()
+        loss = 0.0
+        for t in range(T):
+            obs, rew, done, _ = env.step(a_dev[t])
+            loss = loss + rew.sum()
+        loss.backward()
+        eager.append((float(loss), a_dev.grad.cpu(), env.state.joint_q.detach().cpu().clone()))
+    env2 = make()
+    roll = GraphedRollout(env2, T)
+    env2.clear_grad(); env2.reset(); env2.initialize_trajectory()       # capture warm-up advanced the env: restart
+    for k, a in enumerate(acts):
+        loss, grad = roll(a)
+        assert abs(float(loss) - eager[k][0]) <= 1e-4 * abs(eager[k][0]) + 1e-3
+        assert (grad - eager[k][1]).abs().max() <= 2e-4 * eager[k][1].abs().max() + 1e-6
+        assert torch.allclose(env2.state.joint_q.cpu(), eager[k][2], rtol=1e-5, atol=1e-5)
