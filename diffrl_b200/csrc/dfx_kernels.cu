@@ -37,7 +37,6 @@ struct GroupCuda {
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-    __device__ __forceinline__ void copy_wait_but_one() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 };
 
 constexpr int kMaxThreads = 128;
@@ -79,7 +78,9 @@ struct KernelArgs {
     int pack_smem_floats; // floats reserved at the start of dynamic smem for the staged pack
 };
 
-template <int G, bool BACKWARD>
+// SL..SM > 0: model sizes known at compile time (the six DiffRL articulations are pre-instantiated); the scratch
+// layout and every loop bound then fold into immediates.  SL == 0: generic run-time sizes.
+template <int G, bool BACKWARD, int SL, int SD, int SQ, int SC, int SM>
 __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_constant__ KernelArgs ka) {
     extern __shared__ __align__(16) float smem[];
     // ---- stage the model description
@@ -88,7 +89,13 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
     for (int i = threadIdx.x; i < ka.blob.n_floats; i += blockDim.x) fpack[i] = ka.blob.floats[i];
     for (int i = threadIdx.x; i < ka.blob.n_ints; i += blockDim.x) ipack[i] = ka.blob.ints[i];
     __syncthreads();
-    const Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
+    Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
+    Layout Y = ka.layout;
+    if constexpr (SL > 0) {
+        P.L = SL; P.D = SD; P.Q = SQ; P.C = SC; P.M = SM;
+        constexpr Layout kY = make_layout(SL, SD, SQ, SC, SM);
+        Y = kY;
+    }
 
     const int kEnvsPerCta = blockDim.x / G;
     const int local = threadIdx.x / G;
@@ -102,8 +109,8 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
     g.psync = (ka.step.flags & 2) != 0;
     g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_in_warp / G) * G));
     float* s = smem + ka.pack_smem_floats + (size_t)local * ka.scratch_stride;
-    if (BACKWARD) env_step_backward(P, ka.layout, s, g, env, ka.step);
-    else env_step_forward(P, ka.layout, s, g, env, ka.step);
+    if (BACKWARD) env_step_backward(P, Y, s, g, env, ka.step);
+    else env_step_forward(P, Y, s, g, env, ka.step);
 }
 
 }  // namespace dfx
@@ -125,7 +132,7 @@ struct dfx_pack {
 static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
-static int g_flags = 3;
+static int g_flags = 3;   // bit 1: phase barriers; bit 2: DISABLE the size-specialised kernels (A/B testing)
 
 static void set_err(char* err, int n, const std::string& m) {
     if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
@@ -196,8 +203,8 @@ long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq)
 
 }  // extern "C"
 
-template <int G, bool BWD>
-static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t stream) {
+template <int G, bool BWD, int SL, int SD, int SQ, int SC, int SM>
+static cudaError_t launch_impl(const dfx_pack* p, const StepArgs& step, cudaStream_t stream) {
     KernelArgs ka;
     ka.header = p->header;
     ka.blob = p->blob;
@@ -225,7 +232,7 @@ static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t 
     }
     if (envs_per_cta == 0) return cudaErrorInvalidConfiguration;
     const size_t smem = (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float);
-    auto kern = dfx_step_kernel<G, BWD>;
+    auto kern = dfx_step_kernel<G, BWD, SL, SD, SQ, SC, SM>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -236,6 +243,28 @@ static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t 
     kern<<<grid, envs_per_cta * G, smem, stream>>>(ka);
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+
+// dispatch on the model sizes: specialised instantiations for the DiffRL articulations, generic otherwise
+template <int G, bool BWD>
+static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t stream) {
+    const Pack& h = p->header;
+#define DFX_SPECIAL(l, d, q, c, m) \
+    if (h.L == l && h.D == d && h.Q == q && h.C == c && h.M == m) return launch_impl<G, BWD, l, d, q, c, m>(p, step, stream);
+    if (!(g_flags & 4)) {
+        if constexpr (G == 16) {               // the group width pick_group() chooses for these models
+            DFX_SPECIAL(9, 14, 15, 25, 0)      // Ant
+            DFX_SPECIAL(3, 2, 2, 0, 0)         // CartPole
+            DFX_SPECIAL(6, 6, 6, 8, 0)         // Hopper
+            DFX_SPECIAL(9, 9, 9, 16, 0)        // HalfCheetah
+        }
+        if constexpr (G == 32) {
+            DFX_SPECIAL(22, 27, 28, 35, 0)     // Humanoid
+            DFX_SPECIAL(11, 24, 29, 88, 152)   // SNU humanoid (lower body, 152 muscles)
+        }
+    }
+#undef DFX_SPECIAL
+    return launch_impl<G, BWD, 0, 0, 0, 0, 0>(p, step, stream);
 }
 
 static int pick_group(const dfx_pack* p) {

@@ -82,44 +82,39 @@ struct Layout {
     int bwd_size;
 };
 
-inline int dfx_round_up(int x, int m) { return (x + m - 1) / m * m; }
-
-// the same layout with the taped block [q .. qdd] relocated by `shift` floats (double buffering)
-inline
 #if defined(__CUDACC__)
-__host__ __device__
+#define DFX_LAYOUT_FN __host__ __device__ constexpr
+#else
+#define DFX_LAYOUT_FN constexpr
 #endif
-Layout shifted_tape_block(Layout y, int shift) {
-    y.q += shift; y.qd += shift; y.Xsc += shift; y.Xsm += shift; y.S += shift; y.v += shift; y.a += shift;
-    y.ft += shift; y.qdd += shift;
-    return y;
-}
+DFX_LAYOUT_FN int dfx_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-inline Layout make_layout(int L, int D, int Q, int C, int M) {
-    Layout y;
+DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M) {
+    Layout y{};
     int o = 0;
-    auto take = [&](int n) { int r = o; o += n; return r; };
+#define DFX_TAKE(n) (o += (n), o - (n))
     // [q .. qdd] is one contiguous block: it is what forward writes to the tape per substep and what the
     // adjoint reads back instead of re-running the forward dynamics (tape_row floats)
-    y.q = take(Q); y.qd = take(D);
-    y.Xsc = take(L * 7); y.Xsm = take(L * 7); y.S = take(D * 6); y.v = take(L * 6); y.a = take(L * 6);
-    y.ft = take(L * 6); y.qdd = take(D);
+    y.q = DFX_TAKE(Q); y.qd = DFX_TAKE(D);
+    y.Xsc = DFX_TAKE(L * 7); y.Xsm = DFX_TAKE(L * 7); y.S = DFX_TAKE(D * 6); y.v = DFX_TAKE(L * 6); y.a = DFX_TAKE(L * 6);
+    y.ft = DFX_TAKE(L * 6); y.qdd = DFX_TAKE(D);
     o = dfx_round_up(o, 4);          // rows are copied with 16-byte transactions
     y.tape_row = o;
-    y.act = take(D); y.musc = take(M); y.tau = take(D);
-    y.Xl = take(L * 7); y.vj = take(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
-    y.A = take(D * D); y.Lm = take(D * D);
+    y.act = DFX_TAKE(D); y.musc = DFX_TAKE(M); y.tau = DFX_TAKE(D);
+    y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
+    y.A = DFX_TAKE(D * D); y.Lm = DFX_TAKE(D * D);
     // ---- from here on the forward-only and the adjoint-only fields share the same region
     const int shared_end = o;
-    y.Icmp = take(L * 21 + D * 6);
-    y.f = take(L * 6);
-    y.cw = take(C * 6);              // contact wrenches staged for the deterministic per-body gather
+    y.Icmp = DFX_TAKE(L * 21 + D * 6);
+    y.f = DFX_TAKE(L * 6);
+    y.cw = DFX_TAKE(C * 6);              // contact wrenches staged for the deterministic per-body gather
     y.fwd_size = o;
     o = shared_end;
-    y.aq = take(Q); y.aqd = take(D); y.aqdd = take(D); y.aact = take(D); y.amusc = take(M);
-    y.aXsc = take(L * 7); y.aXsm = take(L * 7); y.aS = take(D * 6); y.av = take(L * 6); y.aa = take(L * 6);
-    y.af = take(L * 6); y.aIbar = take(L * 12); y.pX = take(L * 7);
+    y.aq = DFX_TAKE(Q); y.aqd = DFX_TAKE(D); y.aqdd = DFX_TAKE(D); y.aact = DFX_TAKE(D); y.amusc = DFX_TAKE(M);
+    y.aXsc = DFX_TAKE(L * 7); y.aXsm = DFX_TAKE(L * 7); y.aS = DFX_TAKE(D * 6); y.av = DFX_TAKE(L * 6); y.aa = DFX_TAKE(L * 6);
+    y.af = DFX_TAKE(L * 6); y.aIbar = DFX_TAKE(L * 12); y.pX = DFX_TAKE(L * 7);
     y.bwd_size = o;
+#undef DFX_TAKE
     return y;
 }
 

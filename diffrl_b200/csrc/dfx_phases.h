@@ -35,7 +35,6 @@ struct GroupSerial {  // host / single-lane execution
     // asynchronous global -> scratch row copy (16-byte aligned, n a multiple of 4 floats)
     DFX_HD void copy_row_async(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
     DFX_HD void copy_wait_all() const {}
-    DFX_HD void copy_wait_but_one() const {}
 };
 
 #define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
