@@ -29,12 +29,19 @@ struct GroupCuda {
     bool psync;
     __device__ __forceinline__ void phase_sync() const { if (psync) __syncthreads(); }
     __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_or(unsigned* p, unsigned v) const { atomicOr(p, v); }
     // cp.async (LDGSTS) 16-byte copies, one commit group per row
     __device__ __forceinline__ void copy_row_async(float* dst, const float* src, int n) const {
         const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
         for (int i = lane * 4; i < n; i += G_ * 4)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // scratch -> global row (16-byte aligned, n a multiple of 4 floats)
+    __device__ __forceinline__ void copy_row_out(float* dst, const float* src, int n) const {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = lane; i < n / 4; i += G_) d4[i] = s4[i];
     }
     __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };

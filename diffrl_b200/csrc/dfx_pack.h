@@ -71,6 +71,7 @@ struct Layout {
     int q, qd, act, musc, tau, qdd, Xl, vj;
     int Xsc, Xsm, S, v, a, f, ft;
     int cw;    // contact wrenches (C,6), forward only
+    int cmask;
     int A;     // H, then H^-1 (D,D)
     int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
     int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
@@ -108,6 +109,7 @@ DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M) {
     y.Icmp = DFX_TAKE(L * 21 + D * 6);
     y.f = DFX_TAKE(L * 6);
     y.cw = DFX_TAKE(C * 6);              // contact wrenches staged for the deterministic per-body gather
+    y.cmask = DFX_TAKE(1);               // bit mask of bodies in contact
     y.fwd_size = o;
     o = shared_end;
     y.aq = DFX_TAKE(Q); y.aqd = DFX_TAKE(D); y.aqdd = DFX_TAKE(D); y.aact = DFX_TAKE(D); y.amusc = DFX_TAKE(M);

@@ -32,9 +32,11 @@ struct GroupSerial {  // host / single-lane execution
     DFX_HD void sync() const {}
     DFX_HD void phase_sync() const {}
     DFX_HD void atomic_add(float* p, float v) const { *p += v; }
+    DFX_HD void atomic_or(unsigned* p, unsigned v) const { *p |= v; }
     // asynchronous global -> scratch row copy (16-byte aligned, n a multiple of 4 floats)
     DFX_HD void copy_row_async(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
     DFX_HD void copy_wait_all() const {}
+    DFX_HD void copy_row_out(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
 };
 
 #define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
@@ -394,15 +396,27 @@ DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int 
 template <class Grp>
 DFX_HD void contact_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     if (!P.ground) return;
-    DFX_FOR(k, P.C) st6(s + Y.cw + k * 6, contact_point_fwd(P, Y, s, k));
+    // bodies with at least one penetrating point are flagged in a bit mask (L <= 32) so that the per-body
+    // gather below touches only those; the summation order inside a body is still the contact order
+    unsigned* mask = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const bool use_mask = P.L <= 32;
+    DFX_FOR(k, P.C) {
+        const SV w = contact_point_fwd(P, Y, s, k);
+        st6(s + Y.cw + k * 6, w);
+        if (use_mask && (w.v.x != 0.0f || w.v.y != 0.0f || w.v.z != 0.0f || w.w.x != 0.0f || w.w.y != 0.0f || w.w.z != 0.0f))
+            g.atomic_or(mask, 1u << P.cbody[k]);
+    }
     g.sync();
+    const unsigned active = use_mask ? *mask : 0xffffffffu;
     DFX_FOR(it, P.L * 6) {
         const int i = it / 6, c = it - i * 6;
+        if (!((active >> (i & 31)) & 1u)) continue;
         float acc = s[Y.f + it];
         for (int k = P.cbody_start[i]; k < P.cbody_start[i + 1]; ++k) acc += s[Y.cw + k * 6 + c];
         s[Y.f + it] = acc;
     }
     g.sync();
+    if (g.lane == 0) *mask = 0u;
 }
 
 // adjoint for one contact: cotangent r = af[body]; accumulates into aXsc[body], av[body] with shared-memory
@@ -948,11 +962,7 @@ DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_m
 // aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
 template <class Grp>
 DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool apply_crba, const Grp& g) {
-    zero_range(s + Y.aXsc, P.L * 7, g);
-    zero_range(s + Y.aXsm, P.L * 7, g);
-    zero_range(s + Y.aS, P.D * 6, g);
-    zero_range(s + Y.av, P.L * 6, g);
-    zero_range(s + Y.aa, P.L * 6, g);
+    zero_range(s + Y.aXsc, Y.af - Y.aXsc, g);      // aXsc, aXsm, aS, av, aa are adjacent (af is overwritten by tau_adj)
     zero_range(s + Y.aIbar, P.L * 12, g);
     g.sync();
     // phase_sync(): CTA-wide barrier that keeps the warps of a CTA inside the same phase, so that the

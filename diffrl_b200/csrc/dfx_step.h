@@ -53,6 +53,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
     DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
     DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
     for (int i = Y.qdd + D + g.lane; i < Y.q + Y.tape_row; i += Grp::G) s[i] = 0.0f;   // row padding
+    if (g.lane == 0) s[Y.cmask] = 0.0f;
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
@@ -79,7 +80,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
         solve_fwd(P, Y, s, g);
         if (a.tape) {   // q, qd still hold the values that ENTERED this substep
             float* t = a.tape + ((long long)sub * a.N + env) * QD;
-            DFX_FOR(i, QD) t[i] = s[Y.q + i];
+            g.copy_row_out(t, s + Y.q, QD);
         }
         if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, g);
         g.phase_sync();   // (also orders the tape / dump copies above before integrate_fwd overwrites q, qd)
