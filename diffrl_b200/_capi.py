@@ -9,7 +9,8 @@ import os
 from .modelpack import DfxDerived, DfxModelDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfx.so")
+# DFX_LIBRARY points at another build of the SAME C ABI (same-box A/B timing of two kernel versions); never a fallback
+LIB_PATH = os.environ.get("DFX_LIBRARY") or os.path.join(_HERE, "libdfx.so")
 
 _F = ctypes.c_void_p  # raw device pointers
 _lib = None
@@ -33,6 +34,8 @@ def lib():
         raise DfxError("diffrl_b200: cannot load %s: %s" % (LIB_PATH, exc))
     L.dfx_version.restype = ctypes.c_char_p
     L.dfx_launch_count.restype = ctypes.c_longlong
+    if hasattr(L, "dfx_launch_plan"):   # absent from older builds loaded through DFX_LIBRARY for A/B timing
+        L.dfx_launch_plan.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.dfx_set_group_size.argtypes = [ctypes.c_int]
     L.dfx_pack_create.restype = ctypes.c_void_p
     L.dfx_pack_create.argtypes = [ctypes.POINTER(DfxModelDesc), ctypes.c_int, ctypes.c_char_p, ctypes.c_int]

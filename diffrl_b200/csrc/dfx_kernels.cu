@@ -28,8 +28,16 @@ struct GroupCuda {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
     bool psync;
     __device__ __forceinline__ void phase_sync() const { if (psync) __syncthreads(); }
-    __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
     __device__ __forceinline__ void atomic_or(unsigned* p, unsigned v) const { atomicOr(p, v); }
+    // one word of the fixed-point scatter-add (dfx_phases.h): native ATOMS.ADD, result unused -> fire and forget
+    __device__ __forceinline__ void fx_add(int* p, int v) const { atomicAdd(p, v); }
+    // fp32 add on shared memory: an ATOMS.CAST.SPIN loop, used only where contention is a few lanes at most
+    __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
+    __device__ __forceinline__ float group_max(float v) const {
+#pragma unroll
+        for (int o = G_ / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, G_));
+        return v;
+    }
     // cp.async (LDGSTS) 16-byte copies, one commit group per row
     __device__ __forceinline__ void copy_row_async(float* dst, const float* src, int n) const {
         const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -210,6 +218,36 @@ long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq)
 
 }  // extern "C"
 
+// launch geometry of one step kernel (host arithmetic only, also exported through dfx_launch_plan)
+struct LaunchPlan {
+    int scratch_stride, pack_bytes, envs_per_cta, ctas_per_sm;
+    size_t smem;
+};
+static LaunchPlan plan_launch(const dfx_pack* p, int G, bool bwd) {
+    LaunchPlan lp{};
+    const int per_env = bwd ? p->host.layout.bwd_size : p->host.layout.fwd_size;
+    // multiple of 4 floats (16-byte cp.async rows) that is not a multiple of 32 (bank spreading between groups)
+    lp.scratch_stride = (per_env + 3) & ~3;
+    if (lp.scratch_stride % 32 == 0) lp.scratch_stride += 4;
+    lp.pack_bytes = (((p->blob.n_floats + 3) & ~3) + ((p->blob.n_ints + 3) & ~3)) * 4;
+    // environments per CTA: the candidate (128, 64 or 32 threads) that keeps the most environments resident
+    // per SM under the shared-memory (227 KB) and register (64 K) budgets; ties go to the larger CTA
+    const int regs_per_thread = bwd ? 128 : 96;
+    int best = -1;
+    for (int threads = kMaxThreads; threads >= 32 && threads >= G; threads /= 2) {
+        const int e = threads / G;
+        const size_t bytes = (size_t)lp.pack_bytes + (size_t)e * lp.scratch_stride * sizeof(float) + 1024;
+        if (bytes > 227 * 1024) continue;
+        int ctas = (int)((227 * 1024) / bytes);
+        const int by_regs = 65536 / (regs_per_thread * threads);
+        if (by_regs < ctas) ctas = by_regs;
+        if (ctas > 32) ctas = 32;
+        if (ctas * e > best) { best = ctas * e; lp.envs_per_cta = e; lp.ctas_per_sm = ctas; }
+    }
+    lp.smem = (size_t)lp.pack_bytes + (size_t)lp.envs_per_cta * lp.scratch_stride * sizeof(float);
+    return lp;
+}
+
 template <int G, bool BWD, int SL, int SD, int SQ, int SC, int SM>
 static cudaError_t launch_impl(const dfx_pack* p, const StepArgs& step, cudaStream_t stream) {
     KernelArgs ka;
@@ -217,28 +255,12 @@ static cudaError_t launch_impl(const dfx_pack* p, const StepArgs& step, cudaStre
     ka.blob = p->blob;
     ka.layout = p->host.layout;
     ka.step = step;
-    const int per_env = BWD ? p->host.layout.bwd_size : p->host.layout.fwd_size;
-    // multiple of 4 floats (16-byte cp.async rows) that is not a multiple of 32 (bank spreading between groups)
-    ka.scratch_stride = (per_env + 3) & ~3;
-    if (ka.scratch_stride % 32 == 0) ka.scratch_stride += 4;
-    const int pack_bytes = (((p->blob.n_floats + 3) & ~3) + ((p->blob.n_ints + 3) & ~3)) * 4;
-    ka.pack_smem_floats = pack_bytes / 4;
-    // environments per CTA: the candidate (128, 64 or 32 threads) that keeps the most environments resident
-    // per SM under the shared-memory (227 KB) and register (64 K) budgets; ties go to the larger CTA
-    const int regs_per_thread = BWD ? 128 : 96;
-    int envs_per_cta = 0, best = -1;
-    for (int threads = kMaxThreads; threads >= 32 && threads >= G; threads /= 2) {
-        const int e = threads / G;
-        const size_t bytes = (size_t)pack_bytes + (size_t)e * ka.scratch_stride * sizeof(float) + 1024;
-        if (bytes > 227 * 1024) continue;
-        int ctas = (int)((227 * 1024) / bytes);
-        const int by_regs = 65536 / (regs_per_thread * threads);
-        if (by_regs < ctas) ctas = by_regs;
-        if (ctas > 32) ctas = 32;
-        if (ctas * e > best) { best = ctas * e; envs_per_cta = e; }
-    }
+    const LaunchPlan lp = plan_launch(p, G, BWD);
+    ka.scratch_stride = lp.scratch_stride;
+    ka.pack_smem_floats = lp.pack_bytes / 4;
+    const int envs_per_cta = lp.envs_per_cta;
     if (envs_per_cta == 0) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)pack_bytes + (size_t)envs_per_cta * ka.scratch_stride * sizeof(float);
+    const size_t smem = lp.smem;
     auto kern = dfx_step_kernel<G, BWD, SL, SD, SQ, SC, SM>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -281,6 +303,15 @@ static int pick_group(const dfx_pack* p) {
 }
 
 extern "C" {
+
+int dfx_launch_plan(const dfx_pack_t* p, int backward, int out[6]) {
+    if (!p || !out) return (int)cudaErrorInvalidValue;
+    const int G = pick_group(p);
+    const LaunchPlan lp = plan_launch(p, G, backward != 0);
+    out[0] = G; out[1] = lp.envs_per_cta; out[2] = lp.ctas_per_sm; out[3] = (int)lp.smem;
+    out[4] = lp.scratch_stride; out[5] = lp.pack_bytes;
+    return 0;
+}
 
 int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
                      const float* q, const float* qd, const float* act, const float* musc,

@@ -70,8 +70,7 @@ struct Layout {
     // primal
     int q, qd, act, musc, tau, qdd, Xl, vj;
     int Xsc, Xsm, S, v, a, f, ft;
-    int cw;    // contact wrenches (C,6), forward only
-    int cmask;
+    int cmask, fx, fxH;   // poison bits + int64 fixed-point accumulators of the deterministic scatter-adds
     int A;     // H, then H^-1 (D,D)
     int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
     int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
@@ -104,17 +103,18 @@ DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M) {
     y.act = DFX_TAKE(D); y.musc = DFX_TAKE(M); y.tau = DFX_TAKE(D);
     y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
     y.A = DFX_TAKE(D * D); y.Lm = DFX_TAKE(D * D);
+    y.cmask = DFX_TAKE(1);               // poison bits of the fixed-point scatter-adds (bit = body & 31)
     // ---- from here on the forward-only and the adjoint-only fields share the same region
     const int shared_end = o;
     y.Icmp = DFX_TAKE(L * 21 + D * 6);
     y.f = DFX_TAKE(L * 6);
-    y.cw = DFX_TAKE(C * 6);              // contact wrenches staged for the deterministic per-body gather
-    y.cmask = DFX_TAKE(1);               // bit mask of bodies in contact
+    y.fx = DFX_TAKE(L * 12);             // fixed-point accumulators of the contact + muscle wrenches: (L,6) low words, (L,6) high words
     y.fwd_size = o;
     o = shared_end;
     y.aq = DFX_TAKE(Q); y.aqd = DFX_TAKE(D); y.aqdd = DFX_TAKE(D); y.aact = DFX_TAKE(D); y.amusc = DFX_TAKE(M);
-    y.aXsc = DFX_TAKE(L * 7); y.aXsm = DFX_TAKE(L * 7); y.aS = DFX_TAKE(D * 6); y.av = DFX_TAKE(L * 6); y.aa = DFX_TAKE(L * 6);
+    y.aXsc = DFX_TAKE(L * 7); y.av = DFX_TAKE(L * 6); y.aXsm = DFX_TAKE(L * 7); y.aS = DFX_TAKE(D * 6); y.aa = DFX_TAKE(L * 6);
     y.af = DFX_TAKE(L * 6); y.aIbar = DFX_TAKE(L * 12); y.pX = DFX_TAKE(L * 7);
+    y.fxH = DFX_TAKE(M > 0 ? L * 13 : 0);            // high words of the fixed-point cotangent scatter into aXsc (L,7) and av (L,6); the low words live in aXsc / av
     y.bwd_size = o;
 #undef DFX_TAKE
     return y;

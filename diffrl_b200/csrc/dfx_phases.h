@@ -18,7 +18,7 @@
 // deterministic gathers, and nothing but (q, qd) per substep is taped: the adjoint recomputes
 // the substep in scratch memory.
 //
-// `Grp` provides: static G, lane, sync(), atomic_add(float*, float).
+// `Grp` provides: static G, lane, sync(), fx_add(int*, int), atomic_add(float*, float), group_max(float), atomic_or(unsigned*, unsigned).
 #pragma once
 
 #include "dfx_math.h"
@@ -31,8 +31,10 @@ struct GroupSerial {  // host / single-lane execution
     int lane;
     DFX_HD void sync() const {}
     DFX_HD void phase_sync() const {}
-    DFX_HD void atomic_add(float* p, float v) const { *p += v; }
     DFX_HD void atomic_or(unsigned* p, unsigned v) const { *p |= v; }
+    DFX_HD void fx_add(int* p, int v) const { *p += v; }
+    DFX_HD void atomic_add(float* p, float v) const { *p += v; }
+    DFX_HD float group_max(float v) const { return v; }
     // asynchronous global -> scratch row copy (16-byte aligned, n a multiple of 4 floats)
     DFX_HD void copy_row_async(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
     DFX_HD void copy_wait_all() const {}
@@ -369,6 +371,70 @@ DFX_HD void body_force_adj(const Pack& P, const Layout& Y, float* s, const Grp& 
 }
 
 // =====================================================================================
+// Deterministic scatter-adds.  Shared memory on sm_100 has native atomics for 32-bit integers only: atomicAdd(float*)
+// and the 64-bit integer atomicAdd both compile to ATOMS.CAST.SPIN compare-and-swap loops, which serialise badly when
+// many lanes hit one body (152 muscles on 11 bodies: 69 % of all stall samples).  Integer adds are also associative,
+// so a fixed-point sum is bit-reproducible whatever the order.  A contribution x is scaled by a power of two, rounded
+// to an integer v and split sign-symmetrically into two words, v = hi * 2^21 + lo with |lo| < 2^21: both are added
+// with fire-and-forget ATOMS.ADD (no carry between the words, so no returned value to wait for), and a contribution
+// with |v| < 2^21 costs one atomic.  Capacity: up to 1024 contributions per accumulator, |sum| < 2^52, each
+// contribution < 2^47 in magnitude.  Forward wrenches use the fixed scale 2^24 (resolution 6e-8 N, limit 8.4e6 N per
+// contribution); cotangents use 2^27 / 2^floor(log2 max|af|) per environment and substep.  A contribution that is
+// not representable (NaN, Inf, beyond the limit) raises the body's poison bit instead and the sum reads back NaN.
+// =====================================================================================
+constexpr int kFxLowBits = 21;
+constexpr float kFxLimit = 140737488355328.0f;      // 2^47
+constexpr float kFxForward = 16777216.0f;           // 2^24
+constexpr float kFxForwardInv = 1.0f / 16777216.0f;
+constexpr int kFxAdjointLog2 = 27;
+
+// the low words can live in the (still all-zero) fp32 destination array itself; the high words have their own array.
+// Split in fp32: x = w * scale (exact, power-of-two scale), h = rint(x / 2^21), l = x - h * 2^21 (exact: fma),
+// so that hi * 2^21 + rint(l) == rint(x) with |rint(l)| <= 2^20, using 32-bit conversions only.
+template <int N, class Grp>
+DFX_HD void fx_scatter(int* lo, int* hi, unsigned* poison, int body, const float (&w)[N], float scale, const Grp& g) {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < N; ++c) ok = ok && (fabsf(w[c] * scale) < kFxLimit);     // false for NaN / Inf / out of range
+    if (!ok) { g.atomic_or(poison, 1u << (body & 31)); return; }
+    constexpr float kUnit = (float)(1 << kFxLowBits), kUnitInv = 1.0f / (float)(1 << kFxLowBits);
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const float x = w[c] * scale;
+        const float h = rintf(x * kUnitInv);
+        const int l = (int)rintf(fmaf(h, -kUnit, x));
+        const int hw = (int)h;
+        if (l != 0) g.fx_add(lo + c, l);
+        if (hw != 0) g.fx_add(hi + c, hw);
+    }
+}
+// the fp32 value of an accumulator (two roundings at most; exact whenever |hi| < 2^24 and |lo| < 2^24)
+DFX_HD float fx_value(int lo, int hi, float inv_scale) {
+    return fmaf((float)hi, (float)(1 << kFxLowBits) * inv_scale, (float)lo * inv_scale);
+}
+// 2^(kFxAdjointLog2 - floor(log2 m)): the largest incoming cotangent maps to [2^27, 2^28); contact / muscle
+// cotangents may be up to 2^20 times larger than that before they poison
+DFX_HD float fx_pow2_scale(float m) {
+    if (!(m > 0.0f)) return 1.0f;
+    unsigned bits;
+#if defined(__CUDA_ARCH__)
+    bits = __float_as_uint(m);
+#else
+    memcpy(&bits, &m, 4);
+#endif
+    int field = (254 + kFxAdjointLog2) - (int)((bits >> 23) & 0xffu);
+    field = field > 254 ? 254 : (field < 1 ? 1 : field);
+    bits = (unsigned)field << 23;
+    float r;
+#if defined(__CUDA_ARCH__)
+    r = __uint_as_float(bits);
+#else
+    memcpy(&r, &bits, 4);
+#endif
+    return r;
+}
+
+// =====================================================================================
 // penalty ground contact (y-up plane), smooth Coulomb friction
 // =====================================================================================
 DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int k) {
@@ -393,37 +459,48 @@ DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int 
     return SV{cross(p, ftot), ftot};
 }
 
+// contact + muscle wrenches are scattered into the fixed-point accumulators; wrench_collect() adds them to body_f_s
 template <class Grp>
 DFX_HD void contact_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     if (!P.ground) return;
-    // bodies with at least one penetrating point are flagged in a bit mask (L <= 32) so that the per-body
-    // gather below touches only those; the summation order inside a body is still the contact order
-    unsigned* mask = reinterpret_cast<unsigned*>(s + Y.cmask);
-    const bool use_mask = P.L <= 32;
+    int* lo = reinterpret_cast<int*>(s + Y.fx);
+    int* hi = lo + P.L * 6;
+    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
     DFX_FOR(k, P.C) {
         const SV w = contact_point_fwd(P, Y, s, k);
-        st6(s + Y.cw + k * 6, w);
-        if (use_mask && (w.v.x != 0.0f || w.v.y != 0.0f || w.v.z != 0.0f || w.w.x != 0.0f || w.w.y != 0.0f || w.w.z != 0.0f))
-            g.atomic_or(mask, 1u << P.cbody[k]);
+        if (w.v.x != 0.0f || w.v.y != 0.0f || w.v.z != 0.0f || w.w.x != 0.0f || w.w.y != 0.0f || w.w.z != 0.0f)
+        {
+            const float c6[6] = {w.w.x, w.w.y, w.w.z, w.v.x, w.v.y, w.v.z};
+            fx_scatter(lo + P.cbody[k] * 6, hi + P.cbody[k] * 6, poison, P.cbody[k], c6, kFxForward, g);
+        }
     }
+}
+
+template <class Grp>
+DFX_HD void wrench_collect(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+    if (!P.ground && P.M == 0) return;
     g.sync();
-    const unsigned active = use_mask ? *mask : 0xffffffffu;
+    int* lo = reinterpret_cast<int*>(s + Y.fx);
+    int* hi = lo + P.L * 6;
+    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const unsigned bad = *poison;
     DFX_FOR(it, P.L * 6) {
-        const int i = it / 6, c = it - i * 6;
-        if (!((active >> (i & 31)) & 1u)) continue;
-        float acc = s[Y.f + it];
-        for (int k = P.cbody_start[i]; k < P.cbody_start[i + 1]; ++k) acc += s[Y.cw + k * 6 + c];
-        s[Y.f + it] = acc;
+        const int l = lo[it], h = hi[it];
+        if ((l | h) != 0) { s[Y.f + it] += fx_value(l, h, kFxForwardInv); lo[it] = 0; hi[it] = 0; }
+    }
+    if (bad) {
+        DFX_FOR(it, P.L * 6) { if ((bad >> ((it / 6) & 31)) & 1u) s[Y.f + it] = nanf(""); }
+        g.sync();
+        if (g.lane == 0) *poison = 0u;
     }
     g.sync();
-    if (g.lane == 0) *mask = 0u;
 }
 
 // adjoint for one contact: cotangent r = af[body]; accumulates into aXsc[body], av[body] with shared-memory
 // atomics (only penetrating contacts do any work; the summation order, hence the last bits of the
 // GRADIENT, may vary between runs -- the forward pass stays deterministic)
 template <class Grp>
-DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, const Grp& g) {
+DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, float scale, const Grp& g) {
     const int b = P.cbody[k];
     const Xf X = ld7(s + Y.Xsc + b * 7);
     const SV vs = ld6(s + Y.v + b * 6);
@@ -477,19 +554,64 @@ DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, c
     cross_adj(vs.w, p, adpdt, aw, ap);
     // p = X.p + R(X.q) pt - n d
     const Q4 aq = qrot_adj_q(X.q, pt, ap);
-    float* ax = s + Y.aXsc + b * 7;
-    float* avp = s + Y.av + b * 6;
-    g.atomic_add(ax + 0, ap.x); g.atomic_add(ax + 1, ap.y); g.atomic_add(ax + 2, ap.z);
-    g.atomic_add(ax + 3, aq.x); g.atomic_add(ax + 4, aq.y); g.atomic_add(ax + 5, aq.z); g.atomic_add(ax + 6, aq.w);
-    g.atomic_add(avp + 0, aw.x); g.atomic_add(avp + 1, aw.y); g.atomic_add(avp + 2, aw.z);
-    g.atomic_add(avp + 3, adpdt.x); g.atomic_add(avp + 4, adpdt.y); g.atomic_add(avp + 5, adpdt.z);
+    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const float c7[7] = {ap.x, ap.y, ap.z, aq.x, aq.y, aq.z, aq.w};
+    const float c6[6] = {aw.x, aw.y, aw.z, adpdt.x, adpdt.y, adpdt.z};
+    if (P.M > 0) {
+        // muscle models scatter everything in fixed point: low words accumulate in aXsc / av themselves (both are
+        // still all-zero in this phase), high words in fxH; adj_collect() converts back
+        int* hi = reinterpret_cast<int*>(s + Y.fxH);
+        fx_scatter(reinterpret_cast<int*>(s + Y.aXsc) + b * 7, hi + b * 7, poison, b, c7, scale, g);
+        fx_scatter(reinterpret_cast<int*>(s + Y.av) + b * 6, hi + P.L * 7 + b * 6, poison, b, c6, scale, g);
+    } else {
+        // contact-only models: at most a handful of penetrating points share a body, and the compare-and-swap
+        // float add is then 8-12 % cheaper for the whole adjoint than fixed point + read-back (same-box A/B, Ant
+        // and Humanoid).  The order of these few adds is not fixed, so the last bits of the gradient may vary.
+        float* ax = s + Y.aXsc + b * 7;
+        float* avp = s + Y.av + b * 6;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) g.atomic_add(ax + c, c7[c]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) g.atomic_add(avp + c, c6[c]);
+    }
+}
+
+// power-of-two fixed-point scale of the cotangent scatter of this environment and substep, from max|af|
+template <class Grp>
+DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, const float* s, const Grp& g) {
+    float m = 0.0f;
+    DFX_FOR(i, P.L * 6) { const float v = fabsf(s[Y.af + i]); m = (v > m) ? v : m; }   // NaN never wins: the poison bit handles it
+    return fx_pow2_scale(g.group_max(m));
 }
 
 template <class Grp>
-DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
-    if (!P.ground) return;
-    DFX_FOR(k, P.C) contact_point_adj(P, Y, s, k, g);
+DFX_HD void adj_collect(const Pack& P, const Layout& Y, float* s, float scale, const Grp& g) {
     g.sync();
+    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    int* hi = reinterpret_cast<int*>(s + Y.fxH);
+    const unsigned bad = *poison;
+    const float inv = 1.0f / scale;
+    float* dst = s + Y.aXsc;                       // aXsc (L,7) and av (L,6) are adjacent
+    DFX_FOR(it, P.L * 13) {
+        int l; memcpy(&l, dst + it, 4);
+        const int h = hi[it];
+        if ((l | h) != 0) { dst[it] = fx_value(l, h, inv); hi[it] = 0; }
+    }
+    if (bad) {
+        DFX_FOR(it, P.L * 13) {
+            const int body = (it < P.L * 7) ? it / 7 : (it - P.L * 7) / 6;
+            if ((bad >> (body & 31)) & 1u) dst[it] = nanf("");
+        }
+        g.sync();
+        if (g.lane == 0) *poison = 0u;
+    }
+    g.sync();
+}
+
+template <class Grp>
+DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, float scale, const Grp& g) {
+    if (!P.ground) return;
+    DFX_FOR(k, P.C) contact_point_adj(P, Y, s, k, scale, g);
 }
 
 // =====================================================================================
@@ -498,6 +620,9 @@ DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) 
 template <class Grp>
 DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     if (P.M == 0) return;
+    int* lo = reinterpret_cast<int*>(s + Y.fx);
+    int* hi = lo + P.L * 6;
+    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
     DFX_FOR(m, P.M) {
         const float act = s[Y.musc + m];
         for (int i = P.mstart[m]; i < P.mstart[m + 1] - 1; ++i) {
@@ -510,20 +635,20 @@ DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
             const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
             const V3 f = n * act;
             const V3 t0 = cross(p0, f), t1 = cross(p1, f);
-            float* f0 = s + Y.f + l0 * 6;
-            float* f1 = s + Y.f + l1 * 6;
-            g.atomic_add(f0 + 0, -t0.x); g.atomic_add(f0 + 1, -t0.y); g.atomic_add(f0 + 2, -t0.z);
-            g.atomic_add(f0 + 3, -f.x);  g.atomic_add(f0 + 4, -f.y);  g.atomic_add(f0 + 5, -f.z);
-            g.atomic_add(f1 + 0, t1.x);  g.atomic_add(f1 + 1, t1.y);  g.atomic_add(f1 + 2, t1.z);
-            g.atomic_add(f1 + 3, f.x);   g.atomic_add(f1 + 4, f.y);   g.atomic_add(f1 + 5, f.z);
+            const float w0[6] = {-t0.x, -t0.y, -t0.z, -f.x, -f.y, -f.z};
+            const float w1[6] = {t1.x, t1.y, t1.z, f.x, f.y, f.z};
+            fx_scatter(lo + l0 * 6, hi + l0 * 6, poison, l0, w0, kFxForward, g);
+            fx_scatter(lo + l1 * 6, hi + l1 * 6, poison, l1, w1, kFxForward, g);
         }
     }
-    g.sync();
 }
 
 template <class Grp>
-DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, float scale, const Grp& g) {
     if (P.M == 0) return;
+    int* lo = reinterpret_cast<int*>(s + Y.aXsc);   // still all-zero in this phase: doubles as the low words
+    int* hi = reinterpret_cast<int*>(s + Y.fxH);
+    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
     DFX_FOR(m, P.M) {
         const float act = s[Y.musc + m];
         float aact = 0.0f;
@@ -550,16 +675,13 @@ DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
                 ap0 -= ad;
             }
             const Q4 aq0 = qrot_adj_q(X0.q, r0, ap0), aq1 = qrot_adj_q(X1.q, r1, ap1);
-            float* a0 = s + Y.aXsc + l0 * 7;
-            float* a1 = s + Y.aXsc + l1 * 7;
-            g.atomic_add(a0 + 0, ap0.x); g.atomic_add(a0 + 1, ap0.y); g.atomic_add(a0 + 2, ap0.z);
-            g.atomic_add(a0 + 3, aq0.x); g.atomic_add(a0 + 4, aq0.y); g.atomic_add(a0 + 5, aq0.z); g.atomic_add(a0 + 6, aq0.w);
-            g.atomic_add(a1 + 0, ap1.x); g.atomic_add(a1 + 1, ap1.y); g.atomic_add(a1 + 2, ap1.z);
-            g.atomic_add(a1 + 3, aq1.x); g.atomic_add(a1 + 4, aq1.y); g.atomic_add(a1 + 5, aq1.z); g.atomic_add(a1 + 6, aq1.w);
+            const float g0[7] = {ap0.x, ap0.y, ap0.z, aq0.x, aq0.y, aq0.z, aq0.w};
+            const float g1[7] = {ap1.x, ap1.y, ap1.z, aq1.x, aq1.y, aq1.z, aq1.w};
+            fx_scatter(lo + l0 * 7, hi + l0 * 7, poison, l0, g0, scale, g);
+            fx_scatter(lo + l1 * 7, hi + l1 * 7, poison, l1, g1, scale, g);
         }
         s[Y.amusc + m] += aact;
     }
-    g.sync();
 }
 
 // =====================================================================================
@@ -949,6 +1071,7 @@ DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_m
     body_force_fwd(P, Y, s, g);
     contact_fwd(P, Y, s, g);
     muscle_fwd(P, Y, s, g);
+    wrench_collect(P, Y, s, g);
     tau_fwd(P, Y, s, g);
     if (update_mass) {
         crba_fwd(P, Y, s, g);
@@ -962,7 +1085,7 @@ DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_m
 // aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
 template <class Grp>
 DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool apply_crba, const Grp& g) {
-    zero_range(s + Y.aXsc, Y.af - Y.aXsc, g);      // aXsc, aXsm, aS, av, aa are adjacent (af is overwritten by tau_adj)
+    zero_range(s + Y.aXsc, Y.af - Y.aXsc, g);      // aXsc, av, aXsm, aS, aa are adjacent (af is overwritten by tau_adj)
     zero_range(s + Y.aIbar, P.L * 12, g);
     g.sync();
     // phase_sync(): CTA-wide barrier that keeps the warps of a CTA inside the same phase, so that the
@@ -973,8 +1096,16 @@ DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool
     if (apply_crba) crba_adj(P, Y, s, g);
     tau_adj(P, Y, s, s + Y.tau, g);
     g.phase_sync();
-    muscle_adj(P, Y, s, g);
-    contact_adj(P, Y, s, g);
+    if (P.M > 0) {
+        // muscles (and the contacts of a muscle model) scatter their cotangents in fixed point: deterministic sums
+        const float scale = adj_scatter_scale(P, Y, s, g);
+        muscle_adj(P, Y, s, scale, g);
+        contact_adj(P, Y, s, scale, g);
+        adj_collect(P, Y, s, scale, g);
+    } else if (P.ground) {
+        contact_adj(P, Y, s, 1.0f, g);
+        g.sync();
+    }
     g.phase_sync();
     body_force_adj(P, Y, s, g);
     g.phase_sync();

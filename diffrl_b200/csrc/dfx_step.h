@@ -54,6 +54,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
     DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
     for (int i = Y.qdd + D + g.lane; i < Y.q + Y.tape_row; i += Grp::G) s[i] = 0.0f;   // row padding
     if (g.lane == 0) s[Y.cmask] = 0.0f;
+    DFX_FOR(i, P.L * 12) s[Y.fx + i] = 0.0f;   // fixed-point wrench accumulators (L x 6 low + high words)
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
@@ -63,6 +64,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
         g.phase_sync();
         contact_fwd(P, Y, s, g);
         muscle_fwd(P, Y, s, g);
+        wrench_collect(P, Y, s, g);
         g.phase_sync();
         tau_fwd(P, Y, s, g);
         g.phase_sync();
@@ -96,6 +98,8 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, float* s, const Gr
     const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
     DFX_FOR(i, D) { s[Y.act + i] = a.act[(long long)env * D + i]; s[Y.aact + i] = 0.0f; }
     DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
+    if (g.lane == 0) s[Y.cmask] = 0.0f;
+    if (P.M > 0) DFX_FOR(i, P.L * 13) s[Y.fxH + i] = 0.0f;  // high words of the fixed-point cotangent accumulators
     DFX_FOR(i, Q) s[Y.aq + i] = a.gq_out ? a.gq_out[(long long)env * Q + i] : 0.0f;
     DFX_FOR(i, D) s[Y.aqd + i] = a.gqd_out ? a.gqd_out[(long long)env * D + i] : 0.0f;
     for (int sub = a.substeps - 1; sub >= 0; --sub) {

@@ -170,6 +170,10 @@ int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, con
 int dfx_set_group_size(int lanes);
 /* Tuning flags (default 3): bit 1 = CTA-wide phase barriers (instruction-cache locality). */
 int dfx_set_flags(int flags);
+/* Launch geometry the step kernel would use for this pack (host arithmetic, no GPU needed):
+ * out[0] lanes per environment, out[1] environments per CTA, out[2] CTAs per SM (shared-memory / register bound),
+ * out[3] dynamic shared memory per CTA in bytes, out[4] scratch floats per environment, out[5] staged pack bytes. */
+int dfx_launch_plan(const dfx_pack_t* pack, int backward, int out[6]);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 long long dfx_launch_count(void);
 const char* dfx_version(void);

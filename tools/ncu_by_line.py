@@ -31,8 +31,10 @@ for ln in dis.splitlines():
 # ---- ncu per-instruction rows
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-want = {"ILi8ELb0": "(int)8, (bool)0", "ILi16ELb0": "(int)16, (bool)0", "ILi32ELb0": "(int)32, (bool)0",
-        "ILi8ELb1": "(int)8, (bool)1", "ILi16ELb1": "(int)16, (bool)1", "ILi32ELb1": "(int)32, (bool)1"}[ksub]
+# ksub is a mangled-name fragment such as ILi16ELb0 or ILi32ELb1ELi11; translate to the demangled fragment
+import re as _re
+nums = _re.findall(r"L([ib])(\d+)E", ksub)
+want = ", ".join(("(int)%s" % v) if t == "i" else ("(bool)%s" % v) for t, v in nums)
 i = 0
 sect = None
 while i < len(rows):
