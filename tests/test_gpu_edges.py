@@ -105,3 +105,86 @@ def test_cartpole_has_no_contacts_and_fixed_root():
     t = lambda a: torch.tensor(a.ravel(), device="cuda:0")
     q, qd, _, _ = eng.forward(t(q0), t(qd0), t(act), None, S, mm, dt, want_tape=False)
     assert rel(q.cpu().numpy(), eq) < 1e-5 and rel(qd.cpu().numpy(), eqd) < 1e-5
+
+
+def _snu_case(N, seed=3):
+    import torch
+    d, model = load_golden("SNUHumanoidEnv")
+    n0 = int(d["meta/num_envs"])
+    emu = EmuSim(model, n0)
+    Q, D, M = emu.desc.Q, emu.desc.D, emu.desc.M
+    rng = np.random.default_rng(seed)
+    p = "case%d/" % (int(d["meta/num_cases"]) - 1)
+    pick = rng.integers(0, n0, N)
+    t = lambda a: torch.tensor(np.ascontiguousarray(a, np.float32).ravel(), device="cuda:0")
+    q0, qd0 = d[p + "q0"].reshape(n0, Q)[pick], d[p + "qd0"].reshape(n0, D)[pick]
+    act = d[p + "act"].reshape(n0, D)[pick]
+    musc = np.clip(d[p + "musc"].reshape(n0, M)[pick] * rng.uniform(0.5, 1.5, (N, M)), 0.0, 1.0)
+    return d, emu, t(q0), t(qd0), t(act), t(musc)
+
+
+def test_muscle_model_scatter_is_bit_reproducible():
+    """152 muscles and 88 contact points scatter wrenches / cotangents into 11 bodies through the fixed-point
+    accumulators (dfx_phases.h): integer sums do not depend on the order of the atomics, so forward AND
+    backward results are bit-identical from run to run (and agree across group widths)."""
+    import torch
+    from diffrl_b200 import _capi
+    from diffrl_b200.engine import ArticulationEngine
+    N = 64
+    d, emu, q0, qd0, act, musc = _snu_case(N)
+    S, mm, dt = int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    eng = ArticulationEngine(emu.desc, N, "cuda:0")
+    gq, gqd = torch.ones_like(q0), torch.ones_like(qd0)
+    outs = []
+    try:
+        for grp in (32, 32, 16, 32):
+            _capi.lib().dfx_set_group_size(grp)
+            q, qd, tape, _ = eng.forward(q0, qd0, act, musc, S, mm, dt)
+            g = eng.backward(act, musc, tape, gq, gqd, S, mm, dt)
+            outs.append([x.clone() for x in (q, qd, tape) + tuple(g)])
+    finally:
+        _capi.lib().dfx_set_group_size(0)
+    for other in (outs[1], outs[3]):
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+    for a, b in zip(outs[0][:2] + outs[0][3:], outs[2][:2] + outs[2][3:]):   # 16 lanes: same sums, other lane mapping
+        assert rel(b.cpu().numpy(), a.cpu().numpy()) < 5e-5
+    assert all(torch.isfinite(x).all() for x in outs[0])
+
+
+def test_non_finite_contribution_poisons_the_sum():
+    """A NaN activation cannot be represented in the fixed-point accumulators: it must surface as NaN in the
+    state of THAT environment (poison bit), never be dropped, and must not leak into its CTA neighbours."""
+    import torch
+    from diffrl_b200.engine import ArticulationEngine
+    N = 8
+    d, emu, q0, qd0, act, musc = _snu_case(N)
+    S, mm, dt = int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    eng = ArticulationEngine(emu.desc, N, "cuda:0")
+    ref_q, ref_qd, _, _ = eng.forward(q0, qd0, act, musc, S, mm, dt, want_tape=False)
+    bad = musc.clone().view(N, -1)
+    bad[3, 17] = float("nan")
+    q, qd, _, _ = eng.forward(q0, qd0, act, bad.reshape(-1), S, mm, dt, want_tape=False)
+    qd, ref_qd = qd.view(N, -1), ref_qd.view(N, -1)
+    assert torch.isnan(qd[3]).any()
+    keep = [i for i in range(N) if i != 3]
+    assert torch.equal(qd[keep], ref_qd[keep])
+    huge = musc.clone().view(N, -1)
+    huge[5, :] = 1.0e30                      # beyond the accumulator range: loud, not wrapped around
+    q, qd, _, _ = eng.forward(q0, qd0, act, huge.reshape(-1), S, mm, dt, want_tape=False)
+    assert not torch.isfinite(qd.view(N, -1)[5]).all()
+    assert torch.equal(qd.view(N, -1)[[0, 1, 2, 4, 6, 7]], ref_qd[[0, 1, 2, 4, 6, 7]])
+
+
+def test_launch_plan_keeps_a_full_wave_of_ant_resident():
+    """4096 Ant environments fit one wave of CTAs on 148 SMs (forward and adjoint): DESIGN.md section 4."""
+    from diffrl_b200.engine import ArticulationEngine
+    d, emu, *_ = _case("AntEnv", 1)
+    eng = ArticulationEngine(emu.desc, 1, "cuda:0")
+    for bwd in (0, 1):
+        out = (ctypes.c_int * 6)()
+        assert eng.lib.dfx_launch_plan(eng.pack, bwd, out) == 0
+        lanes, envs_per_cta, ctas_per_sm, smem, stride, pack = list(out)
+        assert lanes == 16 and envs_per_cta * lanes <= 128
+        assert envs_per_cta * ctas_per_sm * 148 >= 4096
+        assert smem == pack + envs_per_cta * stride * 4 and (smem + 1024) * ctas_per_sm <= 227 * 1024
