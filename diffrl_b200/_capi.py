@@ -48,6 +48,8 @@ def lib():
                                    _F, _F, _F, _F, _F, _F, _F, ctypes.POINTER(DfxDerived), ctypes.c_void_p]
     L.dfx_step_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                     _F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_void_p]
+    if os.environ.get("DFX_FLAGS"):      # tuning flags of include/dfx.h (A/B runs of the test-suite)
+        L.dfx_set_flags(int(os.environ["DFX_FLAGS"]))
     _lib = L
     return L
 

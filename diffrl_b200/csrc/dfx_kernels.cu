@@ -38,6 +38,68 @@ struct GroupCuda {
         for (int o = G_ / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, G_));
         return v;
     }
+    // CTA-wide task loop (dfx_phases.h level_tasks): (k, env) pairs, k-major, over the threads of the CTA.  The
+    // leading barrier publishes what the lane groups wrote with tile-level syncs only; the trailing one hands
+    // the results back.  Co-resident CTAs start their task warps on different schedulers (rot).
+    float* scratch0;
+    int stride, envs_shift;
+    bool cta_mode;
+    template <class F>
+    __device__ __forceinline__ void cta_tasks(float* s, int n, bool lead, F f) const {
+        if (!cta_mode) {
+            for (int k = lane; k < n; k += G_) f(s, k);
+            __syncwarp(mask);
+            return;
+        }
+        if (lead) __syncthreads();
+        const int total = n << envs_shift;
+        int t = (int)threadIdx.x - (int)(((blockIdx.x & 3u) << 5) & (blockDim.x - 1));   // blockDim.x is 32, 64 or 128
+        if (t < 0) t += blockDim.x;
+        for (; t < total; t += blockDim.x) {
+            const int k = t >> envs_shift, e = t - (k << envs_shift);
+            f(scratch0 + e * stride, k);
+        }
+        __syncthreads();
+    }
+    // cta_tasks() over the (k, env) pairs that satisfy pred(): the predicate is evaluated for all pairs (cheap),
+    // the hits are compacted into a CTA-wide list (warp-aggregated atomic append), and f() then runs over the list
+    // with full warps.  The order of the list varies from run to run; callers accumulate order-independently.
+    int* task_count;     // [2] (double-buffered by phase parity is not needed: barriers separate uses)
+    int* task_list;      // [n_max * envs]
+    template <class Pr, class F>
+    __device__ __forceinline__ void cta_compact(float* s, int n, Pr pred, F f) const {
+        if (!cta_mode) {
+            for (int k = lane; k < n; k += G_) if (pred(s, k)) f(s, k);
+            __syncwarp(mask);
+            return;
+        }
+        if (threadIdx.x == 0) *task_count = 0;
+        __syncthreads();
+        const int total = n << envs_shift;
+        const int lane32 = threadIdx.x & 31;
+        for (int t0 = (int)threadIdx.x - lane32; t0 < total; t0 += blockDim.x) {   // warp-uniform trip count
+            const int t = t0 + lane32;
+            bool hit = false;
+            if (t < total) { const int k = t >> envs_shift, e = t - (k << envs_shift); hit = pred(scratch0 + e * stride, k); }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                int base = 0;
+                if (lane32 == 0) base = atomicAdd(task_count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) task_list[base + __popc(m & ((1u << lane32) - 1u))] = t;
+            }
+        }
+        __syncthreads();
+        const int hits = *task_count;
+        int i = (int)threadIdx.x - (int)(((blockIdx.x & 3u) << 5) & (blockDim.x - 1));
+        if (i < 0) i += blockDim.x;
+        for (; i < hits; i += blockDim.x) {
+            const int t = task_list[i];
+            const int k = t >> envs_shift, e = t - (k << envs_shift);
+            f(scratch0 + e * stride, k);
+        }
+        __syncthreads();
+    }
     // cp.async (LDGSTS) 16-byte copies, one commit group per row
     __device__ __forceinline__ void copy_row_async(float* dst, const float* src, int n) const {
         const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -91,6 +153,7 @@ struct KernelArgs {
     StepArgs step;
     int scratch_stride;   // floats per environment
     int pack_smem_floats; // floats reserved at the start of dynamic smem for the staged pack
+    int cta_area_floats;  // then: CTA-wide task counter + task list (cta_compact)
 };
 
 // SL..SM > 0: model sizes known at compile time (the six DiffRL articulations are pre-instantiated); the scratch
@@ -123,7 +186,13 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
     g.lane = threadIdx.x % G;
     g.psync = (ka.step.flags & 2) != 0;
     g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane_in_warp / G) * G));
-    float* s = smem + ka.pack_smem_floats + (size_t)local * ka.scratch_stride;
+    float* s = smem + ka.pack_smem_floats + ka.cta_area_floats + (size_t)local * ka.scratch_stride;
+    g.scratch0 = smem + ka.pack_smem_floats + ka.cta_area_floats;
+    g.task_count = reinterpret_cast<int*>(smem + ka.pack_smem_floats);
+    g.task_list = g.task_count + 4;
+    g.stride = ka.scratch_stride;
+    g.envs_shift = 31 - __clz(kEnvsPerCta > 0 ? kEnvsPerCta : 1);
+    g.cta_mode = (ka.step.flags & 8) != 0;
     if (BACKWARD) env_step_backward(P, Y, s, g, env, ka.step);
     else env_step_forward(P, Y, s, g, env, ka.step);
 }
@@ -147,7 +216,7 @@ struct dfx_pack {
 static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
-static int g_flags = 3;   // bit 1: phase barriers; bit 2: DISABLE the size-specialised kernels (A/B testing)
+static int g_flags = 11;  // bit 1: phase barriers; bit 2: DISABLE the size-specialised kernels (A/B testing); bit 3: CTA-wide task loops
 
 static void set_err(char* err, int n, const std::string& m) {
     if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
@@ -220,9 +289,13 @@ long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq)
 
 // launch geometry of one step kernel (host arithmetic only, also exported through dfx_launch_plan)
 struct LaunchPlan {
-    int scratch_stride, pack_bytes, envs_per_cta, ctas_per_sm;
+    int scratch_stride, pack_bytes, cta_area_bytes, envs_per_cta, ctas_per_sm;
     size_t smem;
 };
+// CTA-wide area: task counter (16 bytes) + one list slot per (contact point, environment)
+static int cta_area(const dfx_pack* p, int envs_per_cta) {
+    return 16 + ((p->header.C * envs_per_cta * 4 + 15) & ~15);
+}
 static LaunchPlan plan_launch(const dfx_pack* p, int G, bool bwd) {
     LaunchPlan lp{};
     const int per_env = bwd ? p->host.layout.bwd_size : p->host.layout.fwd_size;
@@ -236,7 +309,7 @@ static LaunchPlan plan_launch(const dfx_pack* p, int G, bool bwd) {
     int best = -1;
     for (int threads = kMaxThreads; threads >= 32 && threads >= G; threads /= 2) {
         const int e = threads / G;
-        const size_t bytes = (size_t)lp.pack_bytes + (size_t)e * lp.scratch_stride * sizeof(float) + 1024;
+        const size_t bytes = (size_t)lp.pack_bytes + cta_area(p, e) + (size_t)e * lp.scratch_stride * sizeof(float) + 1024;
         if (bytes > 227 * 1024) continue;
         int ctas = (int)((227 * 1024) / bytes);
         const int by_regs = 65536 / (regs_per_thread * threads);
@@ -244,7 +317,8 @@ static LaunchPlan plan_launch(const dfx_pack* p, int G, bool bwd) {
         if (ctas > 32) ctas = 32;
         if (ctas * e > best) { best = ctas * e; lp.envs_per_cta = e; lp.ctas_per_sm = ctas; }
     }
-    lp.smem = (size_t)lp.pack_bytes + (size_t)lp.envs_per_cta * lp.scratch_stride * sizeof(float);
+    lp.cta_area_bytes = cta_area(p, lp.envs_per_cta);
+    lp.smem = (size_t)lp.pack_bytes + lp.cta_area_bytes + (size_t)lp.envs_per_cta * lp.scratch_stride * sizeof(float);
     return lp;
 }
 
@@ -258,6 +332,7 @@ static cudaError_t launch_impl(const dfx_pack* p, const StepArgs& step, cudaStre
     const LaunchPlan lp = plan_launch(p, G, BWD);
     ka.scratch_stride = lp.scratch_stride;
     ka.pack_smem_floats = lp.pack_bytes / 4;
+    ka.cta_area_floats = lp.cta_area_bytes / 4;
     const int envs_per_cta = lp.envs_per_cta;
     if (envs_per_cta == 0) return cudaErrorInvalidConfiguration;
     const size_t smem = lp.smem;
@@ -309,7 +384,7 @@ int dfx_launch_plan(const dfx_pack_t* p, int backward, int out[6]) {
     const int G = pick_group(p);
     const LaunchPlan lp = plan_launch(p, G, backward != 0);
     out[0] = G; out[1] = lp.envs_per_cta; out[2] = lp.ctas_per_sm; out[3] = (int)lp.smem;
-    out[4] = lp.scratch_stride; out[5] = lp.pack_bytes;
+    out[4] = lp.scratch_stride; out[5] = lp.pack_bytes + lp.cta_area_bytes;
     return 0;
 }
 

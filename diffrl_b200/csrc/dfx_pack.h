@@ -70,7 +70,7 @@ struct Layout {
     // primal
     int q, qd, act, musc, tau, qdd, Xl, vj;
     int Xsc, Xsm, S, v, a, f, ft;
-    int cmask, fx, fxH;   // poison bits + int64 fixed-point accumulators of the deterministic scatter-adds
+    int cmask, fxs, fx, fxH;   // poison bits + int64 fixed-point accumulators of the deterministic scatter-adds
     int A;     // H, then H^-1 (D,D)
     int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
     int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
@@ -104,6 +104,7 @@ DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M) {
     y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
     y.A = DFX_TAKE(D * D); y.Lm = DFX_TAKE(D * D);
     y.cmask = DFX_TAKE(1);               // poison bits of the fixed-point scatter-adds (bit = body & 31)
+    y.fxs = DFX_TAKE(1);                 // fixed-point scale of the cotangent scatter of the current substep
     // ---- from here on the forward-only and the adjoint-only fields share the same region
     const int shared_end = o;
     y.Icmp = DFX_TAKE(L * 21 + D * 6);

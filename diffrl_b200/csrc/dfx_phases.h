@@ -18,7 +18,7 @@
 // deterministic gathers, and nothing but (q, qd) per substep is taped: the adjoint recomputes
 // the substep in scratch memory.
 //
-// `Grp` provides: static G, lane, sync(), fx_add(int*, int), atomic_add(float*, float), group_max(float), atomic_or(unsigned*, unsigned).
+// `Grp` provides: static G, lane, sync(), cta_tasks(), cta_compact(), fx_add(int*, int), atomic_add(float*, float), group_max(float), atomic_or(unsigned*, unsigned).
 #pragma once
 
 #include "dfx_math.h"
@@ -35,6 +35,12 @@ struct GroupSerial {  // host / single-lane execution
     DFX_HD void fx_add(int* p, int v) const { *p += v; }
     DFX_HD void atomic_add(float* p, float v) const { *p += v; }
     DFX_HD float group_max(float v) const { return v; }
+    // run f(scratch of env, k) for k in [0, n) for every environment the executing CTA holds (here: this one)
+    template <class F>
+    DFX_HD void cta_tasks(float* s, int n, bool lead, F f) const { (void)lead; for (int k = 0; k < n; ++k) f(s, k); }
+    // same, restricted to the (k, env) pairs for which pred() holds (compacted first)
+    template <class Pr, class F>
+    DFX_HD void cta_compact(float* s, int n, Pr pred, F f) const { for (int k = 0; k < n; ++k) if (pred(s, k)) f(s, k); }
     // asynchronous global -> scratch row copy (16-byte aligned, n a multiple of 4 floats)
     DFX_HD void copy_row_async(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
     DFX_HD void copy_wait_all() const {}
@@ -42,6 +48,18 @@ struct GroupSerial {  // host / single-lane execution
 };
 
 #define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
+
+// One level of a HEAVY tree recursion (the two leaf->root passes of the kinematics adjoint).  A level of a DiffRL
+// articulation holds 1-4 links, so a lane group of 16 or 32 runs it with most lanes idle; cta_tasks() instead spreads
+// the (link, environment) pairs of ALL the environments of the CTA over consecutive threads, link-major: a level
+// is then typically ONE warp with full lanes, uniform joint types and broadcast pack reads, at the price of a
+// CTA-wide barrier per level.  Measured (same box, Ant 4096): adjoint -8.5 %; the light forward recursions (one
+// transform product or two vector adds per level) lose more to the barriers than they gain and stay per group.
+template <class Grp, class F>
+DFX_HD void level_tasks(const Pack& P, float* s, int lev, bool lead, const Grp& g, F f) {
+    const int b = P.level_start[lev], e = P.level_start[lev + 1];
+    g.cta_tasks(s, e - b, lead, [&](float* se, int k) { f(se, P.level_links[b + k]); });
+}
 
 template <class Grp>
 DFX_HD void zero_range(float* p, int n, const Grp& g) {
@@ -244,18 +262,12 @@ template <class Grp>
 DFX_HD void kin_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     DFX_FOR(i, P.L) kin_adj_local(P, Y, s, i);
     g.sync();
-    for (int lev = P.nlev - 1; lev >= 0; --lev) {
-        const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) kin_adj_velocity(P, Y, s, P.level_links[k]);
-        g.sync();
-    }
+    for (int lev = P.nlev - 1; lev >= 0; --lev)
+        level_tasks(P, s, lev, lev == P.nlev - 1, g, [&](float* se, int i) { kin_adj_velocity(P, Y, se, i); });
     DFX_FOR(i, P.L) kin_adj_motion(P, Y, s, i);
     g.sync();
-    for (int lev = P.nlev - 1; lev >= 0; --lev) {
-        const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) kin_adj_chain(P, Y, s, P.level_links[k]);
-        g.sync();
-    }
+    for (int lev = P.nlev - 1; lev >= 0; --lev)
+        level_tasks(P, s, lev, lev == P.nlev - 1, g, [&](float* se, int i) { kin_adj_chain(P, Y, se, i); });
     DFX_FOR(i, P.L) kin_adj_joint(P, Y, s, i);
     g.sync();
 }
@@ -446,7 +458,7 @@ DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int 
     p.y -= P.cdist[k];
     const V3 dpdt = vs.v + cross(vs.w, p);
     const float c = p.y;
-    if (c >= 0.0f) return sv_zero();
+    if (c >= 0.0f) return sv_zero();     // (callers compact with contact_penetrates() first)
     const float vn = dpdt.y;
     const V3 vt = V3{dpdt.x, 0.0f, dpdt.z};
     const float fn = c * ke;
@@ -459,21 +471,26 @@ DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int 
     return SV{cross(p, ftot), ftot};
 }
 
-// contact + muscle wrenches are scattered into the fixed-point accumulators; wrench_collect() adds them to body_f_s
+// signed height of contact point k above the ground plane (negative: penetrating); NaN counts as penetrating
+// so that a non-finite state still reaches the poison bit
+DFX_HD bool contact_penetrates(const Pack& P, const Layout& Y, const float* s, int k) {
+    const V3 p = xf_point(ld7(s + Y.Xsc + P.cbody[k] * 7), ld3(P.cpoint + k * 3));
+    return !(p.y - P.cdist[k] >= 0.0f);
+}
+
+// contact + muscle wrenches are scattered into the fixed-point accumulators; wrench_collect() adds them to body_f_s.
+// Typically a fifth of the points penetrate: the (point, environment) pairs that do are compacted over the whole
+// CTA first, so the force model runs with full warps instead of a few lanes per group.
 template <class Grp>
 DFX_HD void contact_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     if (!P.ground) return;
-    int* lo = reinterpret_cast<int*>(s + Y.fx);
-    int* hi = lo + P.L * 6;
-    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
-    DFX_FOR(k, P.C) {
-        const SV w = contact_point_fwd(P, Y, s, k);
-        if (w.v.x != 0.0f || w.v.y != 0.0f || w.v.z != 0.0f || w.w.x != 0.0f || w.w.y != 0.0f || w.w.z != 0.0f)
-        {
-            const float c6[6] = {w.w.x, w.w.y, w.w.z, w.v.x, w.v.y, w.v.z};
-            fx_scatter(lo + P.cbody[k] * 6, hi + P.cbody[k] * 6, poison, P.cbody[k], c6, kFxForward, g);
-        }
-    }
+    g.cta_compact(s, P.C, [&](float* se, int k) { return contact_penetrates(P, Y, se, k); },
+                  [&](float* se, int k) {
+        const SV w = contact_point_fwd(P, Y, se, k);
+        int* lo = reinterpret_cast<int*>(se + Y.fx);
+        const float c6[6] = {w.w.x, w.w.y, w.w.z, w.v.x, w.v.y, w.v.z};
+        fx_scatter(lo + P.cbody[k] * 6, lo + P.L * 6 + P.cbody[k] * 6, reinterpret_cast<unsigned*>(se + Y.cmask), P.cbody[k], c6, kFxForward, g);
+    });
 }
 
 template <class Grp>
@@ -578,10 +595,12 @@ DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, f
 
 // power-of-two fixed-point scale of the cotangent scatter of this environment and substep, from max|af|
 template <class Grp>
-DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, const float* s, const Grp& g) {
+DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     float m = 0.0f;
     DFX_FOR(i, P.L * 6) { const float v = fabsf(s[Y.af + i]); m = (v > m) ? v : m; }   // NaN never wins: the poison bit handles it
-    return fx_pow2_scale(g.group_max(m));
+    const float scale = fx_pow2_scale(g.group_max(m));
+    if (g.lane == 0) s[Y.fxs] = scale;       // CTA-wide contact tasks of this environment read it from here
+    return scale;
 }
 
 template <class Grp>
@@ -609,9 +628,10 @@ DFX_HD void adj_collect(const Pack& P, const Layout& Y, float* s, float scale, c
 }
 
 template <class Grp>
-DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, float scale, const Grp& g) {
+DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
     if (!P.ground) return;
-    DFX_FOR(k, P.C) contact_point_adj(P, Y, s, k, scale, g);
+    g.cta_compact(s, P.C, [&](float* se, int k) { return contact_penetrates(P, Y, se, k); },
+                  [&](float* se, int k) { contact_point_adj(P, Y, se, k, se[Y.fxs], g); });
 }
 
 // =====================================================================================
@@ -1100,11 +1120,10 @@ DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool
         // muscles (and the contacts of a muscle model) scatter their cotangents in fixed point: deterministic sums
         const float scale = adj_scatter_scale(P, Y, s, g);
         muscle_adj(P, Y, s, scale, g);
-        contact_adj(P, Y, s, scale, g);
+        contact_adj(P, Y, s, g);
         adj_collect(P, Y, s, scale, g);
     } else if (P.ground) {
-        contact_adj(P, Y, s, 1.0f, g);
-        g.sync();
+        contact_adj(P, Y, s, g);
     }
     g.phase_sync();
     body_force_adj(P, Y, s, g);

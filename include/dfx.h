@@ -168,11 +168,12 @@ int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, con
 
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
-/* Tuning flags (default 3): bit 1 = CTA-wide phase barriers (instruction-cache locality). */
+/* Tuning flags (default 11): bit 1 (2) = CTA-wide phase barriers (instruction-cache locality); bit 2 (4) = generic
+ * kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases. */
 int dfx_set_flags(int flags);
 /* Launch geometry the step kernel would use for this pack (host arithmetic, no GPU needed):
  * out[0] lanes per environment, out[1] environments per CTA, out[2] CTAs per SM (shared-memory / register bound),
- * out[3] dynamic shared memory per CTA in bytes, out[4] scratch floats per environment, out[5] staged pack bytes. */
+ * out[3] dynamic shared memory per CTA in bytes, out[4] scratch floats per environment, out[5] bytes of the staged pack + CTA task list. */
 int dfx_launch_plan(const dfx_pack_t* pack, int backward, int out[6]);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 long long dfx_launch_count(void);

@@ -12,22 +12,29 @@ subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=t
 dis = ""
 for f in sorted(os.listdir(tmp)):
     if f.endswith(".cubin"):
-        dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-# ---- offset -> (file, line) for the chosen kernel
-off2line, cur, inside = {}, None, False
+        dis += subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+# ---- offset -> (file, line) of the innermost inlined function, and the whole inline chain, for the chosen kernel
+off2line, off2chain, cur, chain, inside, fresh = {}, {}, None, [], False, True
 for ln in dis.splitlines():
     if ln.startswith("//---") and ".text." in ln:
         inside = ksub in ln
         continue
     if not inside:
         continue
-    m = re.match(r'\s*//## File "(.*)", line (\d+)', ln)
+    m = re.match(r'\s*//## File "(.*?)", line (\d+)(?: inlined at "(.*?)", line (\d+))?', ln)
     if m:
-        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        if fresh:
+            chain, fresh = [], False
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        chain.append((os.path.basename(m.group(1)), int(m.group(2))))
+        if m.group(3):
+            chain.append((os.path.basename(m.group(3)), int(m.group(4))))
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
     if m:
         off2line[int(m.group(1), 16)] = cur
+        off2chain[int(m.group(1), 16)] = chain
+        fresh = True
 # ---- ncu per-instruction rows
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -70,6 +77,33 @@ def func_of(file, line):
         else:
             break
     return best
+PHASES = ["kin_fwd", "body_force_fwd", "contact_fwd", "muscle_fwd", "wrench_collect", "tau_fwd", "crba_fwd", "chol_inverse",
+          "solve_fwd", "integrate_fwd", "integrate_adj", "solve_adj", "crba_adj", "tau_adj", "muscle_adj", "contact_adj",
+          "adj_scatter_scale", "adj_collect", "body_force_adj", "kin_adj", "zero_range", "dump_derived"]
+def phase_of(chain):
+    names = [func_of(*c) for c in chain]
+    for nm in reversed(names):            # outermost first
+        if nm in PHASES:
+            return nm
+    for nm in reversed(names):
+        if nm.startswith("env_step") or nm.startswith("dfx_step_kernel") or nm in ("copy_row_async", "copy_row_out", "copy_wait_all"):
+            return nm
+    return names[-1] if names else "?"
+def subphase_of(chain):
+    """(phase, the function called directly from the phase body)"""
+    names = [func_of(*c) for c in chain]
+    for k in range(len(names) - 1, -1, -1):
+        if names[k] in PHASES:
+            child = names[k]
+            for j in range(k - 1, -1, -1):
+                if names[j] != names[k]:
+                    child = names[j]
+                    break
+            return names[k] + " > " + child
+    return phase_of(chain)
+by_sub, samp_sub, thr_sub = collections.Counter(), collections.Counter(), collections.Counter()
+by_phase, samp_phase, thr_phase = collections.Counter(), collections.Counter(), collections.Counter()
+stall_phase = collections.defaultdict(collections.Counter)
 by_line, by_func = collections.Counter(), collections.Counter()
 samp_line, samp_func, thr_func = collections.Counter(), collections.Counter(), collections.Counter()
 stall_func = collections.defaultdict(collections.Counter)
@@ -79,11 +113,24 @@ for r in body:
     loc = off2line.get(off) or ("?", 0)
     n, s, th = float(r[ie] or 0), float(r[isamp] or 0), float(r[ith] or 0)
     fn = func_of(*loc)
+    ph = phase_of(off2chain.get(off) or [])
+    by_phase[ph] += n; samp_phase[ph] += s; thr_phase[ph] += th
+    sp = subphase_of(off2chain.get(off) or [])
+    by_sub[sp] += n; samp_sub[sp] += s; thr_sub[sp] += th
+    for c in stall_cols:
+        stall_phase[ph][c] += float(r[hdr.index(c)] or 0)
     by_line[loc] += n; by_func[fn] += n; samp_line[loc] += s; samp_func[fn] += s; thr_func[fn] += th
     for c in stall_cols:
         stall_func[fn][c] += float(r[hdr.index(c)] or 0)
     tot += n; tots += s
 print("kernel %s: %.3g warp-instructions, %d samples" % (want, tot, tots))
+print("\n== by phase (outermost phase function on the inline chain): %inst  %samples  lanes/inst  top stalls")
+for fn, n in by_phase.most_common(30):
+    st = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(1, samp_phase[fn])) for k, v in stall_phase[fn].most_common(4))
+    print("%6.2f%% %6.2f%%  %5.1f  %-26s %s" % (100 * n / tot, 100 * samp_phase[fn] / max(1, tots), thr_phase[fn] / max(1, n), fn, st))
+print("\n== by phase > callee: %inst  %samples  lanes/inst")
+for fn, n in by_sub.most_common(40):
+    print("%6.2f%% %6.2f%%  %5.1f  %s" % (100 * n / tot, 100 * samp_sub[fn] / max(1, tots), thr_sub[fn] / max(1, n), fn))
 print("\n== by function: %inst  %samples  lanes/inst  top stalls")
 for fn, n in by_func.most_common(30):
     st = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(1, samp_func[fn])) for k, v in stall_func[fn].most_common(4))
