@@ -42,19 +42,15 @@ __device__ __forceinline__ float height_reward(const DfxWalkerParams& p, float h
     return r;
 }
 
-__global__ void walker_forward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
-                                      const float* __restrict__ actions, const long long* __restrict__ progress,
-                                      float* __restrict__ obs, float* __restrict__ rew, long long* __restrict__ reset) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const float* qe = q + (size_t)e * p.num_q;
-    const float* qde = qd + (size_t)e * p.num_qd;
-    const float* ae = actions + (size_t)e * p.num_act;
+// observation (always) and, when want_reward, reward + reset flag of ONE environment; `progress` is the step
+// counter AFTER this step.  `ae` == nullptr stands for all-zero actions (a freshly reset environment).
+__device__ __forceinline__ void walker_eval(const DfxWalkerParams& p, const float* __restrict__ qe, const float* __restrict__ qde,
+                                            const float* __restrict__ ae, long long progress, bool want_reward,
+                                            float* __restrict__ o, float* r_out, long long* rs_out) {
     V3 pos, ang, lin, tt, tdir, up, heading;
     Q4 rot, tq;
     float tn;
     walker_features(p, qe, qde, pos, rot, ang, lin, tt, tn, tdir, tq, up, heading);
-    float* o = obs + (size_t)e * p.num_obs;
     int k = 0;
     o[k++] = pos.y;
     o[k++] = rot.x; o[k++] = rot.y; o[k++] = rot.z; o[k++] = rot.w;
@@ -68,12 +64,12 @@ __global__ void walker_forward_kernel(DfxWalkerParams p, int n, const float* __r
     o[k++] = hproj;
     float act_sq = 0.0f, act_abs = 0.0f;
     for (int i = 0; i < p.num_act; ++i) {
-        const float a = ae[i];
+        const float a = ae ? ae[i] : 0.0f;
         if (p.obs_has_actions) o[k++] = a;
         act_sq += a * a;
         act_abs += fabsf(a);
     }
-    if (!rew) return;
+    if (!want_reward) return;
     float dh;
     const float hr = height_reward(p, pos.y, &dh);
     float r = lin.x + 0.1f * up_y + hproj;
@@ -81,33 +77,40 @@ __global__ void walker_forward_kernel(DfxWalkerParams p, int n, const float* __r
     r += (p.action_penalty_abs ? act_abs : act_sq) * p.action_penalty;
     long long rs = 0;
     if (p.early_termination && pos.y < p.termination_height) rs = 1;
-    if (progress[e] > (long long)p.episode_length - 1) rs = 1;
+    if (progress > (long long)p.episode_length - 1) rs = 1;
     if (p.check_invalid) {
         for (int i = 0; i < p.num_q; ++i) bad |= !isfinite(qe[i]) || fabsf(qe[i]) > 1e6f;
         for (int i = 0; i < p.num_qd; ++i) bad |= !isfinite(qde[i]) || fabsf(qde[i]) > 1e6f;
         for (int i = 0; i < p.num_obs; ++i) bad |= !isfinite(o[i]);
         if (bad) { rs = 1; if (p.zero_reward_on_invalid) r = 0.0f; }
     }
-    rew[e] = r;
-    reset[e] = rs;
+    *r_out = r;
+    *rs_out = rs;
 }
 
-__global__ void walker_backward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
-                                       const float* __restrict__ actions, const float* __restrict__ g_obs,
-                                       const float* __restrict__ g_rew, float* __restrict__ gq, float* __restrict__ gqd,
-                                       float* __restrict__ gact) {
+__global__ void walker_forward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                      const float* __restrict__ actions, const long long* __restrict__ progress,
+                                      float* __restrict__ obs, float* __restrict__ rew, long long* __restrict__ reset) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    const float* qe = q + (size_t)e * p.num_q;
-    const float* qde = qd + (size_t)e * p.num_qd;
-    const float* ae = actions + (size_t)e * p.num_act;
+    float r = 0.0f;
+    long long rs = 0;
+    walker_eval(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
+                rew ? progress[e] : 0, rew != nullptr, obs + (size_t)e * p.num_obs, &r, &rs);
+    if (rew) { rew[e] = r; reset[e] = rs; }
+}
+
+// adjoint of walker_eval for ONE environment: cotangents go (obs, nullable), go2 (a second observation cotangent
+// that is added to the first, nullable), gr (reward) -> gqe, gqde (overwritten), gae (nullable)
+__device__ __forceinline__ void walker_eval_adj(const DfxWalkerParams& p, const float* __restrict__ qe, const float* __restrict__ qde,
+                                                const float* __restrict__ ae, const float* __restrict__ go,
+                                                const float* __restrict__ go2, float gr, bool has_rew,
+                                                float* __restrict__ gqe, float* __restrict__ gqde, float* __restrict__ gae) {
     V3 pos, ang, lin, tt, tdir, up, heading;
     Q4 rot, tq;
     float tn;
     walker_features(p, qe, qde, pos, rot, ang, lin, tt, tn, tdir, tq, up, heading);
-    const float* go = g_obs ? g_obs + (size_t)e * p.num_obs : nullptr;
-    float gr = g_rew ? g_rew[e] : 0.0f;
-    if (p.check_invalid && p.zero_reward_on_invalid && g_rew) {
+    if (p.check_invalid && p.zero_reward_on_invalid && has_rew) {
         bool bad = false;
         for (int i = 0; i < p.num_q; ++i) bad |= !isfinite(qe[i]) || fabsf(qe[i]) > 1e6f;
         for (int i = 0; i < p.num_qd; ++i) bad |= !isfinite(qde[i]) || fabsf(qde[i]) > 1e6f;
@@ -116,21 +119,18 @@ __global__ void walker_backward_kernel(DfxWalkerParams p, int n, const float* __
     float dh;
     height_reward(p, pos.y, &dh);
     int k = 0;
-    auto G = [&](int idx) { return go ? go[idx] : 0.0f; };
+    auto G = [&](int idx) { return (go ? go[idx] : 0.0f) + (go2 ? go2[idx] : 0.0f); };
     // cotangents of the features
     float a_posy = G(0) + (p.height_mode != 2 ? gr * dh : 0.0f);
     Q4 a_rot = Q4{G(1), G(2), G(3), G(4)};
     V3 a_lin = V3{G(5) + gr, G(6), G(7)};
     V3 a_ang = V3{G(8), G(9), G(10)};
     k = 11;
-    float* gqe = gq + (size_t)e * p.num_q;
-    float* gqde = gqd + (size_t)e * p.num_qd;
     for (int i = 7; i < p.num_q; ++i) gqe[i] = G(k++);
     for (int i = 6; i < p.num_qd; ++i) gqde[i] = p.joint_vel_scale * G(k++);
     const float a_upy = G(k) + 0.1f * gr; ++k;
     const float a_h = G(k) + gr; ++k;
-    if (gact) {
-        float* gae = gact + (size_t)e * p.num_act;
+    if (gae) {
         for (int i = 0; i < p.num_act; ++i) {
             const float a = ae[i];
             float g = p.obs_has_actions ? G(k + i) : 0.0f;
@@ -160,6 +160,120 @@ __global__ void walker_backward_kernel(DfxWalkerParams p, int n, const float* __
     gqde[3] = a_v.x; gqde[4] = a_v.y; gqde[5] = a_v.z;
 }
 
+__global__ void walker_backward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                       const float* __restrict__ actions, const float* __restrict__ g_obs,
+                                       const float* __restrict__ g_rew, float* __restrict__ gq, float* __restrict__ gqd,
+                                       float* __restrict__ gact) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    walker_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
+                    g_obs ? g_obs + (size_t)e * p.num_obs : nullptr, nullptr, g_rew ? g_rew[e] : 0.0f, g_rew != nullptr,
+                    gq + (size_t)e * p.num_q, gqd + (size_t)e * p.num_qd, gact ? gact + (size_t)e * p.num_act : nullptr);
+}
+
+// ---- the whole env transition after the simulation step, one thread per environment:
+//   progress+1 -> observation, reward, termination (obs_before_reset) -> masked re-initialisation of the
+//   terminated environments (state <- start state, last actions <- 0, progress <- 0) -> observation of the
+//   state the next step starts from.  Replaces, per env.step(), the epilogue above plus ~12 elementwise ops
+//   (torch.where masks, clones, counters) and, in backward, their ~15 autograd nodes.
+__global__ void walker_transition_forward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                                 const float* __restrict__ actions, const long long* __restrict__ progress,
+                                                 const float* __restrict__ start_q, const float* __restrict__ start_qd,
+                                                 float* __restrict__ obs_before, float* __restrict__ rew, long long* __restrict__ reset,
+                                                 float* __restrict__ q_next, float* __restrict__ qd_next,
+                                                 float* __restrict__ actions_next, long long* __restrict__ progress_next,
+                                                 float* __restrict__ obs_next) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float* qe = q + (size_t)e * p.num_q;
+    const float* qde = qd + (size_t)e * p.num_qd;
+    const float* ae = actions + (size_t)e * p.num_act;
+    float* ob = obs_before + (size_t)e * p.num_obs;
+    float* on = obs_next + (size_t)e * p.num_obs;
+    const long long pr = progress[e] + 1;
+    float r = 0.0f;
+    long long rs = 0;
+    walker_eval(p, qe, qde, ae, pr, true, ob, &r, &rs);
+    rew[e] = r;
+    reset[e] = rs;
+    progress_next[e] = rs ? 0 : pr;
+    float* qn = q_next + (size_t)e * p.num_q;
+    float* qdn = qd_next + (size_t)e * p.num_qd;
+    float* an = actions_next + (size_t)e * p.num_act;
+    if (rs) {
+        const float* sq = start_q + (size_t)e * p.num_q;
+        const float* sqd = start_qd + (size_t)e * p.num_qd;
+        for (int i = 0; i < p.num_q; ++i) qn[i] = sq[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = sqd[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = 0.0f;
+        float r2; long long rs2;
+        walker_eval(p, sq, sqd, nullptr, 0, false, on, &r2, &rs2);
+    } else {
+        for (int i = 0; i < p.num_q; ++i) qn[i] = qe[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = qde[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = ae[i];
+        for (int i = 0; i < p.num_obs; ++i) on[i] = ob[i];
+    }
+}
+
+// cotangents of (obs_before, rew, q_next, qd_next, actions_next, obs_next), any of them NULL == 0, -> gq, gqd, gact.
+// A terminated environment passes nothing through its re-initialised outputs.
+__global__ void walker_transition_backward_kernel(DfxWalkerParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                                  const float* __restrict__ actions, const long long* __restrict__ reset,
+                                                  const float* __restrict__ g_obs_before, const float* __restrict__ g_rew,
+                                                  const float* __restrict__ g_q_next, const float* __restrict__ g_qd_next,
+                                                  const float* __restrict__ g_actions_next, const float* __restrict__ g_obs_next,
+                                                  float* __restrict__ gq, float* __restrict__ gqd, float* __restrict__ gact) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const bool live = reset[e] == 0;
+    float* gqe = gq + (size_t)e * p.num_q;
+    float* gqde = gqd + (size_t)e * p.num_qd;
+    float* gae = gact ? gact + (size_t)e * p.num_act : nullptr;
+    walker_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
+                    g_obs_before ? g_obs_before + (size_t)e * p.num_obs : nullptr,
+                    (live && g_obs_next) ? g_obs_next + (size_t)e * p.num_obs : nullptr,
+                    g_rew ? g_rew[e] : 0.0f, g_rew != nullptr, gqe, gqde, gae);
+    if (!live) return;
+    if (g_q_next) { const float* g = g_q_next + (size_t)e * p.num_q; for (int i = 0; i < p.num_q; ++i) gqe[i] += g[i]; }
+    if (g_qd_next) { const float* g = g_qd_next + (size_t)e * p.num_qd; for (int i = 0; i < p.num_qd; ++i) gqde[i] += g[i]; }
+    if (gae && g_actions_next) { const float* g = g_actions_next + (size_t)e * p.num_act; for (int i = 0; i < p.num_act; ++i) gae[i] += g[i]; }
+}
+
+// ---- policy output -> actuation, one thread per (environment, action):
+//   u = clip(a, -1, 1) * pre_scale + pre_bias          (what the env keeps as `actions`: observation + penalty)
+//   drive[e, offset + j] = (u * drive_scale) * strength[j]   (joint_act row of width `width`, or the muscle activations;
+//                                                        same association as the reference's actions * scale * strengths)
+// Reference: torch.clip + per-env scaling + slice assignment, envs/ant.py:156-166, snu_humanoid.py:283-296.
+__global__ void action_map_forward_kernel(int n, int num_act, int width, int offset, float pre_scale, float pre_bias, float drive_scale,
+                                          const float* __restrict__ strength, const float* __restrict__ raw,
+                                          float* __restrict__ used, float* __restrict__ drive) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int e = t / width, c = t - e * width, j = c - offset;
+    float out = 0.0f;
+    if (j >= 0 && j < num_act) {
+        const float a = raw[(size_t)e * num_act + j];
+        const float u = fminf(fmaxf(a, -1.0f), 1.0f) * pre_scale + pre_bias;
+        used[(size_t)e * num_act + j] = u;
+        out = (u * drive_scale) * strength[j];
+    }
+    drive[t] = out;
+}
+// g_used (nullable), g_drive (nullable) -> g_raw; torch.clip passes the gradient on [-1, 1] including the ends
+__global__ void action_map_backward_kernel(int n, int num_act, int width, int offset, float pre_scale, float drive_scale,
+                                           const float* __restrict__ strength, const float* __restrict__ raw,
+                                           const float* __restrict__ g_used, const float* __restrict__ g_drive,
+                                           float* __restrict__ g_raw) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * num_act) return;
+    const int e = t / num_act, j = t - e * num_act;
+    const float a = raw[t];
+    float g = g_used ? g_used[t] : 0.0f;
+    if (g_drive) g += (g_drive[(size_t)e * width + offset + j] * strength[j]) * drive_scale;
+    g_raw[t] = (a >= -1.0f && a <= 1.0f) ? g * pre_scale : 0.0f;
+}
+
 }  // namespace
 
 extern long long dfx_count_launch(void);
@@ -178,6 +292,53 @@ int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, con
                             const float* g_obs, const float* g_rew, float* gq, float* gqd, float* gact, void* stream) {
     if (!p || n <= 0 || !q || !qd || !actions || !gq || !gqd) return (int)cudaErrorInvalidValue;
     walker_backward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, g_obs, g_rew, gq, gqd, gact);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_walker_transition_forward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                                  const long long* progress, const float* start_q, const float* start_qd,
+                                  float* obs_before, float* rew, long long* reset, float* q_next, float* qd_next,
+                                  float* actions_next, long long* progress_next, float* obs_next, void* stream) {
+    if (!p || n <= 0 || !q || !qd || !actions || !progress || !start_q || !start_qd || !obs_before || !rew || !reset ||
+        !q_next || !qd_next || !actions_next || !progress_next || !obs_next)
+        return (int)cudaErrorInvalidValue;
+    walker_transition_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        *p, n, q, qd, actions, progress, start_q, start_qd, obs_before, rew, reset, q_next, qd_next, actions_next,
+        progress_next, obs_next);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_walker_transition_backward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                                   const long long* reset, const float* g_obs_before, const float* g_rew,
+                                   const float* g_q_next, const float* g_qd_next, const float* g_actions_next,
+                                   const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream) {
+    if (!p || n <= 0 || !q || !qd || !actions || !reset || !gq || !gqd) return (int)cudaErrorInvalidValue;
+    walker_transition_backward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        *p, n, q, qd, actions, reset, g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next, gq, gqd, gact);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_action_map_forward(int n, int num_act, int width, int offset, float pre_scale, float pre_bias, float drive_scale,
+                           const float* strength, const float* raw, float* used, float* drive, void* stream) {
+    if (n <= 0 || num_act <= 0 || width < num_act || offset < 0 || offset + num_act > width || !strength || !raw || !used || !drive)
+        return (int)cudaErrorInvalidValue;
+    const long long total = (long long)n * width;
+    action_map_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, num_act, width, offset, pre_scale, pre_bias, drive_scale, strength, raw, used, drive);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_action_map_backward(int n, int num_act, int width, int offset, float pre_scale, float drive_scale, const float* strength,
+                            const float* raw, const float* g_used, const float* g_drive, float* g_raw, void* stream) {
+    if (n <= 0 || num_act <= 0 || width < num_act || offset < 0 || offset + num_act > width || !strength || !raw || !g_raw)
+        return (int)cudaErrorInvalidValue;
+    const long long total = (long long)n * num_act;
+    action_map_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, num_act, width, offset, pre_scale, drive_scale, strength, raw, g_used, g_drive, g_raw);
     dfx_count_launch();
     return (int)cudaGetLastError();
 }

@@ -46,6 +46,9 @@ def _engine_for(model):
 def _derived_getattr(self, name):
     """Derived State fields (values of the LAST substep, reference model.py:375-388) are produced on
     demand by re-running the step with dumps enabled -- rendering/debugging only, never on the hot path."""
+    if name == "joint_act" and "_act_proto" in self.__dict__:     # zero actuation, materialised on first use only
+        self.__dict__["joint_act"] = torch.zeros_like(self.__dict__["_act_proto"])
+        return self.__dict__["joint_act"]
     if name in _DERIVED and "_derive_ctx" in self.__dict__:
         engine, q, qd, act, musc, substeps, mm_freq, dt = self.__dict__["_derive_ctx"]
         _, _, _, dumps = engine.forward(q, qd, act, musc, substeps, mm_freq, dt, want_tape=False, derived=list(_DERIVED))
@@ -83,7 +86,7 @@ class SemiImplicitIntegrator:
         out = State()
         out.particle_count, out.link_count = model.particle_count, model.link_count
         out.joint_q, out.joint_qd = q_new, qd_new
-        out.joint_act = torch.zeros_like(model.joint_qd)
+        out.__dict__["_act_proto"] = model.joint_qd      # out.joint_act: zeros, created lazily (State.__getattr__)
         out.__dict__["_derive_ctx"] = (engine, state_in.joint_q.detach(), state_in.joint_qd.detach(),
                                        state_in.joint_act.detach(), None if musc is None else musc.detach(),
                                        int(substeps), int(mass_matrix_freq), float(dt))

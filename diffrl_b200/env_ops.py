@@ -29,6 +29,11 @@ def _bind(lib):
     V = ctypes.c_void_p
     lib.dfx_walker_obs_forward.argtypes = [P, ctypes.c_int, V, V, V, V, V, V, V, V]
     lib.dfx_walker_obs_backward.argtypes = [P, ctypes.c_int, V, V, V, V, V, V, V, V, V]
+    lib.dfx_walker_transition_forward.argtypes = [P, ctypes.c_int] + [V] * 15
+    lib.dfx_walker_transition_backward.argtypes = [P, ctypes.c_int] + [V] * 14
+    I, F = ctypes.c_int, ctypes.c_float
+    lib.dfx_action_map_forward.argtypes = [I, I, I, I, F, F, F, V, V, V, V, V]
+    lib.dfx_action_map_backward.argtypes = [I, I, I, I, F, F, V, V, V, V, V, V]
     lib._walker_bound = True
 
 
@@ -80,3 +85,91 @@ class WalkerObsFunction(torch.autograd.Function):
                                                _ptr(g_obs), _ptr(g_rew), _ptr(gq), _ptr(gqd), _ptr(gact), stream)
         _capi.check(code, "dfx_walker_obs_backward")
         return None, None, None, None, gq, gqd, gact
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class WalkerTransitionFunction(torch.autograd.Function):
+    """Everything env.step() does after the simulation step, in one launch (``dfx_walker_transition_forward``):
+    (q, qd, actions) of the stepped state -> (obs_before_reset, rew, reset, q_next, qd_next, actions_next,
+    progress_next, obs_next).  ``progress`` is the counter before the step; ``start_q`` / ``start_qd`` the state a
+    terminated environment restarts from (constants for autograd)."""
+
+    @staticmethod
+    def forward(ctx, params, n, progress, start_q, start_qd, q, qd, actions):
+        lib = _capi.lib()
+        _bind(lib)
+        q, qd, actions = _c(q.detach()), _c(qd.detach()), _c(actions.detach())
+        start_q, start_qd = _c(start_q), _c(start_qd)
+        dev = q.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        obs_before = torch.empty((n, params.num_obs), **f32)
+        obs_next = torch.empty((n, params.num_obs), **f32)
+        rew = torch.empty(n, **f32)
+        reset = torch.empty(n, dtype=torch.long, device=dev)
+        progress_next = torch.empty(n, dtype=torch.long, device=dev)
+        q_next, qd_next, actions_next = torch.empty_like(q), torch.empty_like(qd), torch.empty_like(actions)
+        with torch.cuda.device(dev):
+            code = lib.dfx_walker_transition_forward(
+                ctypes.byref(params), n, _ptr(q), _ptr(qd), _ptr(actions), _ptr(progress), _ptr(start_q), _ptr(start_qd),
+                _ptr(obs_before), _ptr(rew), _ptr(reset), _ptr(q_next), _ptr(qd_next), _ptr(actions_next),
+                _ptr(progress_next), _ptr(obs_next), _stream(dev))
+        _capi.check(code, "dfx_walker_transition_forward")
+        ctx.params, ctx.n = params, n
+        ctx.save_for_backward(q, qd, actions, reset)
+        ctx.mark_non_differentiable(reset, progress_next)
+        return obs_before, rew, reset, q_next, qd_next, actions_next, progress_next, obs_next
+
+    @staticmethod
+    def backward(ctx, g_obs_before, g_rew, g_reset, g_q_next, g_qd_next, g_actions_next, g_progress, g_obs_next):
+        lib = _capi.lib()
+        q, qd, actions, reset = ctx.saved_tensors
+        dev = q.device
+        gq, gqd = torch.empty_like(q), torch.empty_like(qd)
+        gact = torch.empty_like(actions) if ctx.needs_input_grad[7] else None
+        cot = [None if g is None else _c(g) for g in (g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next)]
+        with torch.cuda.device(dev):
+            code = lib.dfx_walker_transition_backward(
+                ctypes.byref(ctx.params), ctx.n, _ptr(q), _ptr(qd), _ptr(actions), _ptr(reset),
+                *[_ptr(g) for g in cot], _ptr(gq), _ptr(gqd), _ptr(gact), _stream(dev))
+        _capi.check(code, "dfx_walker_transition_backward")
+        return None, None, None, None, None, gq, gqd, gact
+
+
+class ActionMapFunction(torch.autograd.Function):
+    """raw policy output [n, A] -> (used, drive): used = clip(raw, -1, 1) * pre_scale + pre_bias (the env's
+    ``actions``), drive [n * width] = zeros with drive[:, offset:offset+A] = (used * drive_scale) * strength (``joint_act`` or the
+    muscle activations).  One launch forward, one backward (``dfx_action_map_forward / _backward``)."""
+
+    @staticmethod
+    def forward(ctx, n, width, offset, pre_scale, pre_bias, drive_scale, strength, raw):
+        lib = _capi.lib()
+        _bind(lib)
+        raw = _c(raw.detach())
+        num_act = raw.shape[-1]
+        dev = raw.device
+        used = torch.empty_like(raw)
+        drive = torch.empty(n * width, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            code = lib.dfx_action_map_forward(n, num_act, width, offset, pre_scale, pre_bias, drive_scale, _ptr(strength), _ptr(raw),
+                                              _ptr(used), _ptr(drive), _stream(dev))
+        _capi.check(code, "dfx_action_map_forward")
+        ctx.cfg = (n, num_act, width, offset, pre_scale, drive_scale)
+        ctx.save_for_backward(strength, raw)
+        return used, drive
+
+    @staticmethod
+    def backward(ctx, g_used, g_drive):
+        lib = _capi.lib()
+        strength, raw = ctx.saved_tensors
+        n, num_act, width, offset, pre_scale, drive_scale = ctx.cfg
+        g_raw = torch.empty_like(raw)
+        g_used = None if g_used is None else _c(g_used)
+        g_drive = None if g_drive is None else _c(g_drive)
+        with torch.cuda.device(raw.device):
+            code = lib.dfx_action_map_backward(n, num_act, width, offset, pre_scale, drive_scale, _ptr(strength), _ptr(raw),
+                                               _ptr(g_used), _ptr(g_drive), _ptr(g_raw), _stream(raw.device))
+        _capi.check(code, "dfx_action_map_backward")
+        return None, None, None, None, None, None, None, g_raw

@@ -81,16 +81,15 @@ class _FreeRootWalker(DFlexEnv):
             self.calculateObservations()
             self.calculateReward()
 
-    def _reset_masked(self, reset_buf):
-        """Re-initialise terminated environments without reading reset_buf on the host."""
+    def _start_state(self):
+        """(start_q [n, Q], start_qd [n, D]): the state terminated environments restart from, for all n rows
+        (same distributions as _reset_state / reference ant.py:192-228, sampled for every row and used by mask)."""
         n = self.num_envs
-        mask = reset_buf.bool().unsqueeze(-1)
-        q = self.state.joint_q.view(n, -1)
-        qd = self.state.joint_qd.view(n, -1)
         if getattr(self, "_start_q_full", None) is None:
             self._start_q_full = torch.cat([self.start_pos, self.start_rotation.expand(n, 4),
                                             self.start_joint_q.expand(n, -1)], dim=-1).contiguous()
-            self._zero_qd, self._zero_act = torch.zeros_like(qd), torch.zeros_like(self.actions)
+            self._zero_qd = torch.zeros((n, self.num_joint_qd), device=self.device)
+            self._zero_act = torch.zeros((n, self.num_actions), device=self.device)
         start_q, start_qd = self._start_q_full, self._zero_qd
         if self.stochastic_init:
             dev = self.device
@@ -102,11 +101,59 @@ class _FreeRootWalker(DFlexEnv):
             if self.randomize_joints:
                 start_q[:, 7:] = start_q[:, 7:] + 0.2 * (torch.rand(size=(n, self.num_joint_q - 7), device=dev) - 0.5) * 2.0
             start_qd = 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
+        return start_q, start_qd
+
+    def _reset_masked(self, reset_buf):
+        """Re-initialise terminated environments without reading reset_buf on the host."""
+        n = self.num_envs
+        mask = reset_buf.bool().unsqueeze(-1)
+        q = self.state.joint_q.view(n, -1)
+        qd = self.state.joint_qd.view(n, -1)
+        start_q, start_qd = self._start_state()
         self.state.joint_q = torch.where(mask, start_q, q).view(-1)
         self.state.joint_qd = torch.where(mask, start_qd, qd).view(-1)
         self.actions = torch.where(mask, self._zero_act, self.actions)
         self.progress_buf = torch.where(reset_buf.bool(), torch.zeros_like(self.progress_buf), self.progress_buf)
         self.calculateObservations()
+
+    # ---- fused step: policy output -> actuation (1 launch), simulation step (1 launch), transition (1 launch) ----
+    fused_transition = True
+
+    def _action_map(self):
+        """(width, offset, pre_scale, pre_bias, drive_scale, strength [A], is_muscle) of dfx_action_map_forward."""
+        raise NotImplementedError
+
+    def step(self, actions):
+        if not (self.fused_transition and self.fused_epilogue and self.sync_free_reset
+                and torch.device(self.device).type == "cuda"):
+            return super().step(actions)
+        from ..env_ops import ActionMapFunction, WalkerTransitionFunction
+        n = self.num_envs
+        if getattr(self, "_amap", None) is None:
+            self._amap = self._action_map()
+            self._wparams = self._walker_params()
+        width, offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = self._amap
+        used, drive = ActionMapFunction.apply(n, width, offset, pre_scale, pre_bias, drive_scale, strength,
+                                              actions.view((n, self.num_actions)))
+        if self.nan_guard:
+            self._nan_guard(used)
+        self.actions = used
+        if is_muscle:
+            self.model.muscle_activation = drive
+        else:
+            self.state.joint_act = drive
+        self.state = self.integrator.forward(self.model, self.state, self.sim_dt, self.sim_substeps, self.MM_caching_frequency)
+        self.sim_time += self.sim_dt
+        self.num_frames += 1
+        start_q, start_qd = self._start_state()
+        (obs_before, self.rew_buf, self.reset_buf, q_next, qd_next, self.actions, self.progress_buf,
+         self.obs_buf) = WalkerTransitionFunction.apply(self._wparams, n, self.progress_buf, start_q, start_qd,
+                                                        self.state.joint_q, self.state.joint_qd, self.actions)
+        self.state.joint_q, self.state.joint_qd = q_next.view(-1), qd_next.view(-1)
+        if not self.no_grad:
+            self.obs_buf_before_reset = obs_before
+            self.extras = {"obs_before_reset": obs_before, "episode_end": self.termination_buf}
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _torso_features(self):
         q = self.state.joint_q.view(self.num_envs, -1)
@@ -164,6 +211,10 @@ class AntEnv(_FreeRootWalker):
     def _apply_actions(self, actions):
         self.state.joint_act.view(self.num_envs, -1)[:, 6:] = actions * self.action_strength
 
+    def _action_map(self):
+        strength = torch.full((self.num_actions,), float(self.action_strength), device=self.device)
+        return self.num_joint_qd, 6, 1.0, 0.0, 1.0, strength, False
+
     def calculateObservations(self):
         if self.fused_epilogue and torch.device(self.device).type == "cuda":
             self.obs_buf = self._fused(False)
@@ -207,6 +258,9 @@ class HumanoidEnv(_FreeRootWalker):
 
     def _apply_actions(self, actions):
         self.state.joint_act.view(self.num_envs, -1)[:, 6:] = actions * self.motor_scale * self.motor_strengths
+
+    def _action_map(self):
+        return self.num_joint_qd, 6, 1.0, 0.0, float(self.motor_scale), self.motor_strengths[0].contiguous(), False
 
     def calculateObservations(self):
         if self.fused_epilogue and torch.device(self.device).type == "cuda":
@@ -265,6 +319,9 @@ class SNUHumanoidEnv(_FreeRootWalker):
 
     def _apply_actions(self, actions):
         self.model.muscle_activation = actions.view(-1) * self.muscle_strengths
+
+    def _action_map(self):
+        return self.num_muscles, 0, 0.5, 0.5, 1.0, self.muscle_strengths[:self.num_muscles].contiguous(), True
 
     def calculateObservations(self):
         if self.fused_epilogue and torch.device(self.device).type == "cuda":

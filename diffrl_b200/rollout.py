@@ -64,15 +64,15 @@ class GraphedRollout:
         env.progress_buf = self.progress0.clone()
         env.actions = self.prev_actions.clone()
         env.calculateObservations()
-        loss = torch.zeros((), device=self.device)
         obs_l, rew_l, done_l = [], [], []
         for t in range(self.T):
             obs, rew, done, _ = env.step(self.actions[t])
-            loss = loss + (rew.sum() if self.weight is None else (rew * self.weight).sum())
             obs_l.append(obs); rew_l.append(rew); done_l.append(done)
+        rew_all = torch.stack(rew_l)                       # one reduction for the whole window
+        loss = rew_all.sum() if self.weight is None else (rew_all * self.weight).sum()
         self.actions.grad = None
         loss.backward()
-        self.obs, self.rew, self.done = torch.stack(obs_l).detach(), torch.stack(rew_l).detach(), torch.stack(done_l)
+        self.obs, self.rew, self.done = torch.stack(obs_l).detach(), rew_all.detach(), torch.stack(done_l)
         self.loss = loss.detach()
         self.final_q = env.state.joint_q.detach()
         self.final_qd = env.state.joint_qd.detach()

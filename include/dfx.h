@@ -166,6 +166,31 @@ int dfx_walker_obs_forward(const DfxWalkerParams* p, int n, const float* q, cons
 int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
                             const float* g_obs, const float* g_rew, float* gq, float* gqd, float* gact, void* stream);
 
+/* ---- the whole env transition after the simulation step (reference envs/ant.py:156-190: progress counter,
+ * calculateObservations, calculateReward, reset of the terminated environments, observation of the new state),
+ * with the reset done by mask so that nothing synchronises with the host.  `progress` is the counter BEFORE this
+ * step.  start_q [n*num_q], start_qd [n*num_qd]: the state a terminated environment restarts from.
+ * Outputs: obs_before [n*num_obs] (the reference's extras["obs_before_reset"]), rew [n], reset [n] (int64 0/1),
+ * q_next, qd_next, actions_next [n*num_act] (zeroed where reset), progress_next [n], obs_next [n*num_obs]. */
+int dfx_walker_transition_forward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                                  const long long* progress, const float* start_q, const float* start_qd,
+                                  float* obs_before, float* rew, long long* reset, float* q_next, float* qd_next,
+                                  float* actions_next, long long* progress_next, float* obs_next, void* stream);
+/* cotangents of the six differentiable outputs (NULL == 0) -> gq, gqd (overwritten), gact (NULL: skip). */
+int dfx_walker_transition_backward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
+                                   const long long* reset, const float* g_obs_before, const float* g_rew,
+                                   const float* g_q_next, const float* g_qd_next, const float* g_actions_next,
+                                   const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream);
+
+/* ---- policy output -> actuation (reference envs/ant.py:156-166, envs/snu_humanoid.py:283-296):
+ * used[e, j] = clip(raw[e, j], -1, 1) * pre_scale + pre_bias ;  drive[e, offset + j] = (used[e, j] * drive_scale) * strength[j],
+ * every other entry of the [n, width] drive rows zero (joint_act, or the muscle activations with offset 0). */
+int dfx_action_map_forward(int n, int num_act, int width, int offset, float pre_scale, float pre_bias, float drive_scale,
+                           const float* strength, const float* raw, float* used, float* drive, void* stream);
+/* g_used [n*num_act] (NULL == 0), g_drive [n*width] (NULL == 0) -> g_raw [n*num_act]. */
+int dfx_action_map_backward(int n, int num_act, int width, int offset, float pre_scale, float drive_scale, const float* strength,
+                            const float* raw, const float* g_used, const float* g_drive, float* g_raw, void* stream);
+
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
 /* Tuning flags (default 11): bit 1 (2) = CTA-wide phase barriers (instruction-cache locality); bit 2 (4) = generic

@@ -100,9 +100,48 @@ def test_fused_epilogue_equals_torch_ops(name):
         loss.backward()
         outs.append((torch.stack(obs_l), torch.stack(rew_l), torch.stack([a.grad for a in acts])))
     (o1, r1, g1), (o2, r2, g2) = outs
-    assert torch.allclose(o1, o2, rtol=1e-5, atol=1e-5)
-    assert torch.allclose(r1, r2, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(o1, o2, rtol=1e-5, atol=1e-5), float((o1 - o2).abs().max())
+    assert torch.allclose(r1, r2, rtol=1e-5, atol=1e-4), float((r1 - r2).abs().max())
     assert (g1 - g2).abs().max() <= 1e-4 * g2.abs().max() + 1e-6
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv"])
+def test_fused_transition_equals_unfused_step(name):
+    """env.step() as three launches (action map, simulation step, transition: dfx_action_map_* /
+    dfx_walker_transition_*) against the op-by-op PyTorch step: observations before and after the masked
+    reset, rewards, flags, counters, next state, and the gradient of a loss through all of them -- with
+    actions beyond the clip range and episodes short enough to terminate inside the window."""
+    import torch
+    import diffrl_b200.envs as envs
+    n, T = 48, 7
+    outs = []
+    for mode in ("fused", "epilogue", "torch"):
+        torch.manual_seed(0)
+        env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=3)
+        env.fused_transition = mode == "fused"
+        env.fused_epilogue = mode != "torch"
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        g = torch.Generator(device="cuda:0").manual_seed(11)
+        acts = [((torch.rand((n, env.num_actions), generator=g, device="cuda:0") * 2 - 1) * 1.6).requires_grad_() for _ in range(T)]
+        w = torch.linspace(0.5, 1.5, env.num_obs, device="cuda:0")
+        loss, rec = 0.0, []
+        for a in acts:
+            obs, rew, done, extras = env.step(a)
+            loss = loss + rew.sum() + (obs * w).sum() * 1e-2 + (extras["obs_before_reset"] * w).sum() * 3e-3
+            rec.append((obs.detach().clone(), rew.detach().clone(), done.clone(), env.progress_buf.clone(),
+                        env.state.joint_q.detach().clone(), env.state.joint_qd.detach().clone(), env.actions.detach().clone(),
+                        extras["obs_before_reset"].detach().clone()))
+        loss.backward()
+        outs.append((rec, torch.stack([a.grad for a in acts]), float(loss)))
+    ref_rec, ref_grad, ref_loss = outs[2]
+    assert any(bool(r[2].any()) for r in ref_rec), "the window must contain terminations"
+    for rec, grad, loss in outs[:2]:
+        for a, b in zip(rec, ref_rec):
+            assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+            for x, y in zip(a[:2] + a[4:], b[:2] + b[4:]):
+                assert torch.allclose(x, y, rtol=1e-5, atol=1e-4), float((x - y).abs().max())
+        assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss) + 1e-3
+        assert (grad - ref_grad).abs().max() <= 1e-4 * ref_grad.abs().max() + 1e-6
 
 
 def test_masked_reset_equals_indexed_reset():
