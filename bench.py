@@ -326,11 +326,12 @@ def run_ours(args):
         from diffrl_b200.rollout import GraphedRollout
         env.clear_grad(); env.reset(); env.initialize_trajectory()
         roll = GraphedRollout(env, T)
+        roll.host_actions.copy_(host_actions)      # the pinned staging buffer the graph's H2D copy reads every rollout
 
         def graphed_rollout():
             env.clear_grad()
             env.reset()
-            loss_h, grad_h = roll(host_actions, sync=False)
+            loss_h, grad_h = roll(None, sync=False)
             if world > 1:
                 comm[: T * env.num_actions] = roll.actions.grad.mean(dim=1).reshape(-1)
                 dist.all_reduce(comm)
@@ -340,6 +341,11 @@ def run_ours(args):
         for _ in range(max(1, args.warmup // 2)):
             graphed_rollout()
         barrier()
+        if args.ncu_range_e2e:          # launch list of ONE end-to-end rollout (profiles/): ncu --profile-from-start off
+            torch.cuda.profiler.start()
+            graphed_rollout()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         e3[0].record()
         for _ in range(e2e_steps):
             graphed_rollout()
@@ -417,6 +423,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e", default="graph", choices=["graph", "eager"])
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: host processes (default: all cores, max 64)")
+    ap.add_argument("--ncu-range-e2e", action="store_true",
+                    help="wrap one graphed end-to-end rollout in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="wrap ONE kernel-path step and ONE e2e step in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -277,13 +277,16 @@ __global__ void action_map_backward_kernel(int n, int num_act, int width, int of
 }  // namespace
 
 extern long long dfx_count_launch(void);
+// one warp per CTA: a thread walks ~100 row entries serially, so the kernels are latency bound and 4096 environments
+// should cover 128 SMs rather than 32
+static constexpr int kEnvThreads = 32;
 
 extern "C" {
 
 int dfx_walker_obs_forward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
                            const long long* progress, float* obs, float* rew, long long* reset, void* stream) {
     if (!p || n <= 0 || !q || !qd || !actions || !obs || (rew && (!reset || !progress))) return (int)cudaErrorInvalidValue;
-    walker_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, progress, obs, rew, reset);
+    walker_forward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, progress, obs, rew, reset);
     dfx_count_launch();
     return (int)cudaGetLastError();
 }
@@ -291,7 +294,7 @@ int dfx_walker_obs_forward(const DfxWalkerParams* p, int n, const float* q, cons
 int dfx_walker_obs_backward(const DfxWalkerParams* p, int n, const float* q, const float* qd, const float* actions,
                             const float* g_obs, const float* g_rew, float* gq, float* gqd, float* gact, void* stream) {
     if (!p || n <= 0 || !q || !qd || !actions || !gq || !gqd) return (int)cudaErrorInvalidValue;
-    walker_backward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, g_obs, g_rew, gq, gqd, gact);
+    walker_backward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(*p, n, q, qd, actions, g_obs, g_rew, gq, gqd, gact);
     dfx_count_launch();
     return (int)cudaGetLastError();
 }
@@ -303,7 +306,7 @@ int dfx_walker_transition_forward(const DfxWalkerParams* p, int n, const float* 
     if (!p || n <= 0 || !q || !qd || !actions || !progress || !start_q || !start_qd || !obs_before || !rew || !reset ||
         !q_next || !qd_next || !actions_next || !progress_next || !obs_next)
         return (int)cudaErrorInvalidValue;
-    walker_transition_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    walker_transition_forward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(
         *p, n, q, qd, actions, progress, start_q, start_qd, obs_before, rew, reset, q_next, qd_next, actions_next,
         progress_next, obs_next);
     dfx_count_launch();
@@ -315,7 +318,7 @@ int dfx_walker_transition_backward(const DfxWalkerParams* p, int n, const float*
                                    const float* g_q_next, const float* g_qd_next, const float* g_actions_next,
                                    const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream) {
     if (!p || n <= 0 || !q || !qd || !actions || !reset || !gq || !gqd) return (int)cudaErrorInvalidValue;
-    walker_transition_backward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    walker_transition_backward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(
         *p, n, q, qd, actions, reset, g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next, gq, gqd, gact);
     dfx_count_launch();
     return (int)cudaGetLastError();

@@ -140,6 +140,7 @@ class SimStepFunction(torch.autograd.Function):
                                                 None if musc is None else musc.detach(),
                                                 substeps, mm_freq, dt, want_tape=any(needs))
         ctx.engine, ctx.cfg, ctx.needs = engine, (substeps, mm_freq, dt), needs
+        ctx.set_materialize_grads(False)      # a missing cotangent is NULL for dfx_step_backward, not a zero fill
         ctx.shapes = (q.shape, qd.shape, act.shape, None if musc is None else musc.shape)
         ctx.save_for_backward(act.detach(), musc.detach() if (musc is not None and engine.M) else None, tape)
         return q_out.view(q.shape), qd_out.view(qd.shape)

@@ -63,6 +63,7 @@ class WalkerObsFunction(torch.autograd.Function):
                                               _ptr(progress) if want_reward else None, _ptr(obs), _ptr(rew), _ptr(reset), stream)
         _capi.check(code, "dfx_walker_obs_forward")
         ctx.params, ctx.n = params, n
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(q, qd, actions)
         ctx.shapes = None
         if want_reward:
@@ -118,6 +119,7 @@ class WalkerTransitionFunction(torch.autograd.Function):
                 _ptr(progress_next), _ptr(obs_next), _stream(dev))
         _capi.check(code, "dfx_walker_transition_forward")
         ctx.params, ctx.n = params, n
+        ctx.set_materialize_grads(False)      # absent cotangents arrive as None (NULL in the C ABI), not as zero fills
         ctx.save_for_backward(q, qd, actions, reset)
         ctx.mark_non_differentiable(reset, progress_next)
         return obs_before, rew, reset, q_next, qd_next, actions_next, progress_next, obs_next
@@ -157,6 +159,7 @@ class ActionMapFunction(torch.autograd.Function):
                                               _ptr(used), _ptr(drive), _stream(dev))
         _capi.check(code, "dfx_action_map_forward")
         ctx.cfg = (n, num_act, width, offset, pre_scale, drive_scale)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(strength, raw)
         return used, drive
 

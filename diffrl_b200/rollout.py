@@ -65,8 +65,8 @@ class GraphedRollout:
         env.actions = self.prev_actions.clone()
         env.calculateObservations()
         obs_l, rew_l, done_l = [], [], []
-        for t in range(self.T):
-            obs, rew, done, _ = env.step(self.actions[t])
+        for t, a_t in enumerate(self.actions.unbind(0)):   # unbind: ONE stack in backward instead of T zero-filled selects
+            obs, rew, done, _ = env.step(a_t)
             obs_l.append(obs); rew_l.append(rew); done_l.append(done)
         rew_all = torch.stack(rew_l)                       # one reduction for the whole window
         loss = rew_all.sum() if self.weight is None else (rew_all * self.weight).sum()
@@ -82,10 +82,12 @@ class GraphedRollout:
         self.host_loss.copy_(self.loss, non_blocking=True)
 
     def __call__(self, host_actions=None, sync=True):
-        """Replay the captured rollout.  ``host_actions``: [T, N, A] tensor (ideally pinned); None re-uses the
-        previous buffer contents.  Returns (loss, grad_actions) as host tensors (valid after the sync)."""
+        """Replay the captured rollout.  ``host_actions``: [T, N, A] tensor, copied into the pinned staging buffer
+        ``self.host_actions`` the graph's H2D copy reads; pass None after writing the actions into
+        ``self.host_actions`` directly (saves the host-side copy).  Returns (loss, grad_actions) as pinned host
+        tensors (valid after the sync)."""
         env = self.env
-        if host_actions is not None:
+        if host_actions is not None and host_actions is not self.host_actions:
             self.host_actions.copy_(host_actions)
         with torch.no_grad():
             # chain from where the env currently is

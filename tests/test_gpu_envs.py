@@ -132,7 +132,7 @@ def test_fused_transition_equals_unfused_step(name):
                         env.state.joint_q.detach().clone(), env.state.joint_qd.detach().clone(), env.actions.detach().clone(),
                         extras["obs_before_reset"].detach().clone()))
         loss.backward()
-        outs.append((rec, torch.stack([a.grad for a in acts]), float(loss)))
+        outs.append((rec, torch.stack([a.grad for a in acts]), float(loss.detach())))
     ref_rec, ref_grad, ref_loss = outs[2]
     assert any(bool(r[2].any()) for r in ref_rec), "the window must contain terminations"
     for rec, grad, loss in outs[:2]:
