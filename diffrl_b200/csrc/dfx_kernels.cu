@@ -216,7 +216,7 @@ struct dfx_pack {
 static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
-static int g_flags = 11;  // bit 1: phase barriers; bit 2: DISABLE the size-specialised kernels (A/B testing); bit 3: CTA-wide task loops
+static int g_flags = 9;   // bit 1: phase barriers; bit 2: DISABLE the size-specialised kernels (A/B testing); bit 3: CTA-wide task loops
 
 static void set_err(char* err, int n, const std::string& m) {
     if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }

@@ -260,16 +260,14 @@ DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, float* s, int i) {    
 
 template <class Grp>
 DFX_HD void kin_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
-    DFX_FOR(i, P.L) kin_adj_local(P, Y, s, i);
-    g.sync();
+    // all five passes run as CTA-wide (link, environment) tasks, link-major: uniform joint types per warp
+    g.cta_tasks(s, P.L, true, [&](float* se, int i) { kin_adj_local(P, Y, se, i); });
     for (int lev = P.nlev - 1; lev >= 0; --lev)
-        level_tasks(P, s, lev, lev == P.nlev - 1, g, [&](float* se, int i) { kin_adj_velocity(P, Y, se, i); });
-    DFX_FOR(i, P.L) kin_adj_motion(P, Y, s, i);
-    g.sync();
+        level_tasks(P, s, lev, false, g, [&](float* se, int i) { kin_adj_velocity(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](float* se, int i) { kin_adj_motion(P, Y, se, i); });
     for (int lev = P.nlev - 1; lev >= 0; --lev)
-        level_tasks(P, s, lev, lev == P.nlev - 1, g, [&](float* se, int i) { kin_adj_chain(P, Y, se, i); });
-    DFX_FOR(i, P.L) kin_adj_joint(P, Y, s, i);
-    g.sync();
+        level_tasks(P, s, lev, false, g, [&](float* se, int i) { kin_adj_chain(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](float* se, int i) { kin_adj_joint(P, Y, se, i); });
 }
 
 // =====================================================================================
@@ -794,8 +792,8 @@ DFX_HD void tau_accum_adj(const Pack& P, const Layout& Y, float* s, int i) {
 
 template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, float* s, const float* atau, const Grp& g) {
-    DFX_FOR(i, P.L) tau_project_adj(P, Y, s, atau, i);
-    g.sync();
+    const int atau_off = (int)(atau - s);
+    g.cta_tasks(s, P.L, true, [&](float* se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
     for (int lev = 1; lev < P.nlev; ++lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
         for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_adj(P, Y, s, P.level_links[k]);
@@ -1077,8 +1075,7 @@ DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, float* s, float d
 
 template <class Grp>
 DFX_HD void integrate_adj(const Pack& P, const Layout& Y, float* s, float dt, const Grp& g) {
-    DFX_FOR(i, P.L) integrate_link_adj(P, Y, s, dt, i);
-    g.sync();
+    g.cta_tasks(s, P.L, true, [&](float* se, int i) { integrate_link_adj(P, Y, se, dt, i); });
 }
 
 // =====================================================================================

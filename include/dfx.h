@@ -193,7 +193,8 @@ int dfx_action_map_backward(int n, int num_act, int width, int offset, float pre
 
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
-/* Tuning flags (default 11): bit 1 (2) = CTA-wide phase barriers (instruction-cache locality); bit 2 (4) = generic
+/* Tuning flags (default 9): bit 1 (2) = extra CTA-wide barriers between phases (instruction-cache locality; no longer
+ * a gain now that the task loops synchronise the CTA anyway); bit 2 (4) = generic
  * kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases. */
 int dfx_set_flags(int flags);
 /* Launch geometry the step kernel would use for this pack (host arithmetic, no GPU needed):
