@@ -100,18 +100,28 @@ struct GroupCuda {
         }
         __syncthreads();
     }
-    // cp.async (LDGSTS) 16-byte copies, one commit group per row
-    __device__ __forceinline__ void copy_row_async(float* dst, const float* src, int n) const {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-        for (int i = lane * 4; i < n; i += G_ * 4)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    // tape blocks [b][env][n]: rows (n % 4 == 0, 16-byte aligned) move with cp.async (LDGSTS) / float4, one commit
+    // group per row; the H^-1 blocks (n = D * D, any alignment) with plain loads
+    __device__ __forceinline__ void block_in(float* dst, const float* base, long long b, int N, int env, int n, bool rows) const {
+        const float* src = base + (b * N + env) * n;
+        if (rows) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+            for (int i = lane * 4; i < n; i += G_ * 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            for (int i = lane; i < n; i += G_) dst[i] = src[i];
+        }
     }
-    // scratch -> global row (16-byte aligned, n a multiple of 4 floats)
-    __device__ __forceinline__ void copy_row_out(float* dst, const float* src, int n) const {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = lane; i < n / 4; i += G_) d4[i] = s4[i];
+    __device__ __forceinline__ void block_out(float* base, long long b, int N, int env, const float* src, int n, bool rows) const {
+        float* dst = base + (b * N + env) * n;
+        if (rows) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = lane; i < n / 4; i += G_) d4[i] = s4[i];
+        } else {
+            for (int i = lane; i < n; i += G_) dst[i] = src[i];
+        }
     }
     __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };

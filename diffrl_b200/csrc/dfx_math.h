@@ -288,26 +288,58 @@ DFX_HD Q4 q_to_m3_adj(Q4 q, const M3& a) {
     return Q4{av.x, av.y, av.z, aw};
 }
 
-// ---------------------------------------------------------------- strided load / store helpers
-DFX_HD V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
-DFX_HD Q4 ld4(const float* p) { return Q4{p[0], p[1], p[2], p[3]}; }
-DFX_HD Xf ld7(const float* p) { return Xf{V3{p[0], p[1], p[2]}, Q4{p[3], p[4], p[5], p[6]}}; }
-DFX_HD SV ld6(const float* p) { return SV{V3{p[0], p[1], p[2]}, V3{p[3], p[4], p[5]}}; }
-DFX_HD void st3(float* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
-DFX_HD void st4(float* p, Q4 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; }
-DFX_HD void st7(float* p, Xf a) { st3(p, a.p); st4(p + 3, a.q); }
-DFX_HD void st6(float* p, SV a) { st3(p, a.w); st3(p + 3, a.v); }
-DFX_HD void add3(float* p, V3 a) { p[0] += a.x; p[1] += a.y; p[2] += a.z; }
-DFX_HD void add4(float* p, Q4 a) { p[0] += a.x; p[1] += a.y; p[2] += a.z; p[3] += a.w; }
-DFX_HD void add7(float* p, Xf a) { add3(p, a.p); add4(p + 3, a.q); }
-DFX_HD void add6(float* p, SV a) { add3(p, a.w); add3(p + 3, a.v); }
-DFX_HD M3 ld9(const float* p) {
+// ---------------------------------------------------------------- scratch pointers and load / store helpers
+// Per-environment scratch is addressed through SP: element i of an environment lives at p[i * DFX_ES].
+//   DFX_ES == 1  : a plain float* (one contiguous block per environment; lane-group kernels, host emulation)
+//   DFX_ES == 32 : structure-of-arrays tile of 32 environments, lane = environment (tile kernels): consecutive
+//                  lanes touch consecutive banks, every pack read is a warp-wide broadcast
+#ifndef DFX_ES
+#define DFX_ES 1
+#endif
+template <class T>
+struct StridedPtr {
+    T* p;
+    DFX_HD StridedPtr operator+(int o) const { return StridedPtr{p + (long long)o * DFX_ES}; }
+    DFX_HD StridedPtr operator-(int o) const { return StridedPtr{p - (long long)o * DFX_ES}; }
+    DFX_HD T& operator[](int i) const { return p[(long long)i * DFX_ES]; }
+    DFX_HD T& operator*() const { return *p; }
+    DFX_HD int operator-(StridedPtr o) const { return (int)((p - o.p) / DFX_ES); }
+};
+#if DFX_ES == 1
+using SP = float*;
+using SPi = int*;
+using SPu = unsigned*;
+DFX_HD SPi sp_int(SP s) { return reinterpret_cast<int*>(s); }
+DFX_HD SPu sp_uint(SP s) { return reinterpret_cast<unsigned*>(s); }
+DFX_HD float* sp_raw(SP s) { return s; }
+#else
+using SP = StridedPtr<float>;
+using SPi = StridedPtr<int>;
+using SPu = StridedPtr<unsigned>;
+DFX_HD SPi sp_int(SP s) { return SPi{reinterpret_cast<int*>(s.p)}; }
+DFX_HD SPu sp_uint(SP s) { return SPu{reinterpret_cast<unsigned*>(s.p)}; }
+DFX_HD float* sp_raw(SP s) { return s.p; }
+#endif
+
+template <class P> DFX_HD V3 ld3(P p) { return V3{p[0], p[1], p[2]}; }
+template <class P> DFX_HD Q4 ld4(P p) { return Q4{p[0], p[1], p[2], p[3]}; }
+template <class P> DFX_HD Xf ld7(P p) { return Xf{V3{p[0], p[1], p[2]}, Q4{p[3], p[4], p[5], p[6]}}; }
+template <class P> DFX_HD SV ld6(P p) { return SV{V3{p[0], p[1], p[2]}, V3{p[3], p[4], p[5]}}; }
+template <class P> DFX_HD void st3(P p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+template <class P> DFX_HD void st4(P p, Q4 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; }
+template <class P> DFX_HD void st7(P p, Xf a) { st3(p, a.p); st4(p + 3, a.q); }
+template <class P> DFX_HD void st6(P p, SV a) { st3(p, a.w); st3(p + 3, a.v); }
+template <class P> DFX_HD void add3(P p, V3 a) { p[0] += a.x; p[1] += a.y; p[2] += a.z; }
+template <class P> DFX_HD void add4(P p, Q4 a) { p[0] += a.x; p[1] += a.y; p[2] += a.z; p[3] += a.w; }
+template <class P> DFX_HD void add7(P p, Xf a) { add3(p, a.p); add4(p + 3, a.q); }
+template <class P> DFX_HD void add6(P p, SV a) { add3(p, a.w); add3(p + 3, a.v); }
+template <class P> DFX_HD M3 ld9(P p) {
     M3 r;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) r.m[i][j] = p[i * 3 + j];
     return r;
 }
-DFX_HD void st9(float* p, const M3& a) {
+template <class P> DFX_HD void st9(P p, const M3& a) {
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) p[i * 3 + j] = a.m[i][j];
 }

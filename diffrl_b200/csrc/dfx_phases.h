@@ -37,14 +37,24 @@ struct GroupSerial {  // host / single-lane execution
     DFX_HD float group_max(float v) const { return v; }
     // run f(scratch of env, k) for k in [0, n) for every environment the executing CTA holds (here: this one)
     template <class F>
-    DFX_HD void cta_tasks(float* s, int n, bool lead, F f) const { (void)lead; for (int k = 0; k < n; ++k) f(s, k); }
+    DFX_HD void cta_tasks(SP s, int n, bool lead, F f) const { (void)lead; for (int k = 0; k < n; ++k) f(s, k); }
     // same, restricted to the (k, env) pairs for which pred() holds (compacted first)
     template <class Pr, class F>
-    DFX_HD void cta_compact(float* s, int n, Pr pred, F f) const { for (int k = 0; k < n; ++k) if (pred(s, k)) f(s, k); }
-    // asynchronous global -> scratch row copy (16-byte aligned, n a multiple of 4 floats)
-    DFX_HD void copy_row_async(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
+    DFX_HD void cta_compact(SP s, int n, Pr pred, F f) const { for (int k = 0; k < n; ++k) if (pred(s, k)) f(s, k); }
+    // tape blocks: block `b` of environment `env` holds n floats ([b][env][n] here and in the lane-group kernels,
+    // [b][tile of 32 envs][n][32] in the tile kernels).  `rows`: n is a multiple of 4 and 16-byte aligned (vector
+    // / asynchronous copies allowed); block_in may complete asynchronously until copy_wait_all().
+    DFX_HD void block_out(float* base, long long b, int N, int env, SP src, int n, bool rows) const {
+        (void)rows;
+        float* d = base + (b * N + env) * n;
+        for (int i = 0; i < n; ++i) d[i] = src[i];
+    }
+    DFX_HD void block_in(SP dst, const float* base, long long b, int N, int env, int n, bool rows) const {
+        (void)rows;
+        const float* t = base + (b * N + env) * n;
+        for (int i = 0; i < n; ++i) dst[i] = t[i];
+    }
     DFX_HD void copy_wait_all() const {}
-    DFX_HD void copy_row_out(float* dst, const float* src, int n) const { for (int i = 0; i < n; ++i) dst[i] = src[i]; }
 };
 
 #define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
@@ -56,13 +66,13 @@ struct GroupSerial {  // host / single-lane execution
 // CTA-wide barrier per level.  Measured (same box, Ant 4096): adjoint -8.5 %; the light forward recursions (one
 // transform product or two vector adds per level) lose more to the barriers than they gain and stay per group.
 template <class Grp, class F>
-DFX_HD void level_tasks(const Pack& P, float* s, int lev, bool lead, const Grp& g, F f) {
+DFX_HD void level_tasks(const Pack& P, SP s, int lev, bool lead, const Grp& g, F f) {
     const int b = P.level_start[lev], e = P.level_start[lev + 1];
-    g.cta_tasks(s, e - b, lead, [&](float* se, int k) { f(se, P.level_links[b + k]); });
+    g.cta_tasks(s, e - b, lead, [&](SP se, int k) { f(se, P.level_links[b + k]); });
 }
 
 template <class Grp>
-DFX_HD void zero_range(float* p, int n, const Grp& g) {
+DFX_HD void zero_range(SP p, int n, const Grp& g) {
     DFX_FOR(i, n) p[i] = 0.0f;
 }
 
@@ -76,7 +86,7 @@ DFX_HD void zero_range(float* p, int n, const Grp& g) {
 //   K4 (root->leaf) v = v[parent] + v_j ; a = a[parent] + v x v_j
 // Scratch: Y.Xl (L,7) and Y.vj (L,6).
 // =====================================================================================
-DFX_HD Xf joint_transform(const Pack& P, const float* q, int i) {
+DFX_HD Xf joint_transform(const Pack& P, SP q, int i) {
     const int type = P.type[i], qs = P.q_start[i];
     Xf Xjc = xf_ident();
     if (type == JOINT_PRISMATIC) Xjc.p = ld3(P.axis + i * 3) * q[qs];
@@ -86,11 +96,11 @@ DFX_HD Xf joint_transform(const Pack& P, const float* q, int i) {
     return Xjc;
 }
 
-DFX_HD void kin_local_fwd(const Pack& P, const Layout& Y, float* s, int i) {   // K1
+DFX_HD void kin_local_fwd(const Pack& P, const Layout& Y, SP s, int i) {   // K1
     st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
 }
 
-DFX_HD void kin_chain_fwd(const Pack& P, const Layout& Y, float* s, int i) {   // K2
+DFX_HD void kin_chain_fwd(const Pack& P, const Layout& Y, SP s, int i) {   // K2
     const int par = P.parent[i];
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
@@ -98,13 +108,13 @@ DFX_HD void kin_chain_fwd(const Pack& P, const Layout& Y, float* s, int i) {   /
     st7(s + Y.Xsc + i * 7, xf_mul(Xp, ld7(s + Y.Xl + i * 7)));
 }
 
-DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, float* s, int i) {  // K3
+DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // K3
     const int par = P.parent[i], type = P.type[i], ds = P.qd_start[i];
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     const Xf Xsj = xf_mul(Xp, ld7(P.X_pj + i * 7));
     const V3 axis = ld3(P.axis + i * 3);
-    const float* qd = s + Y.qd;
-    float* S = s + Y.S;
+    const SP qd = s + Y.qd;
+    const SP S = s + Y.S;
     SV vj = sv_zero();
     if (type == JOINT_PRISMATIC) {
         SV Sk = SV{v3zero(), qrot(Xsj.q, axis)};
@@ -132,7 +142,7 @@ DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, float* s, int i) {  /
     st7(s + Y.Xsm + i * 7, xf_mul(ld7(s + Y.Xsc + i * 7), ld7(P.X_cm + i * 7)));
 }
 
-DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, float* s, int i) {  // K4
+DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // K4
     const int par = P.parent[i];
     SV vp = sv_zero(), ap = sv_zero();
     if (par >= 0) { vp = ld6(s + Y.v + par * 6); ap = ld6(s + Y.a + par * 6); }
@@ -143,7 +153,7 @@ DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, float* s, int i) { 
 }
 
 template <class Grp>
-DFX_HD void kin_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
     g.sync();
     for (int lev = 0; lev < P.nlev; ++lev) {
@@ -167,15 +177,15 @@ DFX_HD void kin_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 //   A3 (parallel)   adjoint of v_j = S qd and of S(X_sj): aS, aqd, aX_sj (kept in the pX slot)
 //   A4 (leaf->root) aXsc totals (children's pushes gathered); push of this link to its parent -> pX
 //   A5 (parallel)   adjoint of X_l = X_pj X_jc(q) -> aq
-DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, float* s, int i) {    // A1
-    float* aX = s + Y.aXsc + i * 7;
+DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, SP s, int i) {    // A1
+    const SP aX = s + Y.aXsc + i * 7;
     Xf acc = ld7(aX);
     xf_mul_adj_a(ld7(s + Y.Xsc + i * 7), ld7(P.X_cm + i * 7), ld7(s + Y.aXsm + i * 7), acc);
     st7(aX, acc);
     st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
     const int type = P.type[i], ds = P.qd_start[i];
-    const float* qd = s + Y.qd;
-    const float* S = s + Y.S;
+    const SP qd = s + Y.qd;
+    const SP S = s + Y.S;
     SV vj = sv_zero();
     if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) vj = ld6(S + ds * 6) * qd[ds];
     else if (type == JOINT_BALL) { for (int k = 0; k < 3; ++k) vj += ld6(S + (ds + k) * 6) * qd[ds + k]; }
@@ -183,7 +193,7 @@ DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, float* s, int i) {    
     st6(s + Y.vj + i * 6, vj);
 }
 
-DFX_HD void kin_adj_velocity(const Pack& P, const Layout& Y, float* s, int i) {  // A2
+DFX_HD void kin_adj_velocity(const Pack& P, const Layout& Y, SP s, int i) {  // A2
     SV av = ld6(s + Y.av + i * 6), aa = ld6(s + Y.aa + i * 6);
     for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) {
         const int c = P.child_idx[k];
@@ -198,16 +208,16 @@ DFX_HD void kin_adj_velocity(const Pack& P, const Layout& Y, float* s, int i) { 
     st6(s + Y.vj + i * 6, avj);
 }
 
-DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, float* s, int i) {    // A3
+DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // A3
     const int par = P.parent[i], type = P.type[i], ds = P.qd_start[i];
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     const Xf Xsj = xf_mul(Xp, ld7(P.X_pj + i * 7));
     const V3 axis = ld3(P.axis + i * 3);
     const SV avj = ld6(s + Y.vj + i * 6);
-    const float* qd = s + Y.qd;
-    const float* S = s + Y.S;
-    const float* aS = s + Y.aS;
-    float* aqd = s + Y.aqd;
+    const SP qd = s + Y.qd;
+    const SP S = s + Y.S;
+    const SP aS = s + Y.aS;
+    const SP aqd = s + Y.aqd;
     Xf aXsj = xf_zero();
     if (type == JOINT_PRISMATIC) {
         const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
@@ -230,7 +240,7 @@ DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, float* s, int i) {   
     st7(s + Y.pX + i * 7, aXsj);
 }
 
-DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, float* s, int i) {     // A4
+DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, SP s, int i) {     // A4
     const int par = P.parent[i];
     Xf aXsc = ld7(s + Y.aXsc + i * 7);
     for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) aXsc += ld7(s + Y.pX + P.child_idx[k] * 7);
@@ -242,13 +252,13 @@ DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, float* s, int i) {    
     st7(s + Y.pX + i * 7, aXp);
 }
 
-DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, float* s, int i) {     // A5
+DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // A5
     const int par = P.parent[i], type = P.type[i], qs = P.q_start[i];
     if (type == JOINT_FIXED) return;
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     const Xf Xpj = ld7(P.X_pj + i * 7);
-    const float* q = s + Y.q;
-    float* aq = s + Y.aq;
+    const SP q = s + Y.q;
+    const SP aq = s + Y.aq;
     const Xf aXl = xf_mul_adj_b(Xp, ld7(s + Y.aXsc + i * 7));   // X_sc = X_p X_l
     const Xf aXjc = xf_mul_adj_b(Xpj, aXl);                      // X_l = X_pj X_jc
     const V3 axis = ld3(P.axis + i * 3);
@@ -259,15 +269,15 @@ DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, float* s, int i) {    
 }
 
 template <class Grp>
-DFX_HD void kin_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void kin_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     // all five passes run as CTA-wide (link, environment) tasks, link-major: uniform joint types per warp
-    g.cta_tasks(s, P.L, true, [&](float* se, int i) { kin_adj_local(P, Y, se, i); });
+    g.cta_tasks(s, P.L, true, [&](SP se, int i) { kin_adj_local(P, Y, se, i); });
     for (int lev = P.nlev - 1; lev >= 0; --lev)
-        level_tasks(P, s, lev, false, g, [&](float* se, int i) { kin_adj_velocity(P, Y, se, i); });
-    g.cta_tasks(s, P.L, false, [&](float* se, int i) { kin_adj_motion(P, Y, se, i); });
+        level_tasks(P, s, lev, false, g, [&](SP se, int i) { kin_adj_velocity(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_motion(P, Y, se, i); });
     for (int lev = P.nlev - 1; lev >= 0; --lev)
-        level_tasks(P, s, lev, false, g, [&](float* se, int i) { kin_adj_chain(P, Y, se, i); });
-    g.cta_tasks(s, P.L, false, [&](float* se, int i) { kin_adj_joint(P, Y, se, i); });
+        level_tasks(P, s, lev, false, g, [&](SP se, int i) { kin_adj_chain(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_joint(P, Y, se, i); });
 }
 
 // =====================================================================================
@@ -284,7 +294,7 @@ struct BodyInertia {
     V3 u;     // R^T c
     float m;
 };
-DFX_HD BodyInertia body_inertia(const Pack& P, const float* Xsm7, int i) {
+DFX_HD BodyInertia body_inertia(const Pack& P, SP Xsm7, int i) {
     BodyInertia B;
     B.R = q_to_m3(ld4(Xsm7 + 3));
     B.Ic = ld9(P.I_c + i * 9);
@@ -328,7 +338,7 @@ DFX_HD void inertia_apply_adj(const BodyInertia& B, SV x, SV r, M3& aR, V3& au, 
     outer_acc(aR, x.v, avb);
 }
 
-DFX_HD void body_force_link_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+DFX_HD void body_force_link_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     const BodyInertia B = body_inertia(P, s + Y.Xsm + i * 7, i);
     const V3 c = ld3(s + Y.Xsm + i * 7);
     const SV v = ld6(s + Y.v + i * 6), a = ld6(s + Y.a + i * 6);
@@ -341,14 +351,14 @@ DFX_HD void body_force_link_fwd(const Pack& P, const Layout& Y, float* s, int i)
 }
 
 template <class Grp>
-DFX_HD void body_force_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void body_force_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     DFX_FOR(i, P.L) body_force_link_fwd(P, Y, s, i);
     g.sync();
 }
 
 // adjoint: af[i] (adjoint of body_f_s[i]) plus what crba_adj left in aR[i] / au[i] -> aXsm, av, aa
-DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, float* s, int i) {
-    const float* Xsm7 = s + Y.Xsm + i * 7;
+DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, SP s, int i) {
+    const SP Xsm7 = s + Y.Xsm + i * 7;
     const BodyInertia B = body_inertia(P, Xsm7, i);
     const V3 c = ld3(Xsm7);
     const SV v = ld6(s + Y.v + i * 6), a = ld6(s + Y.a + i * 6);
@@ -375,7 +385,7 @@ DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, float* s, int i)
 }
 
 template <class Grp>
-DFX_HD void body_force_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void body_force_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     DFX_FOR(i, P.L) body_force_link_adj(P, Y, s, i);
     g.sync();
 }
@@ -402,11 +412,11 @@ constexpr int kFxAdjointLog2 = 27;
 // Split in fp32: x = w * scale (exact, power-of-two scale), h = rint(x / 2^21), l = x - h * 2^21 (exact: fma),
 // so that hi * 2^21 + rint(l) == rint(x) with |rint(l)| <= 2^20, using 32-bit conversions only.
 template <int N, class Grp>
-DFX_HD void fx_scatter(int* lo, int* hi, unsigned* poison, int body, const float (&w)[N], float scale, const Grp& g) {
+DFX_HD void fx_scatter(SPi lo, SPi hi, SPu poison, int body, const float (&w)[N], float scale, const Grp& g) {
     bool ok = true;
 #pragma unroll
     for (int c = 0; c < N; ++c) ok = ok && (fabsf(w[c] * scale) < kFxLimit);     // false for NaN / Inf / out of range
-    if (!ok) { g.atomic_or(poison, 1u << (body & 31)); return; }
+    if (!ok) { g.atomic_or(&poison[0], 1u << (body & 31)); return; }
     constexpr float kUnit = (float)(1 << kFxLowBits), kUnitInv = 1.0f / (float)(1 << kFxLowBits);
 #pragma unroll
     for (int c = 0; c < N; ++c) {
@@ -414,8 +424,8 @@ DFX_HD void fx_scatter(int* lo, int* hi, unsigned* poison, int body, const float
         const float h = rintf(x * kUnitInv);
         const int l = (int)rintf(fmaf(h, -kUnit, x));
         const int hw = (int)h;
-        if (l != 0) g.fx_add(lo + c, l);
-        if (hw != 0) g.fx_add(hi + c, hw);
+        if (l != 0) g.fx_add(&lo[c], l);
+        if (hw != 0) g.fx_add(&hi[c], hw);
     }
 }
 // the fp32 value of an accumulator (two roundings at most; exact whenever |hi| < 2^24 and |lo| < 2^24)
@@ -447,7 +457,7 @@ DFX_HD float fx_pow2_scale(float m) {
 // =====================================================================================
 // penalty ground contact (y-up plane), smooth Coulomb friction
 // =====================================================================================
-DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int k) {
+DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, SP s, int k) {
     const int b = P.cbody[k];
     const Xf X = ld7(s + Y.Xsc + b * 7);
     const SV vs = ld6(s + Y.v + b * 6);
@@ -471,7 +481,7 @@ DFX_HD SV contact_point_fwd(const Pack& P, const Layout& Y, const float* s, int 
 
 // signed height of contact point k above the ground plane (negative: penetrating); NaN counts as penetrating
 // so that a non-finite state still reaches the poison bit
-DFX_HD bool contact_penetrates(const Pack& P, const Layout& Y, const float* s, int k) {
+DFX_HD bool contact_penetrates(const Pack& P, const Layout& Y, SP s, int k) {
     const V3 p = xf_point(ld7(s + Y.Xsc + P.cbody[k] * 7), ld3(P.cpoint + k * 3));
     return !(p.y - P.cdist[k] >= 0.0f);
 }
@@ -480,24 +490,24 @@ DFX_HD bool contact_penetrates(const Pack& P, const Layout& Y, const float* s, i
 // Typically a fifth of the points penetrate: the (point, environment) pairs that do are compacted over the whole
 // CTA first, so the force model runs with full warps instead of a few lanes per group.
 template <class Grp>
-DFX_HD void contact_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void contact_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     if (!P.ground) return;
-    g.cta_compact(s, P.C, [&](float* se, int k) { return contact_penetrates(P, Y, se, k); },
-                  [&](float* se, int k) {
+    g.cta_compact(s, P.C, [&](SP se, int k) { return contact_penetrates(P, Y, se, k); },
+                  [&](SP se, int k) {
         const SV w = contact_point_fwd(P, Y, se, k);
-        int* lo = reinterpret_cast<int*>(se + Y.fx);
+        const SPi lo = sp_int(se + Y.fx);
         const float c6[6] = {w.w.x, w.w.y, w.w.z, w.v.x, w.v.y, w.v.z};
-        fx_scatter(lo + P.cbody[k] * 6, lo + P.L * 6 + P.cbody[k] * 6, reinterpret_cast<unsigned*>(se + Y.cmask), P.cbody[k], c6, kFxForward, g);
+        fx_scatter(lo + P.cbody[k] * 6, lo + P.L * 6 + P.cbody[k] * 6, sp_uint(se + Y.cmask), P.cbody[k], c6, kFxForward, g);
     });
 }
 
 template <class Grp>
-DFX_HD void wrench_collect(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void wrench_collect(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     if (!P.ground && P.M == 0) return;
     g.sync();
-    int* lo = reinterpret_cast<int*>(s + Y.fx);
-    int* hi = lo + P.L * 6;
-    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const SPi lo = sp_int(s + Y.fx);
+    const SPi hi = lo + P.L * 6;
+    const SPu poison = sp_uint(s + Y.cmask);
     const unsigned bad = *poison;
     DFX_FOR(it, P.L * 6) {
         const int l = lo[it], h = hi[it];
@@ -515,7 +525,7 @@ DFX_HD void wrench_collect(const Pack& P, const Layout& Y, float* s, const Grp& 
 // atomics (only penetrating contacts do any work; the summation order, hence the last bits of the
 // GRADIENT, may vary between runs -- the forward pass stays deterministic)
 template <class Grp>
-DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, float scale, const Grp& g) {
+DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, SP s, int k, float scale, const Grp& g) {
     const int b = P.cbody[k];
     const Xf X = ld7(s + Y.Xsc + b * 7);
     const SV vs = ld6(s + Y.v + b * 6);
@@ -569,31 +579,31 @@ DFX_HD void contact_point_adj(const Pack& P, const Layout& Y, float* s, int k, f
     cross_adj(vs.w, p, adpdt, aw, ap);
     // p = X.p + R(X.q) pt - n d
     const Q4 aq = qrot_adj_q(X.q, pt, ap);
-    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const SPu poison = sp_uint(s + Y.cmask);
     const float c7[7] = {ap.x, ap.y, ap.z, aq.x, aq.y, aq.z, aq.w};
     const float c6[6] = {aw.x, aw.y, aw.z, adpdt.x, adpdt.y, adpdt.z};
     if (P.M > 0) {
         // muscle models scatter everything in fixed point: low words accumulate in aXsc / av themselves (both are
         // still all-zero in this phase), high words in fxH; adj_collect() converts back
-        int* hi = reinterpret_cast<int*>(s + Y.fxH);
-        fx_scatter(reinterpret_cast<int*>(s + Y.aXsc) + b * 7, hi + b * 7, poison, b, c7, scale, g);
-        fx_scatter(reinterpret_cast<int*>(s + Y.av) + b * 6, hi + P.L * 7 + b * 6, poison, b, c6, scale, g);
+        const SPi hi = sp_int(s + Y.fxH);
+        fx_scatter(sp_int(s + Y.aXsc) + b * 7, hi + b * 7, poison, b, c7, scale, g);
+        fx_scatter(sp_int(s + Y.av) + b * 6, hi + P.L * 7 + b * 6, poison, b, c6, scale, g);
     } else {
         // contact-only models: at most a handful of penetrating points share a body, and the compare-and-swap
         // float add is then 8-12 % cheaper for the whole adjoint than fixed point + read-back (same-box A/B, Ant
         // and Humanoid).  The order of these few adds is not fixed, so the last bits of the gradient may vary.
-        float* ax = s + Y.aXsc + b * 7;
-        float* avp = s + Y.av + b * 6;
+        const SP ax = s + Y.aXsc + b * 7;
+        const SP avp = s + Y.av + b * 6;
 #pragma unroll
-        for (int c = 0; c < 7; ++c) g.atomic_add(ax + c, c7[c]);
+        for (int c = 0; c < 7; ++c) g.atomic_add(&ax[c], c7[c]);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) g.atomic_add(avp + c, c6[c]);
+        for (int c = 0; c < 6; ++c) g.atomic_add(&avp[c], c6[c]);
     }
 }
 
 // power-of-two fixed-point scale of the cotangent scatter of this environment and substep, from max|af|
 template <class Grp>
-DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     float m = 0.0f;
     DFX_FOR(i, P.L * 6) { const float v = fabsf(s[Y.af + i]); m = (v > m) ? v : m; }   // NaN never wins: the poison bit handles it
     const float scale = fx_pow2_scale(g.group_max(m));
@@ -602,15 +612,15 @@ DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, float* s, const G
 }
 
 template <class Grp>
-DFX_HD void adj_collect(const Pack& P, const Layout& Y, float* s, float scale, const Grp& g) {
+DFX_HD void adj_collect(const Pack& P, const Layout& Y, SP s, float scale, const Grp& g) {
     g.sync();
-    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
-    int* hi = reinterpret_cast<int*>(s + Y.fxH);
+    const SPu poison = sp_uint(s + Y.cmask);
+    const SPi hi = sp_int(s + Y.fxH);
     const unsigned bad = *poison;
     const float inv = 1.0f / scale;
-    float* dst = s + Y.aXsc;                       // aXsc (L,7) and av (L,6) are adjacent
+    const SP dst = s + Y.aXsc;                       // aXsc (L,7) and av (L,6) are adjacent
     DFX_FOR(it, P.L * 13) {
-        int l; memcpy(&l, dst + it, 4);
+        const int l = sp_int(dst)[it];
         const int h = hi[it];
         if ((l | h) != 0) { dst[it] = fx_value(l, h, inv); hi[it] = 0; }
     }
@@ -626,21 +636,21 @@ DFX_HD void adj_collect(const Pack& P, const Layout& Y, float* s, float scale, c
 }
 
 template <class Grp>
-DFX_HD void contact_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void contact_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     if (!P.ground) return;
-    g.cta_compact(s, P.C, [&](float* se, int k) { return contact_penetrates(P, Y, se, k); },
-                  [&](float* se, int k) { contact_point_adj(P, Y, se, k, se[Y.fxs], g); });
+    g.cta_compact(s, P.C, [&](SP se, int k) { return contact_penetrates(P, Y, se, k); },
+                  [&](SP se, int k) { contact_point_adj(P, Y, se, k, se[Y.fxs], g); });
 }
 
 // =====================================================================================
 // muscles: straight-line way-point segments pulling two links together
 // =====================================================================================
 template <class Grp>
-DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     if (P.M == 0) return;
-    int* lo = reinterpret_cast<int*>(s + Y.fx);
-    int* hi = lo + P.L * 6;
-    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const SPi lo = sp_int(s + Y.fx);
+    const SPi hi = lo + P.L * 6;
+    const SPu poison = sp_uint(s + Y.cmask);
     DFX_FOR(m, P.M) {
         const float act = s[Y.musc + m];
         for (int i = P.mstart[m]; i < P.mstart[m + 1] - 1; ++i) {
@@ -662,11 +672,11 @@ DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 }
 
 template <class Grp>
-DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, float scale, const Grp& g) {
+DFX_HD void muscle_adj(const Pack& P, const Layout& Y, SP s, float scale, const Grp& g) {
     if (P.M == 0) return;
-    int* lo = reinterpret_cast<int*>(s + Y.aXsc);   // still all-zero in this phase: doubles as the low words
-    int* hi = reinterpret_cast<int*>(s + Y.fxH);
-    unsigned* poison = reinterpret_cast<unsigned*>(s + Y.cmask);
+    const SPi lo = sp_int(s + Y.aXsc);   // still all-zero in this phase: doubles as the low words
+    const SPi hi = sp_int(s + Y.fxH);
+    const SPu poison = sp_uint(s + Y.cmask);
     DFX_FOR(m, P.M) {
         const float act = s[Y.musc + m];
         float aact = 0.0f;
@@ -706,19 +716,19 @@ DFX_HD void muscle_adj(const Pack& P, const Layout& Y, float* s, float scale, co
 // joint torques: leaf -> root wrench accumulation and projection on the motion subspace
 // =====================================================================================
 // T1 (leaf->root, thin): f_tot[i] = f[i] + sum f_tot[children]   T2 (parallel): project on S, add PD / limits
-DFX_HD void tau_accum_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+DFX_HD void tau_accum_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     SV ft = sv_zero();
     for (int k = P.child_start[i + 1] - 1; k >= P.child_start[i]; --k) ft += ld6(s + Y.ft + P.child_idx[k] * 6);
     st6(s + Y.ft + i * 6, ld6(s + Y.f + i * 6) + ft);
 }
 
-DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, float* s, int i) {
+DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
     const SV f = ld6(s + Y.ft + i * 6);
-    const float* q = s + Y.q;
-    const float* qd = s + Y.qd;
-    const float* S = s + Y.S;
-    float* tau = s + Y.tau;
+    const SP q = s + Y.q;
+    const SP qd = s + Y.qd;
+    const SP S = s + Y.S;
+    const SP tau = s + Y.tau;
     const float tke = P.target_ke[i], tkd = P.target_kd[i];
     if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
         const float qq = q[qs], qdv = qd[ds];
@@ -738,7 +748,7 @@ DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, float* s, int i) {
 }
 
 template <class Grp>
-DFX_HD void tau_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void tau_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     for (int lev = P.nlev - 1; lev >= 0; --lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
         for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_fwd(P, Y, s, P.level_links[k]);
@@ -750,15 +760,15 @@ DFX_HD void tau_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 
 // adjoint: `atau` (D) in; af[] becomes the adjoint of body_f_s; aS, aq, aqd, aact accumulate.
 // T2' (parallel): per-link contribution to a(f_tot) + aS, aq, aqd, aact ;  T1' (root->leaf, thin): af[i] += af[parent]
-DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, float* s, const float* atau, int i) {
+DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, SP s, SP atau, int i) {
     const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
     SV af = sv_zero();
     const SV f = ld6(s + Y.ft + i * 6);
-    const float* q = s + Y.q;
-    const float* S = s + Y.S;
-    float* aS = s + Y.aS;
-    float* aq = s + Y.aq;
-    float* aqd = s + Y.aqd;
+    const SP q = s + Y.q;
+    const SP S = s + Y.S;
+    const SP aS = s + Y.aS;
+    const SP aq = s + Y.aq;
+    const SP aqd = s + Y.aqd;
     if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
         const float at = atau[ds];
         add6(aS + ds * 6, f * (-at));
@@ -785,15 +795,15 @@ DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, float* s, const floa
     st6(s + Y.af + i * 6, af);
 }
 
-DFX_HD void tau_accum_adj(const Pack& P, const Layout& Y, float* s, int i) {
+DFX_HD void tau_accum_adj(const Pack& P, const Layout& Y, SP s, int i) {
     const int par = P.parent[i];
     if (par >= 0) add6(s + Y.af + i * 6, ld6(s + Y.af + par * 6));   // f_tot[parent] = f[parent] + sum f_tot[children]
 }
 
 template <class Grp>
-DFX_HD void tau_adj(const Pack& P, const Layout& Y, float* s, const float* atau, const Grp& g) {
-    const int atau_off = (int)(atau - s);
-    g.cta_tasks(s, P.L, true, [&](float* se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
+DFX_HD void tau_adj(const Pack& P, const Layout& Y, SP s, SP atau, const Grp& g) {
+    const int atau_off = (int)(atau - s);   // (element offset inside the scratch)
+    g.cta_tasks(s, P.L, true, [&](SP se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
     for (int lev = 1; lev < P.nlev; ++lev) {
         const int b = P.level_start[lev], e = P.level_start[lev + 1];
         for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_adj(P, Y, s, P.level_links[k]);
@@ -808,7 +818,7 @@ DFX_HD int sym_idx(int i, int j) {  // packed upper triangle of a symmetric 6x6,
     return i * 6 - (i * (i - 1)) / 2 + (j - i);
 }
 // the 21 unique entries (packed upper triangle) of  I_s = Rb I_body Rb^T
-DFX_HD void inertia_sym21(const BodyInertia& B, float* o) {
+DFX_HD void inertia_sym21(const BodyInertia& B, SP o) {
     const float uu = dot(B.u, B.u);
     const float uv[3] = {B.u.x, B.u.y, B.u.z};
     M3 TLb, K;  // body-frame top-left block and [u]x
@@ -828,7 +838,7 @@ DFX_HD void inertia_sym21(const BodyInertia& B, float* o) {
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) o[sym_idx(i, 3 + j)] = B.m * TR.m[i][j];
 }
-DFX_HD SV sym21_apply(const float* o, SV x) {
+DFX_HD SV sym21_apply(SP o, SV x) {
     const float xv[6] = {x.w.x, x.w.y, x.w.z, x.v.x, x.v.y, x.v.z};
     float y[6];
     for (int i = 0; i < 6; ++i) {
@@ -840,12 +850,12 @@ DFX_HD SV sym21_apply(const float* o, SV x) {
 }
 
 template <class Grp>
-DFX_HD void crba_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void crba_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D, L = P.L;
-    float* Ic = s + Y.Icmp;
-    float* F = s + Y.Icmp + L * 21;
-    float* H = s + Y.A;
-    float* Lm = s + Y.Lm;
+    const SP Ic = s + Y.Icmp;
+    const SP F = s + Y.Icmp + L * 21;
+    const SP H = s + Y.A;
+    const SP Lm = s + Y.Lm;
     DFX_FOR(i, L) inertia_sym21(body_inertia(P, s + Y.Xsm + i * 7, i), Ic + i * 21);
     DFX_FOR(e, D * D) { H[e] = 0.0f; Lm[e] = 0.0f; }
     g.sync();
@@ -878,10 +888,10 @@ DFX_HD void crba_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 
 // Cholesky  L L^T = H + diag(armature)  (column by column), then A <- (L L^T)^-1 column-wise.
 template <class Grp>
-DFX_HD void chol_inverse(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void chol_inverse(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D;
-    float* A = s + Y.A;
-    float* Lm = s + Y.Lm;
+    const SP A = s + Y.A;
+    const SP Lm = s + Y.Lm;
     for (int j = 0; j < D; ++j) {
         float sj = A[j * D + j] + P.armature[j];
         for (int k = 0; k < j; ++k) { const float r = Lm[j * D + k]; sj -= r * r; }
@@ -914,7 +924,7 @@ DFX_HD void chol_inverse(const Pack& P, const Layout& Y, float* s, const Grp& g)
 
 // q'' = H^-1 tau
 template <class Grp>
-DFX_HD void solve_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void solve_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D;
     DFX_FOR(i, D) {
         float acc = 0.0f;
@@ -925,7 +935,7 @@ DFX_HD void solve_fwd(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 }
 // atau = H^-1 aqdd (written over tau);  aH -= atau (x) qdd   (aH lives in the Lm slot during backward)
 template <class Grp>
-DFX_HD void solve_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void solve_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D;
     DFX_FOR(i, D) {
         float acc = 0.0f;
@@ -942,9 +952,9 @@ DFX_HD void solve_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 
 // adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), aH in the Lm slot
 template <class Grp>
-DFX_HD void crba_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
+DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D, L = P.L;
-    const float* aH = s + Y.Lm;
+    const SP aH = s + Y.Lm;
     // body inertia parameters: for each link l and each ancestor dof a:  z = sum_b aH[a][b] S_b ;
     // cotangent S_a on  I_l z
     DFX_FOR(l, L) {
@@ -961,7 +971,7 @@ DFX_HD void crba_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
             }
             inertia_apply_adj(B, z, ld6(s + Y.S + a * 6), aR, au, dummy);
         }
-        float* o = s + Y.aIbar + l * 12;
+        const SP o = s + Y.aIbar + l * 12;
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) o[r * 3 + c] += aR.m[r][c];
         add3(o + 9, au);
@@ -988,11 +998,11 @@ DFX_HD void crba_adj(const Pack& P, const Layout& Y, float* s, const Grp& g) {
 // =====================================================================================
 // semi-implicit Euler
 // =====================================================================================
-DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, float* s, float dt, int i) {
+DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, SP s, float dt, int i) {
     const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
-    float* q = s + Y.q;
-    float* qd = s + Y.qd;
-    const float* qdd = s + Y.qdd;
+    const SP q = s + Y.q;
+    const SP qd = s + Y.qd;
+    const SP qdd = s + Y.qdd;
     if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
         const float qd_new = qd[ds] + qdd[ds] * dt;
         q[qs] = q[qs] + qd_new * dt;
@@ -1018,21 +1028,21 @@ DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, float* s, float d
 }
 
 template <class Grp>
-DFX_HD void integrate_fwd(const Pack& P, const Layout& Y, float* s, float dt, const Grp& g) {
+DFX_HD void integrate_fwd(const Pack& P, const Layout& Y, SP s, float dt, const Grp& g) {
     DFX_FOR(i, P.L) integrate_link_fwd(P, Y, s, dt, i);
     g.sync();
 }
 
 // adjoint: aq/aqd hold d/d(q', qd') on entry and d/d(q, qd) (direct part) on exit; aqdd is written.
 // q, qd, qdd in scratch are the substep INPUT values.
-DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, float* s, float dt, int i) {
+DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, SP s, float dt, int i) {
     const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
-    const float* q = s + Y.q;
-    const float* qd = s + Y.qd;
-    const float* qdd = s + Y.qdd;
-    float* aq = s + Y.aq;
-    float* aqd = s + Y.aqd;
-    float* aqdd = s + Y.aqdd;
+    const SP q = s + Y.q;
+    const SP qd = s + Y.qd;
+    const SP qdd = s + Y.qdd;
+    const SP aq = s + Y.aq;
+    const SP aqd = s + Y.aqd;
+    const SP aqdd = s + Y.aqdd;
     if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
         const float aqdn = aqd[ds] + aq[qs] * dt;
         aqd[ds] = aqdn;
@@ -1074,8 +1084,8 @@ DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, float* s, float d
 }
 
 template <class Grp>
-DFX_HD void integrate_adj(const Pack& P, const Layout& Y, float* s, float dt, const Grp& g) {
-    g.cta_tasks(s, P.L, true, [&](float* se, int i) { integrate_link_adj(P, Y, se, dt, i); });
+DFX_HD void integrate_adj(const Pack& P, const Layout& Y, SP s, float dt, const Grp& g) {
+    g.cta_tasks(s, P.L, true, [&](SP se, int i) { integrate_link_adj(P, Y, se, dt, i); });
 }
 
 // =====================================================================================
@@ -1083,7 +1093,7 @@ DFX_HD void integrate_adj(const Pack& P, const Layout& Y, float* s, float dt, co
 // =====================================================================================
 // forward dynamics up to q'' (everything the adjoint needs to re-create); scratch q, qd, act, musc set.
 template <class Grp>
-DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_mass, const Grp& g) {
+DFX_HD void substep_eval(const Pack& P, const Layout& Y, SP s, bool update_mass, const Grp& g) {
     kin_fwd(P, Y, s, g);
     body_force_fwd(P, Y, s, g);
     contact_fwd(P, Y, s, g);
@@ -1101,7 +1111,7 @@ DFX_HD void substep_eval(const Pack& P, const Layout& Y, float* s, bool update_m
 // forward intermediates), act, musc, A = H^-1 of the segment; aq, aqd = cotangents of the substep output.  Post: aq, aqd = cotangents of the substep input;
 // aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
 template <class Grp>
-DFX_HD void substep_adj(const Pack& P, const Layout& Y, float* s, float dt, bool apply_crba, const Grp& g) {
+DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool apply_crba, const Grp& g) {
     zero_range(s + Y.aXsc, Y.af - Y.aXsc, g);      // aXsc, av, aXsm, aS, aa are adjacent (af is overwritten by tau_adj)
     zero_range(s + Y.aIbar, P.L * 12, g);
     g.sync();

@@ -33,7 +33,7 @@ struct StepArgs {
 };
 
 template <class Grp>
-DFX_HD void dump_derived(const Pack& P, const Layout& Y, const float* s, const DfxDerived& d, int env, const Grp& g) {
+DFX_HD void dump_derived(const Pack& P, const Layout& Y, SP s, const DfxDerived& d, int env, const Grp& g) {
     const int L = P.L, D = P.D;
     if (d.body_X_sc) DFX_FOR(i, L * 7) d.body_X_sc[(long long)env * L * 7 + i] = s[Y.Xsc + i];
     if (d.body_X_sm) DFX_FOR(i, L * 7) d.body_X_sm[(long long)env * L * 7 + i] = s[Y.Xsm + i];
@@ -47,7 +47,7 @@ DFX_HD void dump_derived(const Pack& P, const Layout& Y, const float* s, const D
 }
 
 template <class Grp>
-DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp& g, int env, const StepArgs& a) {
+DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a) {
     const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
     DFX_FOR(i, Q) s[Y.q + i] = a.q[(long long)env * Q + i];
     DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
@@ -74,16 +74,10 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
             g.sync();
             chol_inverse(P, Y, s, g);
             if (a.has_derived && a.derived.L) DFX_FOR(e, DD) a.derived.L[(long long)env * DD + e] = s[Y.Lm + e];
-            if (a.tape) {
-                float* t = a.tape + a.hinv_base + ((long long)(sub / a.mm_freq) * a.N + env) * DD;
-                DFX_FOR(e, DD) t[e] = s[Y.A + e];
-            }
+            if (a.tape) g.block_out(a.tape + a.hinv_base, sub / a.mm_freq, a.N, env, s + Y.A, DD, false);
         }
         solve_fwd(P, Y, s, g);
-        if (a.tape) {   // q, qd still hold the values that ENTERED this substep
-            float* t = a.tape + ((long long)sub * a.N + env) * QD;
-            g.copy_row_out(t, s + Y.q, QD);
-        }
+        if (a.tape) g.block_out(a.tape, sub, a.N, env, s + Y.q, QD, true);   // q, qd still hold the values that ENTERED this substep
         if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, g);
         g.phase_sync();   // (also orders the tape / dump copies above before integrate_fwd overwrites q, qd)
         g.sync();
@@ -94,7 +88,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, float* s, const Grp
 }
 
 template <class Grp>
-DFX_HD void env_step_backward(const Pack& P, const Layout& Y, float* s, const Grp& g, int env, const StepArgs& a) {
+DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a) {
     const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
     DFX_FOR(i, D) { s[Y.act + i] = a.act[(long long)env * D + i]; s[Y.aact + i] = 0.0f; }
     DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
@@ -106,10 +100,10 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, float* s, const Gr
         const int seg = sub / a.mm_freq;
         const int s0 = seg * a.mm_freq;
         const bool seg_last = (sub == a.substeps - 1) || ((sub + 1) % a.mm_freq == 0);   // first visited of its segment
-        g.copy_row_async(s + Y.q, a.tape_in + ((long long)sub * a.N + env) * QD, QD);
+        g.block_in(s + Y.q, a.tape_in, sub, a.N, env, QD, true);
         if (seg_last) {
-            const float* th = a.tape_in + a.hinv_base + ((long long)seg * a.N + env) * DD;
-            DFX_FOR(e, DD) { s[Y.A + e] = th[e]; s[Y.Lm + e] = 0.0f; }
+            g.block_in(s + Y.A, a.tape_in + a.hinv_base, seg, a.N, env, DD, false);
+            DFX_FOR(e, DD) s[Y.Lm + e] = 0.0f;
         }
         g.copy_wait_all();
         g.sync();

@@ -65,9 +65,9 @@ int emu_step_forward(const EmuPack* p, int n, int substeps, int mm_freq, double 
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
     a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
-    std::vector<float> scratch(p->host.layout.bwd_size + 16, 0.0f);
+    std::vector<float> scratch((size_t)(p->host.layout.bwd_size + 16) * DFX_ES, 0.0f);
     GroupSerial g{0};
-    for (int env = 0; env < n; ++env) env_step_forward(p->pack, p->host.layout, scratch.data(), g, env, a);
+    for (int env = 0; env < n; ++env) env_step_forward(p->pack, p->host.layout, SP{scratch.data()}, g, env, a);
     return 0;
 }
 
@@ -82,9 +82,9 @@ int emu_step_backward(const EmuPack* p, int n, int substeps, int mm_freq, double
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
     a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
-    std::vector<float> scratch(p->host.layout.bwd_size + 16, 0.0f);
+    std::vector<float> scratch((size_t)(p->host.layout.bwd_size + 16) * DFX_ES, 0.0f);
     GroupSerial g{0};
-    for (int env = 0; env < n; ++env) env_step_backward(p->pack, p->host.layout, scratch.data(), g, env, a);
+    for (int env = 0; env < n; ++env) env_step_backward(p->pack, p->host.layout, SP{scratch.data()}, g, env, a);
     return 0;
 }
 

@@ -88,3 +88,23 @@ def test_reference_solve_is_conditioning_limited(name):
             worst = max(worst, np.abs(ref[e] - x).max() / np.abs(x).max())
             cond = max(cond, np.linalg.cond(A))
     assert cond > 1e3 and worst > 1e-6, (cond, worst)
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "SNUHumanoidEnv", "CartPoleSwingUpEnv"])
+def test_strided_scratch_is_bit_identical(name):
+    """The tile kernels address the per-environment scratch with an element stride (structure-of-arrays over 32
+    environments, csrc/dfx_math.h DFX_ES).  Built here with stride 3 on the CPU: every result must be bit-identical
+    to the contiguous build -- an access that forgot the stride would read a neighbour's slot."""
+    d, model = load_golden(name)
+    n0 = int(d["meta/num_envs"])
+    S, mm, dt = int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    p = "case0/"
+    res = []
+    for es in (1, 3):
+        emu = EmuSim(model, n0, es=es)
+        musc = d[p + "musc"] if emu.desc.M else None
+        q, qd, tape, _ = emu.forward(d[p + "q0"], d[p + "qd0"], d[p + "act"], musc, S, mm, dt)
+        g = emu.backward(d[p + "act"], musc, tape, d[p + "gq_out"], d[p + "gqd_out"], S, mm, dt)
+        res.append([q, qd, tape] + [x for x in g if x is not None])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
