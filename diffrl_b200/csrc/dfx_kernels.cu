@@ -16,7 +16,7 @@
 #include <cstring>
 #include <string>
 
-#include "dfx_step.h"
+#include "dfx_launch.h"
 
 namespace dfx {
 
@@ -33,7 +33,8 @@ struct GroupCuda {
     __device__ __forceinline__ void fx_add(int* p, int v) const { atomicAdd(p, v); }
     // fp32 add on shared memory: an ATOMS.CAST.SPIN loop, used only where contention is a few lanes at most
     __device__ __forceinline__ void atomic_add(float* p, float v) const { atomicAdd(p, v); }
-    __device__ __forceinline__ float group_max(float v) const {
+    __device__ __forceinline__ float group_max(float v, float* slot) const {
+        (void)slot;
 #pragma unroll
         for (int o = G_ / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, G_));
         return v;
@@ -126,46 +127,6 @@ struct GroupCuda {
     __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };
 
-constexpr int kMaxThreads = 128;
-
-// Copy the pack's arrays into shared memory once per CTA and rebind the pointers.
-struct PackBlob {
-    const int* ints;
-    const float* floats;
-    int n_ints, n_floats;
-    // offsets of each pointer field (same order as PackHost::bind)
-    int int_off[17];
-    int float_off[17];
-};
-
-__device__ __forceinline__ Pack bind_pack(const Pack& header, const PackBlob& b, const int* ib, const float* fb) {
-    Pack p = header;
-    int ii = 0, fi = 0;
-    p.type = ib + b.int_off[ii++]; p.parent = ib + b.int_off[ii++]; p.q_start = ib + b.int_off[ii++];
-    p.qd_start = ib + b.int_off[ii++]; p.level_start = ib + b.int_off[ii++]; p.level_links = ib + b.int_off[ii++];
-    p.child_start = ib + b.int_off[ii++]; p.child_idx = ib + b.int_off[ii++]; p.anc_start = ib + b.int_off[ii++];
-    p.anc_dofs = ib + b.int_off[ii++]; p.sub_start = ib + b.int_off[ii++]; p.sub_links = ib + b.int_off[ii++];
-    p.dof_link = ib + b.int_off[ii++]; p.cbody_start = ib + b.int_off[ii++]; p.cbody = ib + b.int_off[ii++];
-    p.mstart = ib + b.int_off[ii++]; p.mlinks = ib + b.int_off[ii++];
-    p.X_pj = fb + b.float_off[fi++]; p.X_cm = fb + b.float_off[fi++]; p.axis = fb + b.float_off[fi++];
-    p.I_c = fb + b.float_off[fi++]; p.mass = fb + b.float_off[fi++]; p.target_ke = fb + b.float_off[fi++];
-    p.target_kd = fb + b.float_off[fi++]; p.limit_ke = fb + b.float_off[fi++]; p.limit_kd = fb + b.float_off[fi++];
-    p.target = fb + b.float_off[fi++]; p.limit_lower = fb + b.float_off[fi++]; p.limit_upper = fb + b.float_off[fi++];
-    p.armature = fb + b.float_off[fi++]; p.cpoint = fb + b.float_off[fi++]; p.cdist = fb + b.float_off[fi++];
-    p.cmat = fb + b.float_off[fi++]; p.mpoints = fb + b.float_off[fi++];
-    return p;
-}
-
-struct KernelArgs {
-    Pack header;
-    PackBlob blob;
-    Layout layout;
-    StepArgs step;
-    int scratch_stride;   // floats per environment
-    int pack_smem_floats; // floats reserved at the start of dynamic smem for the staged pack
-    int cta_area_floats;  // then: CTA-wide task counter + task list (cta_compact)
-};
-
 // SL..SM > 0: model sizes known at compile time (the six DiffRL articulations are pre-instantiated); the scratch
 // layout and every loop bound then fold into immediates.  SL == 0: generic run-time sizes.
 template <int G, bool BACKWARD, int SL, int SD, int SQ, int SC, int SM>
@@ -215,6 +176,7 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
 using namespace dfx;
 
 struct dfx_pack {
+    bool tile;       // stepped by the 32-environment tile kernels (dfx_tile.cu); fixes the tape layout
     PackHost host;
     int device;
     int* d_ints;
@@ -260,6 +222,9 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
     p->blob.ints = p->d_ints; p->blob.floats = p->d_floats;
     p->blob.n_ints = (int)p->host.ints.size(); p->blob.n_floats = (int)p->host.floats.size();
     for (int i = 0; i < 17; ++i) { p->blob.int_off[i] = (int)p->host.int_off[i]; p->blob.float_off[i] = (int)p->host.float_off[i]; }
+    // flag bit 5 (32) keeps a supported articulation on the lane-group kernels (A/B runs); fixed per pack because
+    // the two kernel families lay the tape out differently
+    p->tile = !(g_flags & 32) && dfx_tile_supported(p->header.L, p->header.D, p->header.Q, p->header.C, p->header.M);
     return p;
 }
 
@@ -281,6 +246,7 @@ int dfx_pack_query(const dfx_pack_t* p, int what) {
         case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
         case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
         case DFX_QUERY_TREE_DEPTH: return p->header.nlev;
+        case DFX_QUERY_TAPE_TILE: return p->tile ? 32 : 0;
     }
     return -1;
 }
@@ -291,8 +257,11 @@ int dfx_pack_set_gravity(dfx_pack_t* p, float gx, float gy, float gz, int ground
     return 0;
 }
 
+// environments as laid out in the tape: tile kernels pad to whole 32-environment tiles
+static int tape_envs(const dfx_pack* p, int n) { return p->tile ? ((n + 31) / 32) * 32 : n; }
+
 long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq) {
-    return tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).total;
+    return tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).total;
 }
 
 }  // extern "C"
@@ -381,6 +350,16 @@ static cudaError_t launch(const dfx_pack* p, const StepArgs& step, cudaStream_t 
     return launch_impl<G, BWD, 0, 0, 0, 0, 0>(p, step, stream);
 }
 
+static cudaError_t launch_tile(const dfx_pack* p, const StepArgs& step, bool backward, cudaStream_t stream) {
+    KernelArgs ka;
+    ka.header = p->header;
+    ka.blob = p->blob;
+    ka.step = step;
+    cudaError_t e = dfx_tile_launch(ka, backward, stream);
+    g_launches.fetch_add(1);
+    return e;
+}
+
 static int pick_group(const dfx_pack* p) {
     if (g_group) return g_group;
     const int widest = p->header.D > p->header.L ? p->header.D : p->header.L;
@@ -391,6 +370,17 @@ extern "C" {
 
 int dfx_launch_plan(const dfx_pack_t* p, int backward, int out[6]) {
     if (!p || !out) return (int)cudaErrorInvalidValue;
+    if (p->tile) {      // one CTA per SM: a tile of 32 environments, lane = environment
+        KernelArgs ka;
+        ka.header = p->header;
+        ka.blob = p->blob;
+        const size_t smem = dfx_tile_smem(ka, backward != 0);
+        const Layout& Y = p->host.layout;
+        out[0] = 32; out[1] = 32; out[2] = (int)((227 * 1024) / (smem + 1024)); out[3] = (int)smem;
+        out[4] = ((backward ? Y.bwd_size : Y.fwd_size) + 3) & ~3;
+        out[5] = (int)smem - out[4] * 32 * 4;
+        return 0;
+    }
     const int G = pick_group(p);
     const LaunchPlan lp = plan_launch(p, G, backward != 0);
     out[0] = G; out[1] = lp.envs_per_cta; out[2] = lp.ctas_per_sm; out[3] = (int)lp.smem;
@@ -409,9 +399,10 @@ int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, doub
     a.dt_sub = (float)(dt / (double)substeps);
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
-    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).hinv_base;
     a.flags = g_flags;
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->tile) return (int)launch_tile(p, a, false, st);
     switch (pick_group(p)) {
         case 8: return (int)launch<8, false>(p, a, st);
         case 16: return (int)launch<16, false>(p, a, st);
@@ -431,9 +422,10 @@ int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, dou
     a.dt_sub = (float)(dt / (double)substeps);
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
-    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, n, substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).hinv_base;
     a.flags = g_flags;
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->tile) return (int)launch_tile(p, a, true, st);
     switch (pick_group(p)) {
         case 8: return (int)launch<8, true>(p, a, st);
         case 16: return (int)launch<16, true>(p, a, st);

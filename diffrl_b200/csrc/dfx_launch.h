@@ -1,0 +1,59 @@
+// dfx_launch.h -- launch-side structs shared by the lane-group kernels (dfx_kernels.cu) and the 32-environment
+// tile kernels (dfx_tile.cu): the packed model blob, its staging into shared memory, the kernel argument block.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "dfx_step.h"
+
+namespace dfx {
+
+constexpr int kMaxThreads = 128;
+
+// Copy the pack's arrays into shared memory once per CTA and rebind the pointers.
+struct PackBlob {
+    const int* ints;
+    const float* floats;
+    int n_ints, n_floats;
+    // offsets of each pointer field (same order as PackHost::bind)
+    int int_off[17];
+    int float_off[17];
+};
+
+__device__ __forceinline__ Pack bind_pack(const Pack& header, const PackBlob& b, const int* ib, const float* fb) {
+    Pack p = header;
+    int ii = 0, fi = 0;
+    p.type = ib + b.int_off[ii++]; p.parent = ib + b.int_off[ii++]; p.q_start = ib + b.int_off[ii++];
+    p.qd_start = ib + b.int_off[ii++]; p.level_start = ib + b.int_off[ii++]; p.level_links = ib + b.int_off[ii++];
+    p.child_start = ib + b.int_off[ii++]; p.child_idx = ib + b.int_off[ii++]; p.anc_start = ib + b.int_off[ii++];
+    p.anc_dofs = ib + b.int_off[ii++]; p.sub_start = ib + b.int_off[ii++]; p.sub_links = ib + b.int_off[ii++];
+    p.dof_link = ib + b.int_off[ii++]; p.cbody_start = ib + b.int_off[ii++]; p.cbody = ib + b.int_off[ii++];
+    p.mstart = ib + b.int_off[ii++]; p.mlinks = ib + b.int_off[ii++];
+    p.X_pj = fb + b.float_off[fi++]; p.X_cm = fb + b.float_off[fi++]; p.axis = fb + b.float_off[fi++];
+    p.I_c = fb + b.float_off[fi++]; p.mass = fb + b.float_off[fi++]; p.target_ke = fb + b.float_off[fi++];
+    p.target_kd = fb + b.float_off[fi++]; p.limit_ke = fb + b.float_off[fi++]; p.limit_kd = fb + b.float_off[fi++];
+    p.target = fb + b.float_off[fi++]; p.limit_lower = fb + b.float_off[fi++]; p.limit_upper = fb + b.float_off[fi++];
+    p.armature = fb + b.float_off[fi++]; p.cpoint = fb + b.float_off[fi++]; p.cdist = fb + b.float_off[fi++];
+    p.cmat = fb + b.float_off[fi++]; p.mpoints = fb + b.float_off[fi++];
+    return p;
+}
+
+struct KernelArgs {
+    Pack header;
+    PackBlob blob;
+    Layout layout;
+    StepArgs step;
+    int scratch_stride;   // floats per environment
+    int pack_smem_floats; // floats reserved at the start of dynamic smem for the staged pack
+    int cta_area_floats;  // then: CTA-wide task counter + task list (cta_compact)
+};
+
+
+}  // namespace dfx
+
+// ---- tile kernels (dfx_tile.cu): one CTA = 32 environments, lane = environment, warp = link / dof / contact
+// true when a size-specialised tile kernel exists for this articulation
+bool dfx_tile_supported(int L, int D, int Q, int C, int M);
+// dynamic shared memory of the tile kernel (bytes): pack + task list + 32 x scratch
+size_t dfx_tile_smem(const dfx::KernelArgs& ka, bool backward);
+cudaError_t dfx_tile_launch(dfx::KernelArgs& ka, bool backward, cudaStream_t stream);

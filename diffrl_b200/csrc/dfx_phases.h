@@ -18,7 +18,7 @@
 // deterministic gathers, and nothing but (q, qd) per substep is taped: the adjoint recomputes
 // the substep in scratch memory.
 //
-// `Grp` provides: static G, lane, sync(), cta_tasks(), cta_compact(), fx_add(int*, int), atomic_add(float*, float), group_max(float), atomic_or(unsigned*, unsigned).
+// `Grp` provides: static G, lane, sync(), cta_tasks(), cta_compact(), fx_add(int*, int), atomic_add(float*, float), group_max(float, SP slot), atomic_or(unsigned*, unsigned).
 #pragma once
 
 #include "dfx_math.h"
@@ -34,7 +34,7 @@ struct GroupSerial {  // host / single-lane execution
     DFX_HD void atomic_or(unsigned* p, unsigned v) const { *p |= v; }
     DFX_HD void fx_add(int* p, int v) const { *p += v; }
     DFX_HD void atomic_add(float* p, float v) const { *p += v; }
-    DFX_HD float group_max(float v) const { return v; }
+    DFX_HD float group_max(float v, SP slot) const { (void)slot; return v; }
     // run f(scratch of env, k) for k in [0, n) for every environment the executing CTA holds (here: this one)
     template <class F>
     DFX_HD void cta_tasks(SP s, int n, bool lead, F f) const { (void)lead; for (int k = 0; k < n; ++k) f(s, k); }
@@ -606,7 +606,7 @@ template <class Grp>
 DFX_HD float adj_scatter_scale(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     float m = 0.0f;
     DFX_FOR(i, P.L * 6) { const float v = fabsf(s[Y.af + i]); m = (v > m) ? v : m; }   // NaN never wins: the poison bit handles it
-    const float scale = fx_pow2_scale(g.group_max(m));
+    const float scale = fx_pow2_scale(g.group_max(m, s + Y.fxs));
     if (g.lane == 0) s[Y.fxs] = scale;       // CTA-wide contact tasks of this environment read it from here
     return scale;
 }

@@ -70,6 +70,17 @@ class ArticulationEngine:
                         "dfx_pack_set_gravity")
             self._gravity = key
 
+    def tape_rows(self, tape, substeps):
+        """The [substeps, num_envs, row] view of the tape's per-substep rows as a NEW tensor, whatever the kernel
+        family's layout (debugging / tests; the tape is otherwise opaque to callers)."""
+        row = int(self.lib.dfx_pack_query(self.pack, 8))
+        tile = int(self.lib.dfx_pack_query(self.pack, 9))
+        if not tile:
+            return tape[: substeps * self.N * row].view(substeps, self.N, row).clone()
+        ntiles = (self.N + tile - 1) // tile
+        t = tape[: substeps * ntiles * row * tile].view(substeps, ntiles, row, tile)
+        return t.permute(0, 1, 3, 2).reshape(substeps, ntiles * tile, row)[:, : self.N].contiguous()
+
     def tape_floats(self, substeps, mm_freq):
         return int(self.lib.dfx_tape_floats(self.pack, self.N, substeps, mm_freq))
 

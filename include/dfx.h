@@ -100,7 +100,8 @@ enum {
     DFX_QUERY_FWD_SCRATCH_FLOATS = 5, /* shared-memory floats per environment, forward */
     DFX_QUERY_BWD_SCRATCH_FLOATS = 6, /* shared-memory floats per environment, backward */
     DFX_QUERY_TREE_DEPTH = 7,
-    DFX_QUERY_TAPE_ROW_FLOATS = 8     /* floats per (substep, environment) tape row */
+    DFX_QUERY_TAPE_ROW_FLOATS = 8,    /* floats per (substep, environment) tape row */
+    DFX_QUERY_TAPE_TILE = 9           /* 0: tape blocks are [block][env][n]; 32: [block][tile of 32 envs][n][32] (tile kernels) */
 };
 
 /* Build the device-resident pack for CUDA device `device` (>= 0).  Returns NULL on failure and

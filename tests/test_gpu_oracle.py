@@ -89,8 +89,7 @@ def test_full_size_properties_ant_4096():
     qp, qdp, _, _ = eng.forward(t(q0[perm]), t(qd0[perm]), t(act[perm]), None, c["S"], c["mm"], c["dt"], want_tape=False)
     Q, D = o.desc.Q, o.desc.D
     assert torch.equal(qp.view(N, Q), q.view(N, Q)[torch.tensor(perm, device="cuda:0")])       # envs are independent
-    row = eng.lib.dfx_pack_query(eng.pack, 8)   # DFX_QUERY_TAPE_ROW_FLOATS
-    first = tape[: N * row].view(N, row)
+    first = eng.tape_rows(tape, 1)[0]            # rows of substep 0, env-major whatever the kernel family's layout
     assert torch.equal(first[:, :Q].reshape(-1), t(q0)) and torch.equal(first[:, Q:Q + D].reshape(-1), t(qd0))
     # one 16-substep call with the mass matrix refreshed every 8 == two chained 8-substep calls
     qa, qda, _, _ = eng.forward(t(q0), t(qd0), t(act), None, 16, 8, c["dt"], want_tape=False)

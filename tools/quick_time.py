@@ -13,7 +13,6 @@ flag_list = [int(f) for f in sys.argv[4].split(",")] if len(sys.argv) > 4 else [
 d, model = load_golden(name)
 n0, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
 desc, _ = articulation_from_model(model, n0)
-eng = ArticulationEngine(desc, N, "cuda:0")
 p = "case%d/" % (int(d["meta/num_cases"]) - 1)
 rng = np.random.default_rng(0)
 pick = rng.integers(0, n0, N)
@@ -24,6 +23,7 @@ gq = torch.randn_like(q0); gqd = torch.randn_like(qd0)
 for grp, flags in [(g_, f_) for g_ in groups for f_ in flag_list]:
     _capi.lib().dfx_set_group_size(grp)
     _capi.lib().dfx_set_flags(flags)
+    eng = ArticulationEngine(desc, N, "cuda:0")     # after the flags: bit 5 picks the kernel family per pack
     for _ in range(3):
         q, qd, tape, _x = eng.forward(q0, qd0, act, musc, S, mm, dt)
         eng.backward(act, musc, tape, gq, gqd, S, mm, dt)
