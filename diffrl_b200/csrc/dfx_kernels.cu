@@ -23,6 +23,7 @@ namespace dfx {
 template <int G_>
 struct GroupCuda {
     static constexpr int G = G_;
+    static constexpr bool kPathPasses = false;   // group barriers are cheap: level-by-level tree recursions
     int lane;
     unsigned mask;
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }

@@ -28,6 +28,10 @@ namespace dfx {
 
 struct GroupSerial {  // host / single-lane execution
     static constexpr int G = 1;
+#ifndef DFX_EMU_PATH_PASSES
+#define DFX_EMU_PATH_PASSES 0
+#endif
+    static constexpr bool kPathPasses = DFX_EMU_PATH_PASSES != 0;   // see kin_fwd / tau_fwd
     int lane;
     DFX_HD void sync() const {}
     DFX_HD void phase_sync() const {}
@@ -78,12 +82,15 @@ DFX_HD void zero_range(SP p, int n, const Grp& g) {
 
 // =====================================================================================
 // kinematics: transforms, motion subspace, velocity and bias acceleration.
-// Organised as PARALLEL per-link passes plus THIN tree recursions, so that the level-serial part of
-// the work is one transform product / a few vector adds per level instead of the whole per-link body:
+// Organised as PARALLEL per-link passes:
 //   K1 (parallel)   X_l = X_pj X_jc(q)                                  joint-local transform
-//   K2 (root->leaf) X_sc = X_sc[parent] X_l
-//   K3 (parallel)   X_sm = X_sc X_cm ; X_sj = X_sc[parent] X_pj ; S ; v_j = S qd
-//   K4 (root->leaf) v = v[parent] + v_j ; a = a[parent] + v x v_j
+//   K2   (root->leaf, or per link along its path) X_sc = X_sc[parent] X_l
+//   K3 (parallel)   X_sm = X_sc X_cm ;
+//                   X_sj = X_sc[parent] X_pj ; S ; v_j = S qd
+//   K4   (root->leaf, or per link along its path) v = v[parent] + v_j ; a = a[parent] + v x v_j
+// With Grp::kPathPasses (tile kernels: every barrier is CTA-wide) each link walks its own path from the root
+// instead of waiting for its parent -- three barriers per substep, same operations in the same order; the
+// lane-group kernels (cheap barriers, deeper trees) keep the level-by-level recursions K2 / K4.
 // Scratch: Y.Xl (L,7) and Y.vj (L,6).
 // =====================================================================================
 DFX_HD Xf joint_transform(const Pack& P, SP q, int i) {
@@ -100,17 +107,43 @@ DFX_HD void kin_local_fwd(const Pack& P, const Layout& Y, SP s, int i) {   // K1
     st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
 }
 
-DFX_HD void kin_chain_fwd(const Pack& P, const Layout& Y, SP s, int i) {   // K2
-    const int par = P.parent[i];
-    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
-    // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
-    // derivative along |q| (q is not assumed unit) agrees
-    st7(s + Y.Xsc + i * 7, xf_mul(Xp, ld7(s + Y.Xl + i * 7)));
+// call f(p) for the links on the path root -> ... -> parent(i) [-> i], in that order.  The path is re-walked
+// from i for every depth (O(depth^2) parent look-ups, all warp-uniform broadcasts from the staged pack): trees here
+// are 3-8 levels deep, and it replaces one barrier per level by none.
+template <class F>
+DFX_HD void for_path_root_first(const Pack& P, int i, bool include_self, F f) {
+    int dep = 0;
+    for (int p = P.parent[i]; p >= 0; p = P.parent[p]) ++dep;
+    for (int d = dep; d >= (include_self ? 0 : 1); --d) {
+        int p = i;
+        for (int k = 0; k < d; ++k) p = P.parent[p];
+        f(p);
+    }
 }
 
-DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // K3
+// K2: X_sc[parent] as the product of the joint-local transforms along the path from the root, multiplied in the
+// same order (and so to the same bits) as a level-by-level recursion X_sc = X_sc[parent] X_l would
+DFX_HD Xf kin_parent_transform(const Pack& P, const Layout& Y, SP s, int i) {
+    Xf Xp = xf_ident();
+    // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
+    // derivative along |q| (q is not assumed unit) agrees
+    for_path_root_first(P, i, false, [&](int p) { Xp = xf_mul(Xp, ld7(s + Y.Xl + p * 7)); });
+    return Xp;
+}
+
+// K3, and with PATH also K2 (X_sc of this link from the path product instead of a preceding level recursion)
+template <bool PATH>
+DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     const int par = P.parent[i], type = P.type[i], ds = P.qd_start[i];
-    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    Xf Xp, Xsc;
+    if (PATH) {
+        Xp = kin_parent_transform(P, Y, s, i);
+        Xsc = xf_mul(Xp, ld7(s + Y.Xl + i * 7));
+        st7(s + Y.Xsc + i * 7, Xsc);
+    } else {
+        Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+        Xsc = ld7(s + Y.Xsc + i * 7);
+    }
     const Xf Xsj = xf_mul(Xp, ld7(P.X_pj + i * 7));
     const V3 axis = ld3(P.axis + i * 3);
     const SP qd = s + Y.qd;
@@ -139,7 +172,27 @@ DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // K3
         vj = ld6(qd + ds);
     }
     st6(s + Y.vj + i * 6, vj);
-    st7(s + Y.Xsm + i * 7, xf_mul(ld7(s + Y.Xsc + i * 7), ld7(P.X_cm + i * 7)));
+    st7(s + Y.Xsm + i * 7, xf_mul(Xsc, ld7(P.X_cm + i * 7)));
+}
+
+DFX_HD void kin_velocity_path_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // K4
+    // v = v[parent] + v_j ; a = a[parent] + v x v_j, accumulated along the path from the root (same order, same bits)
+    SV v = sv_zero(), a = sv_zero();
+    for_path_root_first(P, i, true, [&](int p) {
+        const SV vj = ld6(s + Y.vj + p * 6);
+        v = v + vj;
+        a = a + sv_cross(v, vj);
+    });
+    st6(s + Y.v + i * 6, v);
+    st6(s + Y.a + i * 6, a);
+}
+
+DFX_HD void kin_chain_fwd(const Pack& P, const Layout& Y, SP s, int i) {   // K2
+    const int par = P.parent[i];
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    // X_sc = X_sp (X_pj X_jc): same association as the reference (sim.py:1668) so that even the
+    // derivative along |q| (q is not assumed unit) agrees
+    st7(s + Y.Xsc + i * 7, xf_mul(Xp, ld7(s + Y.Xl + i * 7)));
 }
 
 DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // K4
@@ -156,17 +209,26 @@ template <class Grp>
 DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
     g.sync();
-    for (int lev = 0; lev < P.nlev; ++lev) {
-        const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) kin_chain_fwd(P, Y, s, P.level_links[k]);
+    if constexpr (Grp::kPathPasses) {
+        // every barrier is CTA-wide here: each link walks its own path from the root, three barriers in all
+        DFX_FOR(i, P.L) kin_motion_fwd<true>(P, Y, s, i);
         g.sync();
-    }
-    DFX_FOR(i, P.L) kin_motion_fwd(P, Y, s, i);
-    g.sync();
-    for (int lev = 0; lev < P.nlev; ++lev) {
-        const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) kin_velocity_fwd(P, Y, s, P.level_links[k]);
+        DFX_FOR(i, P.L) kin_velocity_path_fwd(P, Y, s, i);
         g.sync();
+    } else {
+        // cheap group barriers, possibly deep trees: level-by-level recursions (root -> leaf)
+        for (int lev = 0; lev < P.nlev; ++lev) {
+            const int b = P.level_start[lev], e = P.level_start[lev + 1];
+            for (int k = b + g.lane; k < e; k += Grp::G) kin_chain_fwd(P, Y, s, P.level_links[k]);
+            g.sync();
+        }
+        DFX_FOR(i, P.L) kin_motion_fwd<false>(P, Y, s, i);
+        g.sync();
+        for (int lev = 0; lev < P.nlev; ++lev) {
+            const int b = P.level_start[lev], e = P.level_start[lev + 1];
+            for (int k = b + g.lane; k < e; k += Grp::G) kin_velocity_fwd(P, Y, s, P.level_links[k]);
+            g.sync();
+        }
     }
 }
 
@@ -509,16 +571,20 @@ DFX_HD void wrench_collect(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const SPi hi = lo + P.L * 6;
     const SPu poison = sp_uint(s + Y.cmask);
     const unsigned bad = *poison;
-    DFX_FOR(it, P.L * 6) {
-        const int l = lo[it], h = hi[it];
-        if ((l | h) != 0) { s[Y.f + it] += fx_value(l, h, kFxForwardInv); lo[it] = 0; hi[it] = 0; }
+    DFX_FOR(i, P.L) {          // one item per link: its six components are independent loads (ILP), one pass
+        int l[6], h[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { l[c] = lo[i * 6 + c]; h[c] = hi[i * 6 + c]; }
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            if ((l[c] | h[c]) != 0) { s[Y.f + i * 6 + c] += fx_value(l[c], h[c], kFxForwardInv); lo[i * 6 + c] = 0; hi[i * 6 + c] = 0; }
+        if ((bad >> (i & 31)) & 1u) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s[Y.f + i * 6 + c] = nanf("");
+        }
     }
-    if (bad) {
-        DFX_FOR(it, P.L * 6) { if ((bad >> ((it / 6) & 31)) & 1u) s[Y.f + it] = nanf(""); }
-        g.sync();
-        if (g.lane == 0) *poison = 0u;
-    }
-    g.sync();
+    g.sync();                  // (barriers stay unconditional: `bad` differs between the environments of a tile)
+    if (g.lane == 0) *poison = 0u;
 }
 
 // adjoint for one contact: cotangent r = af[body]; accumulates into aXsc[body], av[body] with shared-memory
@@ -623,16 +689,11 @@ DFX_HD void adj_collect(const Pack& P, const Layout& Y, SP s, float scale, const
         const int l = sp_int(dst)[it];
         const int h = hi[it];
         if ((l | h) != 0) { dst[it] = fx_value(l, h, inv); hi[it] = 0; }
-    }
-    if (bad) {
-        DFX_FOR(it, P.L * 13) {
-            const int body = (it < P.L * 7) ? it / 7 : (it - P.L * 7) / 6;
-            if ((bad >> (body & 31)) & 1u) dst[it] = nanf("");
-        }
-        g.sync();
-        if (g.lane == 0) *poison = 0u;
+        const int body = (it < P.L * 7) ? it / 7 : (it - P.L * 7) / 6;
+        if ((bad >> (body & 31)) & 1u) dst[it] = nanf("");
     }
     g.sync();
+    if (g.lane == 0) *poison = 0u;
 }
 
 template <class Grp>
@@ -715,16 +776,26 @@ DFX_HD void muscle_adj(const Pack& P, const Layout& Y, SP s, float scale, const 
 // =====================================================================================
 // joint torques: leaf -> root wrench accumulation and projection on the motion subspace
 // =====================================================================================
-// T1 (leaf->root, thin): f_tot[i] = f[i] + sum f_tot[children]   T2 (parallel): project on S, add PD / limits
+// per link, in one pass: f_tot[i] = sum of f over the subtree of i (the pack lists it, i first), then the projection
+// on the joint axes plus PD targets and limits.  (A leaf->root recursion f_tot[i] = f[i] + sum f_tot[children]
+// would need a barrier per tree level; the flat sum associates differently, within rounding.)
+DFX_HD SV tau_subtree_force(const Pack& P, const Layout& Y, SP s, int i) {
+    SV ft = sv_zero();
+    for (int k = P.sub_start[i + 1] - 1; k >= P.sub_start[i]; --k) ft += ld6(s + Y.f + P.sub_links[k] * 6);
+    st6(s + Y.ft + i * 6, ft);
+    return ft;
+}
+
 DFX_HD void tau_accum_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     SV ft = sv_zero();
     for (int k = P.child_start[i + 1] - 1; k >= P.child_start[i]; --k) ft += ld6(s + Y.ft + P.child_idx[k] * 6);
     st6(s + Y.ft + i * 6, ld6(s + Y.f + i * 6) + ft);
 }
 
+template <bool SUBTREE>
 DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     const int type = P.type[i], qs = P.q_start[i], ds = P.qd_start[i];
-    const SV f = ld6(s + Y.ft + i * 6);
+    const SV f = SUBTREE ? tau_subtree_force(P, Y, s, i) : ld6(s + Y.ft + i * 6);
     const SP q = s + Y.q;
     const SP qd = s + Y.qd;
     const SP S = s + Y.S;
@@ -749,13 +820,18 @@ DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, SP s, int i) {
 
 template <class Grp>
 DFX_HD void tau_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
-    for (int lev = P.nlev - 1; lev >= 0; --lev) {
-        const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_fwd(P, Y, s, P.level_links[k]);
+    if constexpr (Grp::kPathPasses) {
+        DFX_FOR(i, P.L) tau_project_fwd<true>(P, Y, s, i);
+        g.sync();
+    } else {
+        for (int lev = P.nlev - 1; lev >= 0; --lev) {
+            const int b = P.level_start[lev], e = P.level_start[lev + 1];
+            for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_fwd(P, Y, s, P.level_links[k]);
+            g.sync();
+        }
+        DFX_FOR(i, P.L) tau_project_fwd<false>(P, Y, s, i);
         g.sync();
     }
-    DFX_FOR(i, P.L) tau_project_fwd(P, Y, s, i);
-    g.sync();
 }
 
 // adjoint: `atau` (D) in; af[] becomes the adjoint of body_f_s; aS, aq, aqd, aact accumulate.
@@ -894,11 +970,13 @@ DFX_HD void chol_inverse(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const SP Lm = s + Y.Lm;
     for (int j = 0; j < D; ++j) {
         float sj = A[j * D + j] + P.armature[j];
-        for (int k = 0; k < j; ++k) { const float r = Lm[j * D + k]; sj -= r * r; }
+#pragma unroll 4
+        for (int k = 0; k < j; ++k) { const float r = Lm[j * D + k]; sj -= r * r; }   // (unrolled: the loads pipeline)
         const float ljj = sqrtf(sj);
         const float inv = 1.0f / ljj;
         for (int i = j + 1 + g.lane; i < D; i += Grp::G) {
             float si = A[i * D + j];
+#pragma unroll 4
             for (int k = 0; k < j; ++k) si -= Lm[i * D + k] * Lm[j * D + k];
             Lm[i * D + j] = si * inv;
         }
@@ -909,12 +987,14 @@ DFX_HD void chol_inverse(const Pack& P, const Layout& Y, SP s, const Grp& g) {
         // L y = e_c  (y_i = 0 for i < c)
         for (int i = 0; i < D; ++i) {
             float acc = (i == c) ? 1.0f : 0.0f;
+#pragma unroll 4
             for (int k = c; k < i; ++k) acc -= Lm[i * D + k] * A[k * D + c];
             A[i * D + c] = (i < c) ? 0.0f : acc / Lm[i * D + i];
         }
         // L^T x = y
         for (int i = D - 1; i >= 0; --i) {
             float acc = A[i * D + c];
+#pragma unroll 4
             for (int k = i + 1; k < D; ++k) acc -= Lm[k * D + i] * A[k * D + c];
             A[i * D + c] = acc / Lm[i * D + i];
         }

@@ -21,6 +21,7 @@ namespace dfx {
 template <int NW>
 struct GroupTile {
     static constexpr int G = NW;
+    static constexpr bool kPathPasses = true;    // barriers are CTA-wide: path / subtree passes instead of per-level recursions
     int lane;            // warp index: the item slot of DFX_FOR
     int lane32;          // environment inside the tile
     int tile, ntiles;
@@ -151,15 +152,25 @@ static cudaError_t tile_launch_impl(KernelArgs& ka, cudaStream_t stream) {
 
 using namespace dfx;
 
-// the articulations with a tile kernel: (warps, L, D, Q, C, M)
+// the articulations with a tile kernel: (warps forward, warps backward, L, D, Q, C, M)
+#ifndef DFX_TILE_NWF
+#define DFX_TILE_NWF 16
+#endif
+#ifndef DFX_TILE_NWB
+#define DFX_TILE_NWB 16
+#endif
+#ifdef DFX_TILE_ONLY_ANT      // (tuning builds)
+#define DFX_TILE_MODELS(X) X(DFX_TILE_NWF, DFX_TILE_NWB, 9, 14, 15, 25, 0)
+#else
 #define DFX_TILE_MODELS(X)       \
-    X(16, 9, 14, 15, 25, 0) /* Ant */         \
-    X(8, 3, 2, 2, 0, 0)     /* CartPole */    \
-    X(16, 6, 6, 6, 8, 0)    /* Hopper */      \
-    X(16, 9, 9, 9, 16, 0)   /* HalfCheetah */
+    X(DFX_TILE_NWF, DFX_TILE_NWB, 9, 14, 15, 25, 0) /* Ant */         \
+    X(8, 8, 3, 2, 2, 0, 0)     /* CartPole */    \
+    X(16, 16, 6, 6, 6, 8, 0)    /* Hopper */      \
+    X(16, 16, 9, 9, 9, 16, 0)   /* HalfCheetah */
+#endif
 
 bool dfx_tile_supported(int L, int D, int Q, int C, int M) {
-#define X(nw, l, d, q, c, m) if (L == l && D == d && Q == q && C == c && M == m) return true;
+#define X(nwf, nwb, l, d, q, c, m) if (L == l && D == d && Q == q && C == c && M == m) return true;
     DFX_TILE_MODELS(X)
 #undef X
     return false;
@@ -173,10 +184,10 @@ size_t dfx_tile_smem(const KernelArgs& ka, bool backward) {
 
 cudaError_t dfx_tile_launch(KernelArgs& ka, bool backward, cudaStream_t stream) {
     const Pack& h = ka.header;
-#define X(nw, l, d, q, c, m)                                                                  \
+#define X(nwf, nwb, l, d, q, c, m)                                                            \
     if (h.L == l && h.D == d && h.Q == q && h.C == c && h.M == m)                               \
-        return backward ? tile_launch_impl<nw, true, l, d, q, c, m>(ka, stream)               \
-                        : tile_launch_impl<nw, false, l, d, q, c, m>(ka, stream);
+        return backward ? tile_launch_impl<nwb, true, l, d, q, c, m>(ka, stream)              \
+                        : tile_launch_impl<nwf, false, l, d, q, c, m>(ka, stream);
     DFX_TILE_MODELS(X)
 #undef X
     return cudaErrorInvalidConfiguration;

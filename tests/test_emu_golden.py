@@ -15,11 +15,14 @@ def rel(a, b):
     return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
 
 
+@pytest.mark.parametrize("variant", ["level", "tile"])
 @pytest.mark.parametrize("name", ENVS)
-def test_forward_and_adjoint_match_reference(name):
+def test_forward_and_adjoint_match_reference(name, variant):
+    """variant "level": the lane-group kernels' formulation (contiguous scratch, level-by-level tree recursions);
+    "tile": the tile kernels' (strided scratch, path / subtree passes)."""
     d, model = load_golden(name)
     N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
-    sim = EmuSim(model, N)
+    sim = EmuSim(model, N) if variant == "level" else EmuSim(model, N, es=3, path_passes=True)
     for k in range(int(d["meta/num_cases"])):
         p = "case%d/" % k
         musc = d[p + "musc"] if (p + "musc") in d.files else None
