@@ -566,7 +566,7 @@ DFX_HD void contact_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
 template <class Grp>
 DFX_HD void wrench_collect(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     if (!P.ground && P.M == 0) return;
-    g.sync();
+    if (!Grp::kPathPasses || P.M > 0) g.sync();   // (tile kernels: the contact tasks ended with a CTA-wide barrier)
     const SPi lo = sp_int(s + Y.fx);
     const SPi hi = lo + P.L * 6;
     const SPu poison = sp_uint(s + Y.cmask);

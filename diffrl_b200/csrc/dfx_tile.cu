@@ -45,15 +45,15 @@ struct GroupTile {
     }
     template <class F>
     __device__ __forceinline__ void cta_tasks(SP s, int n, bool lead, F f) const {
-        if (lead) __syncthreads();
+        (void)lead;      // every phase ends with sync(), which is already CTA-wide here
         for (int k = lane; k < n; k += NW) f(s, k);
         __syncthreads();
     }
     // (k, environment) pairs with pred() true, compacted over the tile, then f() over the list with full warps
     template <class Pr, class F>
     __device__ __forceinline__ void cta_compact(SP s, int n, Pr pred, F f) const {
-        if (threadIdx.x == 0) *task_count = 0;
-        __syncthreads();
+        // (*task_count is 0 on entry: cleared at kernel start and after every use; the preceding phase's closing
+        //  barrier has published what pred() reads)
         for (int k0 = 0; k0 < n; k0 += NW) {
             const int k = k0 + lane;
             const bool hit = (k < n) && pred(s, k);
@@ -72,6 +72,7 @@ struct GroupTile {
             f(SP{tile_base + (t & 31)}, t >> 5);
         }
         __syncthreads();
+        if (threadIdx.x == 0) *task_count = 0;
     }
     // tape blocks [b][tile][n][32]: the scratch tile of the block is the same bytes, one flat copy by the whole CTA
     __device__ __forceinline__ void block_in(SP dst, const float* base, long long b, int N, int env, int n, bool rows) const {
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(NW * 32) dfx_tile_kernel(const __grid_constant
     int* ipack = reinterpret_cast<int*>(smem + ((ka.blob.n_floats + 3) & ~3));
     for (int i = threadIdx.x; i < ka.blob.n_floats; i += NW * 32) fpack[i] = ka.blob.floats[i];
     for (int i = threadIdx.x; i < ka.blob.n_ints; i += NW * 32) ipack[i] = ka.blob.ints[i];
+    if (threadIdx.x == 0) *reinterpret_cast<int*>(smem + ka.pack_smem_floats) = 0;   // task counter of cta_compact
     __syncthreads();
     Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
     P.L = SL; P.D = SD; P.Q = SQ; P.C = SC; P.M = SM;
