@@ -230,14 +230,24 @@ def run_ours(args):
             acts[t] = env.state.joint_act.detach().clone()
     gq_seed, gqd_seed = torch.randn(N * Q, device=dev), torch.randn(N * D, device=dev)
 
-    def kernel_rollout():
+    phase_events = []      # (start, forward done, backward done) of every timed rollout, on the launching stream
+
+    def kernel_rollout(record=False):
+        ev3 = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
+        if record:
+            ev3[0].record()
         q, qd, tapes = q0, qd0, []
         for t in range(T):
             q, qd, tape, _ = eng.forward(q, qd, acts[t], muscs[t], S, mm, dt)
             tapes.append(tape)
+        if record:
+            ev3[1].record()
         gq, gqd = gq_seed, gqd_seed
         for t in reversed(range(T)):
             gq, gqd, gact, gm = eng.backward(acts[t], muscs[t], tapes[t], gq, gqd, S, mm, dt)
+        if record:
+            ev3[2].record()
+            phase_events.append(ev3)
         return gq
 
     def barrier():
@@ -258,26 +268,16 @@ def run_ours(args):
     with ClockSampler(local) as clocks:
         ev[0].record()
         for _ in range(args.steps):
-            kernel_rollout()
+            kernel_rollout(record=True)
         ev[1].record()
         barrier()
     kernel_ms = ev[0].elapsed_time(ev[1])
     launches = lib.dfx_launch_count() - launches0
 
-    # per-kernel launch time of the dominant (adjoint) kernel, for the roofline
-    q, qd, tape, _ = eng.forward(q0, qd0, acts[0], muscs[0], S, mm, dt)
-    reps = 20
-    e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    torch.cuda.synchronize()
-    e2[0].record()
-    for _ in range(reps):
-        eng.forward(q0, qd0, acts[0], muscs[0], S, mm, dt)
-    e2[1].record()
-    for _ in range(reps):
-        eng.backward(acts[0], muscs[0], tape, gq_seed, gqd_seed, S, mm, dt)
-    e2[2].record()
-    torch.cuda.synchronize()
-    fwd_ms, bwd_ms = e2[0].elapsed_time(e2[1]) / reps, e2[1].elapsed_time(e2[2]) / reps
+    # average launch duration of the forward and of the adjoint kernel INSIDE the timed rollouts (every launch reads /
+    # writes its own tape block, gigabytes per rollout, far beyond L2): the roofline denominators
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in phase_events) / (len(phase_events) * T)
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in phase_events) / (len(phase_events) * T)
 
     # ------------------------------------------------------------ end to end through env.step + autograd
     host_actions = torch.empty((T, N, env.num_actions), dtype=torch.float32).pin_memory()
@@ -386,7 +386,7 @@ def run_ours(args):
                                "mass_matrix_freq=%d" % (env_name, N, T, S, mm),
                    "parallelism": "env-sharded x%d, no data-path collective%s" % (world, "; 64 KB policy-gradient all-reduce per rollout (e2e)" if world > 1 else ""),
                    "cache": "per-rollout tape %.0f MB > 126 MB L2 (inputs larger than L2)" % (T * eng.tape_floats(S, mm) * 4 / 1e6),
-                   "group_lanes": "auto"},
+                   "kernel_family": "tile (32 envs per CTA, lane = env)" if lib.dfx_pack_query(eng.pack, 9) else "lane group"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(host_actions.numel() * 4),
                 "d2h_bytes_per_step": int(host_grad.numel() * 4 + 4), "api": e2e_api,
                 "ms_per_step": e2e_ms / e2e_steps,
@@ -395,13 +395,14 @@ def run_ours(args):
         "kernel_ms": {"forward_env_step": fwd_ms, "backward_env_step": bwd_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                     "kernel": "dfx_step_kernel<G,BWD=1> (adjoint of one env-step)",
+                     "kernel": ("dfx_tile_kernel<NW,BWD=1> (adjoint of one env-step, 32-environment tiles)"
+                                if lib.dfx_pack_query(eng.pack, 9) else "dfx_step_kernel<G,BWD=1> (adjoint of one env-step)"),
                      "algorithmic_bytes_per_launch": N * b_bwd,
                      "survey_8d_state_only_bytes_per_launch": N * s_bwd,
                      "forward_kernel": {"achieved": N * b_fwd / (fwd_ms * 1e-3) / 1e9, "algorithmic_bytes_per_launch": N * b_fwd},
                      "note": "algorithmic bytes = this design's tape rows (q, qd + forward intermediates, 4*row B per env-substep) "
                              "+ H^-1 blocks + state I/O; the fused path is FP32-issue/latency bound, not HBM bound "
-                             "(profiles/r01_ant_full.md, DESIGN.md section 3)"},
+                             "(profiles/r01_ant_full.md, DESIGN.md section 3); launch durations are averages over the timed rollouts"},
         "clocks": clocks.summary(),
     }
     if cpu is not None:

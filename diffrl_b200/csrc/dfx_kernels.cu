@@ -125,6 +125,12 @@ struct GroupCuda {
             for (int i = lane; i < n; i += G_) dst[i] = src[i];
         }
     }
+    // (rows are 60-120 B here and the head is not 16-byte aligned: one part, issued with the first call)
+    __device__ __forceinline__ void row_in(float* dst, const float* base, long long b, int N, int env, int n, int head, int tail, bool first) const {
+        (void)head; (void)tail;
+        if (first) block_in(dst, base, b, N, env, n, true);
+    }
+    __device__ __forceinline__ void copy_wait_first() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };
 

@@ -58,6 +58,12 @@ struct GroupSerial {  // host / single-lane execution
         const float* t = base + (b * N + env) * n;
         for (int i = 0; i < n; ++i) dst[i] = t[i];
     }
+    // a tape row in two parts: first == true: elements [0, head) and [tail, n); first == false: [head, tail)
+    DFX_HD void row_in(SP dst, const float* base, long long b, int N, int env, int n, int head, int tail, bool first) const {
+        const float* t = base + (b * N + env) * n;
+        for (int i = 0; i < n; ++i) if (((i < head) || (i >= tail)) == first) dst[i] = t[i];
+    }
+    DFX_HD void copy_wait_first() const {}     // all asynchronous copies but the most recent one have landed
     DFX_HD void copy_wait_all() const {}
 };
 
@@ -1199,7 +1205,8 @@ DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool app
     // instruction working set per SM is one or two phases (~10 KB each) instead of the whole 140 KB body
     integrate_adj(P, Y, s, dt, g);
     solve_adj(P, Y, s, g);                  // tau slot <- atau
-    g.phase_sync();
+    g.copy_wait_all();                      // the bulk of the tape row (transforms, S, v, a, wrenches) is needed from here on
+    g.sync();
     if (apply_crba) crba_adj(P, Y, s, g);
     tau_adj(P, Y, s, s + Y.tau, g);
     g.phase_sync();

@@ -100,12 +100,15 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g
         const int seg = sub / a.mm_freq;
         const int s0 = seg * a.mm_freq;
         const bool seg_last = (sub == a.substeps - 1) || ((sub + 1) % a.mm_freq == 0);   // first visited of its segment
-        g.block_in(s + Y.q, a.tape_in, sub, a.N, env, QD, true);
+        // the row arrives in two asynchronous parts: (q, qd, q'') -- all that the first two adjoint phases read -- then
+        // the rest, which substep_adj() waits for only before the phases that need it
+        g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, true);
         if (seg_last) {
             g.block_in(s + Y.A, a.tape_in + a.hinv_base, seg, a.N, env, DD, false);
             DFX_FOR(e, DD) s[Y.Lm + e] = 0.0f;
         }
-        g.copy_wait_all();
+        g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, false);
+        g.copy_wait_first();
         g.sync();
         substep_adj(P, Y, s, a.dt_sub, sub == s0, g);
     }

@@ -89,6 +89,23 @@ struct GroupTile {
         const float4* s4 = reinterpret_cast<const float4*>(sp_raw(src) - lane32);
         for (int i = threadIdx.x; i < n * 8; i += NW * 32) d4[i] = s4[i];
     }
+    // a row tile in two commit groups: the [0, head) and [tail, n) element ranges first, the middle second
+    __device__ __forceinline__ void row_in(SP dst, const float* base, long long b, int N, int env, int n, int head, int tail, bool first) const {
+        (void)N; (void)env;
+        const float* src = base + ((b * ntiles + tile) * n) * 32;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(sp_raw(dst) - lane32);
+        if (first) {
+            for (int i = threadIdx.x * 4; i < head * 32; i += NW * 32 * 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+            for (int i = tail * 32 + threadIdx.x * 4; i < n * 32; i += NW * 32 * 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+        } else {
+            for (int i = head * 32 + threadIdx.x * 4; i < tail * 32; i += NW * 32 * 4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void copy_wait_first() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
     __device__ __forceinline__ void copy_wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };
 
