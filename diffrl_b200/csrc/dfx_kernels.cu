@@ -102,6 +102,13 @@ struct GroupCuda {
         }
         __syncthreads();
     }
+    static constexpr bool kConcurrentItems = false;
+    template <class Pr, class F, class H>
+    __device__ __forceinline__ void cta_compact_with(float* s, int n, Pr pred, F f, int m, H item) const {
+        for (int k = lane; k < m; k += G_) item(s, k);
+        __syncwarp(mask);
+        cta_compact(s, n, pred, f);
+    }
     // tape blocks [b][env][n]: rows (n % 4 == 0, 16-byte aligned) move with cp.async (LDGSTS) / float4, one commit
     // group per row; the H^-1 blocks (n = D * D, any alignment) with plain loads
     __device__ __forceinline__ void block_in(float* dst, const float* base, long long b, int N, int env, int n, bool rows) const {

@@ -45,6 +45,13 @@ struct GroupSerial {  // host / single-lane execution
     // same, restricted to the (k, env) pairs for which pred() holds (compacted first)
     template <class Pr, class F>
     DFX_HD void cta_compact(SP s, int n, Pr pred, F f) const { for (int k = 0; k < n; ++k) if (pred(s, k)) f(s, k); }
+    // cta_compact() plus m independent dense items item(s, k): the two kinds of work may run concurrently
+    template <class Pr, class F, class H>
+    DFX_HD void cta_compact_with(SP s, int n, Pr pred, F f, int m, H item) const {
+        for (int k = 0; k < m; ++k) item(s, k);
+        for (int k = 0; k < n; ++k) if (pred(s, k)) f(s, k);
+    }
+    static constexpr bool kConcurrentItems = false;   // cta_compact_with() really overlaps the two
     // tape blocks: block `b` of environment `env` holds n floats ([b][env][n] here and in the lane-group kernels,
     // [b][tile of 32 envs][n][32] in the tile kernels).  `rows`: n is a multiple of 4 and 16-byte aligned (vector
     // / asynchronous copies allowed); block_in may complete asynchronously until copy_wait_all().
@@ -425,7 +432,9 @@ DFX_HD void body_force_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
 }
 
 // adjoint: af[i] (adjoint of body_f_s[i]) plus what crba_adj left in aR[i] / au[i] -> aXsm, av, aa
-DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, SP s, int i) {
+// ATOMIC_AV: another phase (the contact adjoint) adds to av concurrently
+template <bool ATOMIC_AV, class Grp>
+DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, SP s, int i, const Grp& g) {
     const SP Xsm7 = s + Y.Xsm + i * 7;
     const BodyInertia B = body_inertia(P, Xsm7, i);
     const V3 c = ld3(Xsm7);
@@ -448,13 +457,19 @@ DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, SP s, int i) {
     outer_acc(aR, c, au);
     add3(s + Y.aXsm + i * 7, ac);
     add4(s + Y.aXsm + i * 7 + 3, q_to_m3_adj(ld4(Xsm7 + 3), aR));
-    add6(s + Y.av + i * 6, av);
+    if (ATOMIC_AV) {
+        const SP d = s + Y.av + i * 6;
+        g.atomic_add(&d[0], av.w.x); g.atomic_add(&d[1], av.w.y); g.atomic_add(&d[2], av.w.z);
+        g.atomic_add(&d[3], av.v.x); g.atomic_add(&d[4], av.v.y); g.atomic_add(&d[5], av.v.z);
+    } else {
+        add6(s + Y.av + i * 6, av);
+    }
     add6(s + Y.aa + i * 6, aa);
 }
 
 template <class Grp>
 DFX_HD void body_force_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
-    DFX_FOR(i, P.L) body_force_link_adj(P, Y, s, i);
+    DFX_FOR(i, P.L) body_force_link_adj<false>(P, Y, s, i, g);
     g.sync();
 }
 
@@ -567,6 +582,24 @@ DFX_HD void contact_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
         const float c6[6] = {w.w.x, w.w.y, w.w.z, w.v.x, w.v.y, w.v.z};
         fx_scatter(lo + P.cbody[k] * 6, lo + P.L * 6 + P.cbody[k] * 6, sp_uint(se + Y.cmask), P.cbody[k], c6, kFxForward, g);
     });
+}
+
+// rigid-body forces (dense: one item per link) and contact forces (sparse: compacted tasks) are independent: policies
+// whose barriers are CTA-wide run them as ONE phase, the link items on some warps and the contact tasks on the rest
+template <class Grp>
+DFX_HD void body_and_contact_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
+    if (!Grp::kConcurrentItems || !P.ground) {
+        body_force_fwd(P, Y, s, g);
+        contact_fwd(P, Y, s, g);
+        return;
+    }
+    g.cta_compact_with(s, P.C, [&](SP se, int k) { return contact_penetrates(P, Y, se, k); },
+                       [&](SP se, int k) {
+        const SV w = contact_point_fwd(P, Y, se, k);
+        const SPi lo = sp_int(se + Y.fx);
+        const float c6[6] = {w.w.x, w.w.y, w.w.z, w.v.x, w.v.y, w.v.z};
+        fx_scatter(lo + P.cbody[k] * 6, lo + P.L * 6 + P.cbody[k] * 6, sp_uint(se + Y.cmask), P.cbody[k], c6, kFxForward, g);
+    }, P.L, [&](SP se, int i) { body_force_link_fwd(P, Y, se, i); });
 }
 
 template <class Grp>
@@ -1181,8 +1214,7 @@ DFX_HD void integrate_adj(const Pack& P, const Layout& Y, SP s, float dt, const 
 template <class Grp>
 DFX_HD void substep_eval(const Pack& P, const Layout& Y, SP s, bool update_mass, const Grp& g) {
     kin_fwd(P, Y, s, g);
-    body_force_fwd(P, Y, s, g);
-    contact_fwd(P, Y, s, g);
+    body_and_contact_fwd(P, Y, s, g);
     muscle_fwd(P, Y, s, g);
     wrench_collect(P, Y, s, g);
     tau_fwd(P, Y, s, g);
@@ -1216,11 +1248,17 @@ DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool app
         muscle_adj(P, Y, s, scale, g);
         contact_adj(P, Y, s, g);
         adj_collect(P, Y, s, scale, g);
-    } else if (P.ground) {
-        contact_adj(P, Y, s, g);
+        body_force_adj(P, Y, s, g);
+    } else if (P.ground && Grp::kConcurrentItems) {
+        // contact-only model, CTA-wide barriers: the contact cotangents (compacted tasks, float atomics into aXsc / av)
+        // and the rigid-body force adjoint (one item per link, its av contribution by atomics too) as one phase
+        g.cta_compact_with(s, P.C, [&](SP se, int k) { return contact_penetrates(P, Y, se, k); },
+                           [&](SP se, int k) { contact_point_adj(P, Y, se, k, 1.0f, g); },
+                           P.L, [&](SP se, int i) { body_force_link_adj<true>(P, Y, se, i, g); });
+    } else {
+        if (P.ground) contact_adj(P, Y, s, g);
+        body_force_adj(P, Y, s, g);
     }
-    g.phase_sync();
-    body_force_adj(P, Y, s, g);
     g.phase_sync();
     kin_adj(P, Y, s, g);
     g.phase_sync();

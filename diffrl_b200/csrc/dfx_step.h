@@ -60,9 +60,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
         const bool upd = (sub % a.mm_freq) == 0;
         kin_fwd(P, Y, s, g);
         g.phase_sync();
-        body_force_fwd(P, Y, s, g);
-        g.phase_sync();
-        contact_fwd(P, Y, s, g);
+        body_and_contact_fwd(P, Y, s, g);
         muscle_fwd(P, Y, s, g);
         wrench_collect(P, Y, s, g);
         g.phase_sync();

@@ -74,6 +74,40 @@ struct GroupTile {
         __syncthreads();
         if (threadIdx.x == 0) *task_count = 0;
     }
+    // cta_compact() and m dense items item(s, k) as ONE phase: after the compaction every warp first does its items
+    // (k = warp, warp + NW, ...), then all warps drain the task list 32 tasks at a time through a shared cursor, so the
+    // warps without an item start on the tasks at once and nobody idles while work is left
+    static constexpr bool kConcurrentItems = true;
+    template <class Pr, class F, class H>
+    __device__ __forceinline__ void cta_compact_with(SP s, int n, Pr pred, F f, int m, H item) const {
+        int* cursor = task_count + 1;                  // 0 on entry, like *task_count
+        for (int k0 = 0; k0 < n; k0 += NW) {
+            const int k = k0 + lane;
+            const bool hit = (k < n) && pred(s, k);
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (b) {
+                int base = 0;
+                if (lane32 == 0) base = atomicAdd(task_count, __popc(b));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) task_list[base + __popc(b & ((1u << lane32) - 1u))] = (k << 5) | lane32;
+            }
+        }
+        __syncthreads();
+        const int hits = *task_count;
+        for (int k = lane; k < m; k += NW) item(s, k);
+        for (;;) {
+            int base = 0;
+            if (lane32 == 0) base = atomicAdd(cursor, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= hits) break;
+            if (base + lane32 < hits) {
+                const int t = task_list[base + lane32];
+                f(SP{tile_base + (t & 31)}, t >> 5);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { *task_count = 0; *cursor = 0; }
+    }
     // tape blocks [b][tile][n][32]: the scratch tile of the block is the same bytes, one flat copy by the whole CTA
     __device__ __forceinline__ void block_in(SP dst, const float* base, long long b, int N, int env, int n, bool rows) const {
         (void)N; (void)env; (void)rows;
@@ -116,7 +150,7 @@ __global__ void __launch_bounds__(NW * 32) dfx_tile_kernel(const __grid_constant
     int* ipack = reinterpret_cast<int*>(smem + ((ka.blob.n_floats + 3) & ~3));
     for (int i = threadIdx.x; i < ka.blob.n_floats; i += NW * 32) fpack[i] = ka.blob.floats[i];
     for (int i = threadIdx.x; i < ka.blob.n_ints; i += NW * 32) ipack[i] = ka.blob.ints[i];
-    if (threadIdx.x == 0) *reinterpret_cast<int*>(smem + ka.pack_smem_floats) = 0;   // task counter of cta_compact
+    if (threadIdx.x < 4) reinterpret_cast<int*>(smem + ka.pack_smem_floats)[threadIdx.x] = 0;   // task counter / cursor of cta_compact
     __syncthreads();
     Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
     P.L = SL; P.D = SD; P.Q = SQ; P.C = SC; P.M = SM;
