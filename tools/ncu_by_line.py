@@ -79,12 +79,19 @@ def func_of(file, line):
     return best
 PHASES = ["kin_fwd", "body_force_fwd", "contact_fwd", "muscle_fwd", "wrench_collect", "tau_fwd", "crba_fwd", "chol_inverse",
           "solve_fwd", "integrate_fwd", "integrate_adj", "solve_adj", "crba_adj", "tau_adj", "muscle_adj", "contact_adj",
-          "adj_scatter_scale", "adj_collect", "body_force_adj", "kin_adj", "zero_range", "dump_derived"]
+          "adj_scatter_scale", "adj_collect", "body_force_adj", "kin_adj", "zero_range", "dump_derived",
+          # the items / tasks of the combined rigid-body + contact phases (cta_compact_with)
+          "contact_point_fwd", "contact_point_adj", "body_force_link_fwd", "body_force_link_adj", "contact_penetrates",
+          "fx_scatter", "cta_compact_with", "cta_compact", "block_in", "block_out", "row_in"]
 def phase_of(chain):
     names = [func_of(*c) for c in chain]
-    for nm in reversed(names):            # outermost first
-        if nm in PHASES:
-            return nm
+    hit = None
+    for nm in names:                      # innermost first; keep the OUTERMOST of a run of nested phase names,
+        if nm in PHASES:                  # but let the combined-phase items (listed last in PHASES) win over their host
+            if hit is None or PHASES.index(nm) < PHASES.index("contact_point_fwd"):
+                hit = nm
+    if hit is not None:
+        return hit
     for nm in reversed(names):
         if nm.startswith("env_step") or nm.startswith("dfx_step_kernel") or nm in ("copy_row_async", "copy_row_out", "copy_wait_all"):
             return nm
