@@ -249,7 +249,7 @@ DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
 // downstream of the kinematics.  Passes (leaves -> root recursions are thin):
 //   A1 (parallel)   aXsc += adj(X_sm = X_sc X_cm) ; recompute X_l, v_j
 //   A2 (leaf->root) av, aa totals (children gathered), adjoint of a = a_p + v x v_j  -> avj (in the vj slot)
-//   A3 (parallel)   adjoint of v_j = S qd and of S(X_sj): aS, aqd, aX_sj (kept in the pX slot)
+//   A3 (parallel)   adjoint of v_j = S qd and of S(X_sj): aS, aqd, aX_sj and its push to the parent (pX slot)
 //   A4 (leaf->root) aXsc totals (children's pushes gathered); push of this link to its parent -> pX
 //   A5 (parallel)   adjoint of X_l = X_pj X_jc(q) -> aq
 DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, SP s, int i) {    // A1
@@ -312,7 +312,11 @@ DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // 
     } else if (type == JOINT_FREE) {
         add6(aqd + ds, avj);
     }
-    st7(s + Y.pX + i * 7, aXsj);
+    // X_sj = X_p X_pj: this link's push to its parent through the joint frame does not depend on the recursion
+    // below, so it is formed here (parallel over the links) and A4 only adds the X_sc = X_p X_l part per level
+    Xf aXp = xf_zero();
+    xf_mul_adj_a(Xp, ld7(P.X_pj + i * 7), aXsj, aXp);
+    st7(s + Y.pX + i * 7, aXp);
 }
 
 DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, SP s, int i) {     // A4
@@ -323,7 +327,7 @@ DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, SP s, int i) {     // 
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     Xf aXp = xf_zero();
     xf_mul_adj_a(Xp, ld7(s + Y.Xl + i * 7), aXsc, aXp);                   // X_sc = X_p X_l
-    xf_mul_adj_a(Xp, ld7(P.X_pj + i * 7), ld7(s + Y.pX + i * 7), aXp);    // X_sj = X_p X_pj
+    aXp += ld7(s + Y.pX + i * 7);                                         // + the X_sj = X_p X_pj part from A3
     st7(s + Y.pX + i * 7, aXp);
 }
 
