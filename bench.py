@@ -325,7 +325,7 @@ def run_ours(args):
     # the same rollout through the package's graphed-rollout API (one CUDA graph per rollout: H2D actions,
     # horizon x env.step, loss.backward, D2H loss + action gradients)
     e2e_ms, e2e_api = eager_ms, "envs.%s.step -> dflex.sim.SemiImplicitIntegrator.forward -> autograd (eager)" % env_name
-    if args.e2e != "eager" and hasattr(env, "_reset_masked"):
+    if args.e2e != "eager" and hasattr(env, "_start_state"):
         from diffrl_b200.rollout import GraphedRollout
         env.clear_grad(); env.reset(); env.initialize_trajectory()
         roll = GraphedRollout(env, T)

@@ -139,13 +139,27 @@ class DFlexEnv:
         if not self.no_grad:
             self.obs_buf_before_reset = self.obs_buf.clone()
             self.extras = {"obs_before_reset": self.obs_buf_before_reset, "episode_end": self.termination_buf}
-        if self.sync_free_reset and hasattr(self, "_reset_masked"):
+        if self.sync_free_reset and hasattr(self, "_start_state"):
             self._reset_masked(self.reset_buf)
         else:
             env_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
             if len(env_ids) > 0:
                 self.reset(env_ids)
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _reset_masked(self, reset_buf):
+        """Re-initialise terminated environments without reading reset_buf on the host: the start state is formed
+        for every row (``_start_state()``: the same distributions as ``_reset_state``) and selected by mask."""
+        n = self.num_envs
+        flag = reset_buf.bool()
+        mask = flag.unsqueeze(-1)
+        start_q, start_qd = self._start_state()
+        self.state.joint_q = torch.where(mask, start_q, self.state.joint_q.view(n, -1)).view(-1)
+        self.state.joint_qd = torch.where(mask, start_qd, self.state.joint_qd.view(n, -1)).view(-1)
+        if self.clone_actions:
+            self.actions = torch.where(mask, torch.zeros_like(self.actions), self.actions)
+        self.progress_buf = torch.where(flag, torch.zeros_like(self.progress_buf), self.progress_buf)
+        self.calculateObservations()
 
     def _observe_and_reward(self):
         self.calculateObservations()

@@ -103,19 +103,6 @@ class _FreeRootWalker(DFlexEnv):
             start_qd = 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
         return start_q, start_qd
 
-    def _reset_masked(self, reset_buf):
-        """Re-initialise terminated environments without reading reset_buf on the host."""
-        n = self.num_envs
-        mask = reset_buf.bool().unsqueeze(-1)
-        q = self.state.joint_q.view(n, -1)
-        qd = self.state.joint_qd.view(n, -1)
-        start_q, start_qd = self._start_state()
-        self.state.joint_q = torch.where(mask, start_q, q).view(-1)
-        self.state.joint_qd = torch.where(mask, start_qd, qd).view(-1)
-        self.actions = torch.where(mask, self._zero_act, self.actions)
-        self.progress_buf = torch.where(reset_buf.bool(), torch.zeros_like(self.progress_buf), self.progress_buf)
-        self.calculateObservations()
-
     # ---- fused step: policy output -> actuation (1 launch), simulation step (1 launch), transition (1 launch) ----
     fused_transition = True
 
@@ -374,6 +361,15 @@ class CartPoleSwingUpEnv(DFlexEnv):
             q[env_ids, :] = q[env_ids, :] + np.pi * (torch.rand(size=(k, self.num_joint_q), device=dev) - 0.5)
             qd[env_ids, :] = qd[env_ids, :] + 0.5 * (torch.rand(size=(k, self.num_joint_qd), device=dev) - 0.5)
 
+    def _start_state(self):
+        n, dev = self.num_envs, self.device
+        start_q = self.start_joint_q.view(n, self.num_joint_q)
+        start_qd = self.start_joint_qd.view(n, self.num_joint_qd)
+        if self.stochastic_init:
+            start_q = start_q + np.pi * (torch.rand(size=(n, self.num_joint_q), device=dev) - 0.5)
+            start_qd = start_qd + 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
+        return start_q, start_qd
+
     def clear_grad(self, checkpoint=None):
         with torch.no_grad():
             q, qd, act = self.state.joint_q.clone(), self.state.joint_qd.clone(), self.state.joint_act.clone()
@@ -429,6 +425,22 @@ class _PlanarHopper(DFlexEnv):
             q[env_ids, 2] = (torch.rand(k, device=dev) - 0.5) * a_rot
             q[env_ids, 3:] = q[env_ids, 3:] + a_joint * (torch.rand(size=(k, self.num_joint_q - 3), device=dev) - 0.5) * 2.0
             qd[env_ids, :] = a_vel * (torch.rand(size=(k, self.num_joint_qd), device=dev) - 0.5)
+
+    def _start_state(self):
+        n, dev = self.num_envs, self.device
+        if getattr(self, "_start_q_full", None) is None:
+            self._start_q_full = torch.cat([self.start_pos, self.start_rotation.expand(n, 1),
+                                            self.start_joint_q.expand(n, -1)], dim=-1).contiguous()
+            self._zero_qd = torch.zeros((n, self.num_joint_qd), device=dev)
+        start_q, start_qd = self._start_q_full, self._zero_qd
+        if self.stochastic_init:
+            a_pos, a_rot, a_joint, a_vel = self.init_noise
+            start_q = start_q.clone()
+            start_q[:, 0:2] = start_q[:, 0:2] + a_pos * (torch.rand(size=(n, 2), device=dev) - 0.5) * 2.0
+            start_q[:, 2] = (torch.rand(n, device=dev) - 0.5) * a_rot
+            start_q[:, 3:] = start_q[:, 3:] + a_joint * (torch.rand(size=(n, self.num_joint_q - 3), device=dev) - 0.5) * 2.0
+            start_qd = a_vel * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
+        return start_q, start_qd
 
     def calculateObservations(self):
         self.obs_buf = torch.cat([self.state.joint_q.view(self.num_envs, -1)[:, 1:], self.state.joint_qd.view(self.num_envs, -1)], dim=-1)

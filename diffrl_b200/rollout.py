@@ -9,6 +9,9 @@ the actions and the device->host copies of the loss and the action gradients, an
     roll = GraphedRollout(env, horizon=32)
     loss, grad_actions = roll(host_actions)        # host_actions: pinned [horizon, num_envs, num_actions]
 
+Capture is exercised for the walker envs (fused step) and the planar Hopper / HalfCheetah (op-by-op step with masked
+resets); CartPoleSwingUpEnv's capture is known to be invalidated (open issue) -- use its eager ``step`` loop.
+
 Each call starts from the env's current state (``env.state.joint_q/qd``, ``progress_buf``, last actions)
 and leaves the env at the end of the rollout with the graph cut (as ``env.clear_grad()`` would), so
 consecutive calls chain like SHAC's short-horizon windows (reference algorithms/shac.py:169-292).
@@ -22,7 +25,7 @@ class GraphedRollout:
             raise RuntimeError("GraphedRollout needs a CUDA environment")
         if env.no_grad:
             raise RuntimeError("GraphedRollout differentiates the rollout: construct the env with no_grad=False")
-        if not getattr(env, "sync_free_reset", False) or not hasattr(env, "_reset_masked"):
+        if not getattr(env, "sync_free_reset", False) or not hasattr(env, "_start_state"):
             raise RuntimeError("%s resets through reset_buf.nonzero(), which cannot be captured" % type(env).__name__)
         self.env, self.T = env, int(horizon)
         dev = torch.device(env.device)

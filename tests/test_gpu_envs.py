@@ -144,27 +144,32 @@ def test_fused_transition_equals_unfused_step(name):
         assert (grad - ref_grad).abs().max() <= 1e-4 * ref_grad.abs().max() + 1e-6
 
 
-def test_masked_reset_equals_indexed_reset():
+@pytest.mark.parametrize("name", ["AntEnv", "HopperEnv", "CheetahEnv", "CartPoleSwingUpEnv"])
+def test_masked_reset_equals_indexed_reset(name):
+    """Terminated environments re-initialised by mask (no host sync, graph-capturable) == the reference's
+    reset_buf.nonzero() + indexed writes."""
     import torch
     import diffrl_b200.envs as envs
     n = 32
     res = []
     for masked in (True, False):
-        env = envs.AntEnv(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=16, episode_length=3)
+        env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=3)
         env.sync_free_reset = masked
+        env.fused_transition = False
         env.clear_grad(); env.reset(); env.initialize_trajectory()
         g = torch.Generator(device="cuda:0").manual_seed(5)
         traj = []
         for t in range(5):     # episode_length 3 forces resets at t = 2
-            obs, rew, done, _ = env.step(torch.rand((n, 8), generator=g, device="cuda:0") * 2 - 1)
+            obs, rew, done, _ = env.step(torch.rand((n, env.num_actions), generator=g, device="cuda:0") * 2 - 1)
             traj.append((obs.detach().clone(), done.clone(), env.progress_buf.clone(), env.state.joint_q.detach().clone()))
         res.append(traj)
+    assert any(bool(a[1].any()) for a in res[0])
     for a, b in zip(*res):
         assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
         assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[3], b[3], atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv"])
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "HopperEnv"])
 def test_graphed_rollout_equals_eager(name):
     """One CUDA graph for horizon env-steps + backward reproduces the eager rollout (loss, action gradients,
     final state) and chains across calls."""
@@ -173,7 +178,8 @@ def test_graphed_rollout_equals_eager(name):
     from diffrl_b200.rollout import GraphedRollout
     n, T = 48, 6
     g = torch.Generator().manual_seed(2)
-    acts = [torch.rand((T, n, 8 if name == "AntEnv" else 21), generator=g) * 2 - 1 for _ in range(2)]
+    num_act = {"AntEnv": 8, "HumanoidEnv": 21, "HopperEnv": 3, "CartPoleSwingUpEnv": 1}[name]
+    acts = [torch.rand((T, n, num_act), generator=g) * 2 - 1 for _ in range(2)]
 
     def make():
         env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=9)
