@@ -1,7 +1,8 @@
-// dfx_kernels.cu -- sm_100a kernels and the C ABI (include/dfx.h) of the differentiable
-// articulated rigid-body step.
+// dfx_kernels.cu -- the C ABI (include/dfx.h) of the differentiable articulated rigid-body step and the
+// LANE-GROUP sm_100a kernels (the humanoids and any generic articulation; the small DiffRL articulations run
+// on the 32-environment tile kernels of dfx_tile.cu, same phase code, other mapping).
 //
-// Execution model: a cooperative group of G lanes (8, 16 or 32; a sub-warp tile) owns one
+// Execution model here: a cooperative group of G lanes (8, 16 or 32; a sub-warp tile) owns one
 // environment for the whole env-step; the environment's working set (transforms, spatial
 // vectors, H^-1, adjoint accumulators: dfx_pack.h Layout) lives in a private shared-memory block,
 // the model description is staged once per CTA into shared memory, and the only global traffic is
@@ -202,7 +203,7 @@ struct dfx_pack {
 static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
-static int g_flags = 9;   // bit 1: phase barriers; bit 2: DISABLE the size-specialised kernels (A/B testing); bit 3: CTA-wide task loops
+static int g_flags = 9;   // include/dfx.h dfx_set_flags: 2 phase barriers, 4 generic kernels, 8 CTA-wide task loops, 32 no tile kernels
 
 static void set_err(char* err, int n, const std::string& m) {
     if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }

@@ -194,9 +194,11 @@ int dfx_action_map_backward(int n, int num_act, int width, int offset, float pre
 
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
-/* Tuning flags (default 9): bit 1 (2) = extra CTA-wide barriers between phases (instruction-cache locality; no longer
- * a gain now that the task loops synchronise the CTA anyway); bit 2 (4) = generic
- * kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases. */
+/* Tuning flags (default 9; for A/B timing and tests).  Lane-group kernels: bit 1 (2) = extra CTA-wide barriers between
+ * phases (instruction-cache locality; no longer a gain now that the task loops synchronise the CTA anyway); bit 2 (4) =
+ * generic kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases.
+ * Bit 5 (32), read when a pack is CREATED: keep an articulation that has a 32-environment tile kernel on the
+ * lane-group kernels (the two families lay the tape out differently, DFX_QUERY_TAPE_TILE). */
 int dfx_set_flags(int flags);
 /* Launch geometry the step kernel would use for this pack (host arithmetic, no GPU needed):
  * out[0] lanes per environment, out[1] environments per CTA, out[2] CTAs per SM (shared-memory / register bound),
