@@ -30,6 +30,21 @@ def _f32c(t, device):
     return t
 
 
+_GRAVEYARD = []
+
+
+def _bury():
+    """Free the packs of dead engines unless a capture is in progress."""
+    try:
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            return
+    except Exception:
+        return
+    while _GRAVEYARD:
+        lib, pack = _GRAVEYARD.pop()
+        lib.dfx_pack_destroy(pack)
+
+
 class ArticulationEngine:
     """Device-resident description of one articulation + launchers for N environments."""
 
@@ -44,6 +59,7 @@ class ArticulationEngine:
         self.device = torch.device("cuda", index)
         err = ctypes.create_string_buffer(512)
         struct = desc.as_struct()
+        _bury()
         self.pack = self.lib.dfx_pack_create(ctypes.byref(struct), index, err, 512)
         if not self.pack:
             raise _capi.DfxError("dfx_pack_create: " + err.value.decode())
@@ -56,10 +72,13 @@ class ArticulationEngine:
         return cls(desc, n, device)
 
     def __del__(self):
+        # dfx_pack_destroy() is a cudaFree (device-synchronising): it must not run while a CUDA graph is being captured,
+        # and the garbage collector can fire at any time -- packs released during a capture wait for the next engine
         try:
             if getattr(self, "pack", None):
-                self.lib.dfx_pack_destroy(self.pack)
+                _GRAVEYARD.append((self.lib, self.pack))
                 self.pack = None
+                _bury()
         except Exception:
             pass
 

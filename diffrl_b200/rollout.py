@@ -52,8 +52,16 @@ class GraphedRollout:
         torch.cuda.synchronize(dev)
         self.actions.grad = None
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        import gc
+        gc.collect()                      # nothing device-synchronising (e.g. a dead engine's cudaFree) may run mid-capture
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph):
+                self._body()
+        finally:
+            if gc_was_enabled:
+                gc.enable()
         torch.cuda.synchronize(dev)
 
     def _body(self):
