@@ -218,3 +218,30 @@ def test_tile_and_lane_group_kernels_agree(name):
         lib.dfx_set_flags(9)
     for a, b in zip(*res):
         assert rel(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+
+
+def test_ant_65536_envs_equal_their_64_env_pattern():
+    """BASELINE.json configs[4] size on ONE device (2048 tiles, 1.7 GB of tape per env-step): 65 536 environments that
+    repeat a 64-environment pattern give, environment by environment, the results of the 64-environment batch
+    (64-bit tape offsets, tile padding, grid far beyond one wave)."""
+    import torch
+    from diffrl_b200.engine import ArticulationEngine
+    d, emu, q0, qd0, act = _case("AntEnv", 64, seed=9)
+    S, mm, dt = int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    t = lambda a: torch.tensor(np.ascontiguousarray(a).ravel(), device="cuda:0")
+    small = ArticulationEngine(emu.desc, 64, "cuda:0")
+    gq_s, gqd_s = torch.linspace(-1.0, 1.0, q0.size, device="cuda:0"), torch.linspace(1.0, -1.0, qd0.size, device="cuda:0")
+    q, qd, tape, _ = small.forward(t(q0), t(qd0), t(act), None, S, mm, dt)
+    g_small = small.backward(t(act), None, tape, gq_s, gqd_s, S, mm, dt)
+    N, rep = 65536, 65536 // 64
+    big = ArticulationEngine(emu.desc, N, "cuda:0")
+    tile = lambda a: t(np.tile(a, (rep, 1)))
+    Q, D = emu.desc.Q, emu.desc.D
+    Q_, QD_, TP, _ = big.forward(tile(q0), tile(qd0), tile(act), None, S, mm, dt)
+    assert TP.numel() == big.tape_floats(S, mm) and TP.numel() * 4 > 1.5e9
+    assert torch.equal(Q_.view(rep, 64 * Q), q.view(1, -1).expand(rep, -1))
+    assert torch.equal(QD_.view(rep, 64 * D), qd.view(1, -1).expand(rep, -1))
+    G = big.backward(tile(act), None, TP, gq_s.view(64, Q).repeat(rep, 1).reshape(-1), gqd_s.view(64, D).repeat(rep, 1).reshape(-1), S, mm, dt)
+    for a, b, w in zip(G[:3], g_small[:3], (Q, D, D)):
+        ref = b.view(1, 64 * w).expand(rep, -1)
+        assert (a.view(rep, 64 * w) - ref).abs().max() <= 2e-5 * ref.abs().max()
