@@ -68,18 +68,26 @@ class Actor(nn.Module):
 
 
 class RunningMeanStd:
+    """Running moments kept in device tensors and updated IN PLACE (so that a captured CUDA graph sees them)."""
+
     def __init__(self, shape, device):
         self.mean = torch.zeros(shape, device=device)
         self.var = torch.ones(shape, device=device)
-        self.count = 1e-4
+        self.count = torch.full((), 1e-4, device=device)
 
     @torch.no_grad()
     def update(self, x):
         n, m, v = allreduce_moments(x.shape[0], x.mean(0), x.var(0, unbiased=False))
         delta, tot = m - self.mean, self.count + n
-        self.var = (self.var * self.count + v * n + delta.square() * self.count * n / tot) / tot
-        self.mean = self.mean + delta * n / tot
-        self.count = tot
+        self.var.copy_((self.var * self.count + v * n + delta.square() * self.count * n / tot) / tot)
+        self.mean.add_(delta * n / tot)
+        self.count.copy_(tot)
+
+    def frozen(self):
+        """A snapshot (the statistics entering a rollout)."""
+        f = RunningMeanStd.__new__(RunningMeanStd)
+        f.mean, f.var, f.count = self.mean.clone(), self.var.clone(), self.count.clone()
+        return f
 
     def normalize(self, x):
         return (x - self.mean) / torch.sqrt(self.var + 1e-5)
@@ -94,6 +102,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--log-interval", type=int, default=50)
     ap.add_argument("--out", default="")
+    ap.add_argument("--graph", type=int, default=-1,
+                    help="1: capture one whole training iteration (rollout, backward, actor step, critic training) in ONE "
+                         "CUDA graph and replay it per epoch; 0: eager; default: on for single-GPU runs")
     args = ap.parse_args()
     cfg = PRESETS[args.env]
 
@@ -119,27 +130,35 @@ def main():
     critic = mlp([obs_dim] + cfg["critic"] + [1]).to(dev)
     target_critic = copy.deepcopy(critic)
     torch.manual_seed(args.seed + 1000 * (rank + 1))   # different exploration noise / resets per rank
-    a_opt = torch.optim.Adam(actor.parameters(), lr=cfg["lr"], betas=cfg["betas"])
-    c_opt = torch.optim.Adam(critic.parameters(), lr=cfg["lr"], betas=cfg["betas"])
+    use_graph = (world == 1) if args.graph < 0 else bool(args.graph)
+    lr0 = torch.tensor(cfg["lr"], device=dev) if use_graph else cfg["lr"]      # a tensor lr can change under a captured graph
+    a_opt = torch.optim.Adam(actor.parameters(), lr=lr0, betas=cfg["betas"], capturable=use_graph)
+    c_opt = torch.optim.Adam(critic.parameters(), lr=lr0.clone() if use_graph else lr0, betas=cfg["betas"], capturable=use_graph)
     obs_rms = RunningMeanStd((obs_dim,), dev)
 
     obs_buf = torch.zeros((T, n, obs_dim), device=dev)
     rew_buf, done_mask, next_vals = (torch.zeros((T, n), device=dev) for _ in range(3))
-    ep_ret, ep_len_cnt = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
     fin_ret, fin_cnt = torch.zeros((), device=dev), torch.zeros((), device=dev)
+    actor_loss_s = torch.zeros((), device=dev)
     history, t_start = [], time.time()
     env.clear_grad()
     env.reset()
+    # everything carried from one iteration to the next lives in static tensors that are updated in place, so that the
+    # same code runs eagerly and as a replayed CUDA graph
+    carry = {"q": env.state.joint_q.detach().clone(), "qd": env.state.joint_qd.detach().clone(),
+             "progress": env.progress_buf.clone(), "actions": env.actions.detach().clone(),
+             "ep_ret": torch.zeros(n, device=dev), "ep_len": torch.zeros(n, device=dev)}
 
-    for epoch in range(max_epochs):
-        lr = (1e-5 - cfg["lr"]) * epoch / max_epochs + cfg["lr"]
-        for opt in (a_opt, c_opt):
-            for group in opt.param_groups:
-                group["lr"] = lr
+    def train_iteration():
         # ---------------------------------------------------------------- actor: short-horizon rollout
         a_opt.zero_grad(set_to_none=True)
-        frozen = copy.copy(obs_rms)                       # normalise with the statistics entering the rollout
-        obs = env.initialize_trajectory()
+        frozen = obs_rms.frozen()                         # normalise with the statistics entering the rollout
+        env.state = env.model.state()                     # == env.initialize_trajectory() on the carried state
+        env.state.joint_q, env.state.joint_qd = carry["q"].clone(), carry["qd"].clone()
+        env.progress_buf, env.actions = carry["progress"].clone(), carry["actions"].clone()
+        env.calculateObservations()
+        obs = env.obs_buf
+        ep_ret, ep_len_cnt = carry["ep_ret"].clone(), carry["ep_len"].clone()
         obs_rms.update(obs)
         obs = frozen.normalize(obs)
         rew_acc = torch.zeros(n, device=dev)
@@ -151,9 +170,8 @@ def main():
             obs_rms.update(obs)
             obs = frozen.normalize(obs)
             done_b = done.bool()
-            ep_len_cnt += 1
-            with torch.no_grad():
-                ep_ret += rew
+            ep_len_cnt = ep_len_cnt + 1
+            ep_ret = ep_ret + rew.detach()
             before = extra["obs_before_reset"]
             v = target_critic(obs).squeeze(-1)
             v_term = target_critic(frozen.normalize(before)).squeeze(-1)
@@ -171,8 +189,8 @@ def main():
                 rew_buf[i] = rew
                 done_mask[i] = done_b.float() if i < T - 1 else 1.0
                 next_vals[i] = nv
-                fin_ret += (ep_ret * done_b).sum()
-                fin_cnt += done_b.sum()
+                fin_ret.add_((ep_ret * done_b).sum())
+                fin_cnt.add_(done_b.sum())
                 ep_ret = torch.where(done_b, torch.zeros_like(ep_ret), ep_ret)
                 ep_len_cnt = torch.where(done_b, torch.zeros_like(ep_len_cnt), ep_len_cnt)
         actor_loss = actor_loss / (T * n * world)          # global batch normalisation (reference shac.py:291)
@@ -180,6 +198,11 @@ def main():
         allreduce_gradients(list(actor.parameters()), average=False)     # the one collective per rollout
         torch.nn.utils.clip_grad_norm_(actor.parameters(), 1.0)
         a_opt.step()
+        with torch.no_grad():
+            actor_loss_s.copy_(actor_loss.detach())
+            carry["q"].copy_(env.state.joint_q.detach().view(-1)); carry["qd"].copy_(env.state.joint_qd.detach().view(-1))
+            carry["progress"].copy_(env.progress_buf); carry["actions"].copy_(env.actions.detach())
+            carry["ep_ret"].copy_(ep_ret); carry["ep_len"].copy_(ep_len_cnt)
         # ---------------------------------------------------------------- critic: TD(lambda) targets
         with torch.no_grad():
             Ai, Bi, lm = (torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.ones(n, device=dev))
@@ -192,7 +215,7 @@ def main():
             flat_obs, flat_tgt = obs_buf.view(-1, obs_dim), targets.view(-1)
         batch = flat_obs.shape[0] // 4
         for _ in range(16):
-            perm = torch.randperm(flat_obs.shape[0], device=dev)
+            perm = torch.rand(flat_obs.shape[0], device=dev).argsort()       # (graph-capturable random permutation)
             for b in range(4):
                 idx = perm[b * batch:(b + 1) * batch]
                 c_opt.zero_grad(set_to_none=True)
@@ -206,6 +229,33 @@ def main():
         with torch.no_grad():
             for p, pt in zip(critic.parameters(), target_critic.parameters()):
                 pt.mul_(cfg["alpha"]).add_((1.0 - cfg["alpha"]) * p)
+
+    graph, warm_epochs = None, 3
+    for epoch in range(max_epochs):
+        lr = (1e-5 - cfg["lr"]) * epoch / max_epochs + cfg["lr"]
+        for opt in (a_opt, c_opt):
+            for group in opt.param_groups:
+                if use_graph:
+                    group["lr"].fill_(lr)
+                else:
+                    group["lr"] = lr
+        if not use_graph:
+            train_iteration()
+        elif epoch < warm_epochs:         # warm-up on a side stream, as the capture will run on one
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                train_iteration()
+            torch.cuda.current_stream(dev).wait_stream(side)
+        else:
+            if graph is None:             # the first iterations ran eagerly (allocator / optimizer state warm-up)
+                import gc
+                torch.cuda.synchronize()
+                gc.collect()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    train_iteration()
+            graph.replay()
         # ---------------------------------------------------------------- logging (one host sync per interval)
         if (epoch + 1) % args.log_interval == 0 or epoch == max_epochs - 1:
             stats = torch.stack([fin_ret, fin_cnt])
@@ -215,14 +265,14 @@ def main():
             steps = (epoch + 1) * T * n * world
             if rank == 0:
                 rec = {"epoch": epoch + 1, "env_steps": steps, "mean_episode_return": ret, "episodes": int(stats[1]),
-                       "actor_loss": float(actor_loss), "wall_s": round(time.time() - t_start, 1),
+                       "actor_loss": float(actor_loss_s), "wall_s": round(time.time() - t_start, 1),
                        "env_steps_per_s_training": round(steps / (time.time() - t_start))}
                 history.append(rec)
                 print(json.dumps(rec), flush=True)
             fin_ret.zero_(); fin_cnt.zero_()
     if rank == 0 and args.out:
         with open(args.out, "w") as f:
-            json.dump({"env": args.env, "num_envs": total_envs, "world": world, "history": history}, f, indent=1)
+            json.dump({"env": args.env, "num_envs": total_envs, "world": world, "cuda_graph": bool(use_graph), "history": history}, f, indent=1)
     if world > 1:
         torch.distributed.destroy_process_group()
 
