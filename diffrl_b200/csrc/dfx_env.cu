@@ -240,6 +240,144 @@ __global__ void walker_transition_backward_kernel(DfxWalkerParams p, int n, cons
     if (gae && g_actions_next) { const float* g = g_actions_next + (size_t)e * p.num_act; for (int i = 0; i < p.num_act; ++i) gae[i] += g[i]; }
 }
 
+
+// ---- planar envs (Hopper, HalfCheetah: observation = [q[1:], qd]; CartPole swing-up: [x, xd, sin th, cos th, thd]):
+// the same transition as walker_transition_*, reference envs/hopper.py:170-268, envs/cheetah.py:160-244,
+// envs/cartpole_swing_up.py:120-187
+__device__ __forceinline__ void planar_eval(const DfxPlanarParams& p, const float* __restrict__ qe, const float* __restrict__ qde,
+                                            const float* __restrict__ ae, long long progress, bool want_reward,
+                                            float* __restrict__ o, float* r_out, long long* rs_out) {
+    float act_sq = 0.0f;
+    for (int i = 0; i < p.num_act; ++i) { const float a = ae ? ae[i] : 0.0f; act_sq += a * a; }
+    if (p.kind == 2) {                      // CartPole
+        const float x = qe[0], th = qe[1], xd = qde[0], thd = qde[1];
+        o[0] = x; o[1] = xd; o[2] = sinf(th); o[3] = cosf(th); o[4] = thd;
+        if (!want_reward) return;
+        const float t = atan2f(sinf(th), cosf(th));                  // normalize_angle
+        *r_out = -(t * t) * p.pole_angle_penalty - (thd * thd) * p.pole_velocity_penalty - (x * x) * p.cart_position_penalty
+                 - (xd * xd) * p.cart_velocity_penalty - act_sq * p.action_penalty;
+        *rs_out = (progress > (long long)p.episode_length - 1) ? 1 : 0;
+        return;
+    }
+    int k = 0;
+    for (int i = 1; i < p.num_q; ++i) o[k++] = qe[i];
+    for (int i = 0; i < p.num_qd; ++i) o[k++] = qde[i];
+    if (!want_reward) return;
+    const float vx = qde[0];                // o[num_q - 1]
+    long long rs = (progress > (long long)p.episode_length - 1) ? 1 : 0;
+    if (p.kind == 0) {                      // Hopper
+        const float h0 = qe[1], ang = qe[2];
+        float h = fminf(fmaxf(h0 - (p.termination_height + p.termination_height_tolerance), -1.0f), 0.3f);
+        if (h < 0.0f) h = -200.0f * h * h;
+        if (h > 0.0f) h = p.height_rew_scale * h;
+        const float angle_reward = 1.0f * (-(ang * ang) / (p.termination_angle * p.termination_angle) + 1.0f);
+        *r_out = vx + h + angle_reward + act_sq * p.action_penalty;
+        if (p.early_termination && h0 < p.termination_height) rs = 1;
+    } else {                                // HalfCheetah
+        *r_out = vx + act_sq * p.action_penalty;
+    }
+    *rs_out = rs;
+}
+
+__device__ __forceinline__ void planar_eval_adj(const DfxPlanarParams& p, const float* __restrict__ qe, const float* __restrict__ qde,
+                                                const float* __restrict__ ae, const float* __restrict__ go,
+                                                const float* __restrict__ go2, float gr,
+                                                float* __restrict__ gqe, float* __restrict__ gqde, float* __restrict__ gae) {
+    auto G = [&](int idx) { return (go ? go[idx] : 0.0f) + (go2 ? go2[idx] : 0.0f); };
+    if (gae) for (int i = 0; i < p.num_act; ++i) gae[i] = (p.kind == 2 ? -1.0f : 1.0f) * gr * p.action_penalty * 2.0f * ae[i];
+    if (p.kind == 2) {
+        const float x = qe[0], th = qe[1], xd = qde[0], thd = qde[1];
+        const float t = atan2f(sinf(th), cosf(th));
+        gqe[0] = G(0) - gr * 2.0f * x * p.cart_position_penalty;
+        gqe[1] = G(2) * cosf(th) - G(3) * sinf(th) - gr * 2.0f * t * p.pole_angle_penalty;     // d normalize_angle / d th = 1
+        gqde[0] = G(1) - gr * 2.0f * xd * p.cart_velocity_penalty;
+        gqde[1] = G(4) - gr * 2.0f * thd * p.pole_velocity_penalty;
+        return;
+    }
+    int k = 0;
+    gqe[0] = 0.0f;
+    for (int i = 1; i < p.num_q; ++i) gqe[i] = G(k++);
+    for (int i = 0; i < p.num_qd; ++i) gqde[i] = G(k++);
+    gqde[0] += gr;
+    if (p.kind == 0) {
+        const float h0 = qe[1], ang = qe[2];
+        const float x = h0 - (p.termination_height + p.termination_height_tolerance);
+        const float h = fminf(fmaxf(x, -1.0f), 0.3f);
+        const float dclip = (x >= -1.0f && x <= 0.3f) ? 1.0f : 0.0f;     // torch.clip passes the gradient on the closed interval
+        float dh = dclip;                                                   // h == 0: both torch.where keep h
+        if (h < 0.0f) dh = -400.0f * h * dclip;
+        else if (h > 0.0f) dh = p.height_rew_scale * dclip;
+        gqe[1] += gr * dh;
+        gqe[2] += gr * (-2.0f * ang / (p.termination_angle * p.termination_angle));
+    }
+}
+
+__global__ void planar_transition_forward_kernel(DfxPlanarParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                                 const float* __restrict__ actions, const long long* __restrict__ progress,
+                                                 const float* __restrict__ start_q, const float* __restrict__ start_qd,
+                                                 float* __restrict__ obs_before, float* __restrict__ rew, long long* __restrict__ reset,
+                                                 float* __restrict__ q_next, float* __restrict__ qd_next,
+                                                 float* __restrict__ actions_next, long long* __restrict__ progress_next,
+                                                 float* __restrict__ obs_next) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float* qe = q + (size_t)e * p.num_q;
+    const float* qde = qd + (size_t)e * p.num_qd;
+    const float* ae = actions + (size_t)e * p.num_act;
+    float* ob = obs_before + (size_t)e * p.num_obs;
+    float* on = obs_next + (size_t)e * p.num_obs;
+    const long long pr = progress[e] + 1;
+    float r = 0.0f;
+    long long rs = 0;
+    planar_eval(p, qe, qde, ae, pr, true, ob, &r, &rs);
+    rew[e] = r;
+    reset[e] = rs;
+    progress_next[e] = rs ? 0 : pr;
+    float* qn = q_next + (size_t)e * p.num_q;
+    float* qdn = qd_next + (size_t)e * p.num_qd;
+    float* an = actions_next + (size_t)e * p.num_act;
+    if (rs) {
+        const float* sq = start_q + (size_t)e * p.num_q;
+        const float* sqd = start_qd + (size_t)e * p.num_qd;
+        for (int i = 0; i < p.num_q; ++i) qn[i] = sq[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = sqd[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = p.zero_actions_on_reset ? 0.0f : ae[i];
+        float r2; long long rs2;
+        planar_eval(p, sq, sqd, p.zero_actions_on_reset ? nullptr : ae, 0, false, on, &r2, &rs2);
+    } else {
+        for (int i = 0; i < p.num_q; ++i) qn[i] = qe[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = qde[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = ae[i];
+        for (int i = 0; i < p.num_obs; ++i) on[i] = ob[i];
+    }
+}
+
+__global__ void planar_transition_backward_kernel(DfxPlanarParams p, int n, const float* __restrict__ q, const float* __restrict__ qd,
+                                                  const float* __restrict__ actions, const long long* __restrict__ reset,
+                                                  const float* __restrict__ g_obs_before, const float* __restrict__ g_rew,
+                                                  const float* __restrict__ g_q_next, const float* __restrict__ g_qd_next,
+                                                  const float* __restrict__ g_actions_next, const float* __restrict__ g_obs_next,
+                                                  float* __restrict__ gq, float* __restrict__ gqd, float* __restrict__ gact) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const bool live = reset[e] == 0;
+    float* gqe = gq + (size_t)e * p.num_q;
+    float* gqde = gqd + (size_t)e * p.num_qd;
+    float* gae = gact ? gact + (size_t)e * p.num_act : nullptr;
+    planar_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
+                    g_obs_before ? g_obs_before + (size_t)e * p.num_obs : nullptr,
+                    (live && g_obs_next) ? g_obs_next + (size_t)e * p.num_obs : nullptr,
+                    g_rew ? g_rew[e] : 0.0f, gqe, gqde, gae);
+    // the actions survive a reset in envs that do not clear them (CartPole): their cotangent passes either way
+    if (gae && g_actions_next && (live || !p.zero_actions_on_reset)) {
+        const float* g = g_actions_next + (size_t)e * p.num_act;
+        for (int i = 0; i < p.num_act; ++i) gae[i] += g[i];
+    }
+    if (!live) return;
+    if (g_q_next) { const float* g = g_q_next + (size_t)e * p.num_q; for (int i = 0; i < p.num_q; ++i) gqe[i] += g[i]; }
+    if (g_qd_next) { const float* g = g_qd_next + (size_t)e * p.num_qd; for (int i = 0; i < p.num_qd; ++i) gqde[i] += g[i]; }
+}
+
 // ---- policy output -> actuation, one thread per (environment, action):
 //   u = clip(a, -1, 1) * pre_scale + pre_bias          (what the env keeps as `actions`: observation + penalty)
 //   drive[e, offset + j] = (u * drive_scale) * strength[j]   (joint_act row of width `width`, or the muscle activations;
@@ -319,6 +457,31 @@ int dfx_walker_transition_backward(const DfxWalkerParams* p, int n, const float*
                                    const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream) {
     if (!p || n <= 0 || !q || !qd || !actions || !reset || !gq || !gqd) return (int)cudaErrorInvalidValue;
     walker_transition_backward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(
+        *p, n, q, qd, actions, reset, g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next, gq, gqd, gact);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_planar_transition_forward(const DfxPlanarParams* p, int n, const float* q, const float* qd, const float* actions,
+                                  const long long* progress, const float* start_q, const float* start_qd,
+                                  float* obs_before, float* rew, long long* reset, float* q_next, float* qd_next,
+                                  float* actions_next, long long* progress_next, float* obs_next, void* stream) {
+    if (!p || n <= 0 || !q || !qd || !actions || !progress || !start_q || !start_qd || !obs_before || !rew || !reset ||
+        !q_next || !qd_next || !actions_next || !progress_next || !obs_next || p->kind < 0 || p->kind > 2)
+        return (int)cudaErrorInvalidValue;
+    planar_transition_forward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(
+        *p, n, q, qd, actions, progress, start_q, start_qd, obs_before, rew, reset, q_next, qd_next, actions_next,
+        progress_next, obs_next);
+    dfx_count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dfx_planar_transition_backward(const DfxPlanarParams* p, int n, const float* q, const float* qd, const float* actions,
+                                   const long long* reset, const float* g_obs_before, const float* g_rew,
+                                   const float* g_q_next, const float* g_qd_next, const float* g_actions_next,
+                                   const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream) {
+    if (!p || n <= 0 || !q || !qd || !actions || !reset || !gq || !gqd || p->kind < 0 || p->kind > 2) return (int)cudaErrorInvalidValue;
+    planar_transition_backward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(
         *p, n, q, qd, actions, reset, g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next, gq, gqd, gact);
     dfx_count_launch();
     return (int)cudaGetLastError();

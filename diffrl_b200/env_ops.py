@@ -22,6 +22,20 @@ class DfxWalkerParams(ctypes.Structure):
     ]
 
 
+class DfxPlanarParams(ctypes.Structure):
+    """ctypes mirror of ``DfxPlanarParams`` in include/dfx.h (keep field order in sync)."""
+
+    _fields_ = [
+        ("num_q", ctypes.c_int), ("num_qd", ctypes.c_int), ("num_act", ctypes.c_int), ("num_obs", ctypes.c_int),
+        ("kind", ctypes.c_int), ("early_termination", ctypes.c_int), ("zero_actions_on_reset", ctypes.c_int),
+        ("episode_length", ctypes.c_int),
+        ("termination_height", ctypes.c_float), ("termination_height_tolerance", ctypes.c_float),
+        ("termination_angle", ctypes.c_float), ("height_rew_scale", ctypes.c_float), ("action_penalty", ctypes.c_float),
+        ("pole_angle_penalty", ctypes.c_float), ("pole_velocity_penalty", ctypes.c_float),
+        ("cart_position_penalty", ctypes.c_float), ("cart_velocity_penalty", ctypes.c_float),
+    ]
+
+
 def _bind(lib):
     if getattr(lib, "_walker_bound", False):
         return
@@ -31,6 +45,9 @@ def _bind(lib):
     lib.dfx_walker_obs_backward.argtypes = [P, ctypes.c_int, V, V, V, V, V, V, V, V, V]
     lib.dfx_walker_transition_forward.argtypes = [P, ctypes.c_int] + [V] * 15
     lib.dfx_walker_transition_backward.argtypes = [P, ctypes.c_int] + [V] * 14
+    PP = ctypes.POINTER(DfxPlanarParams)
+    lib.dfx_planar_transition_forward.argtypes = [PP, ctypes.c_int] + [V] * 15
+    lib.dfx_planar_transition_backward.argtypes = [PP, ctypes.c_int] + [V] * 14
     I, F = ctypes.c_int, ctypes.c_float
     lib.dfx_action_map_forward.argtypes = [I, I, I, I, F, F, F, V, V, V, V, V]
     lib.dfx_action_map_backward.argtypes = [I, I, I, I, F, F, V, V, V, V, V, V]
@@ -93,7 +110,8 @@ def _stream(dev):
 
 
 class WalkerTransitionFunction(torch.autograd.Function):
-    """Everything env.step() does after the simulation step, in one launch (``dfx_walker_transition_forward``):
+    """Everything env.step() does after the simulation step, in one launch (``dfx_walker_transition_forward``, or
+    ``dfx_planar_transition_forward`` when ``params`` is a ``DfxPlanarParams``):
     (q, qd, actions) of the stepped state -> (obs_before_reset, rew, reset, q_next, qd_next, actions_next,
     progress_next, obs_next).  ``progress`` is the counter before the step; ``start_q`` / ``start_qd`` the state a
     terminated environment restarts from (constants for autograd)."""
@@ -112,12 +130,13 @@ class WalkerTransitionFunction(torch.autograd.Function):
         reset = torch.empty(n, dtype=torch.long, device=dev)
         progress_next = torch.empty(n, dtype=torch.long, device=dev)
         q_next, qd_next, actions_next = torch.empty_like(q), torch.empty_like(qd), torch.empty_like(actions)
+        fwd = lib.dfx_planar_transition_forward if isinstance(params, DfxPlanarParams) else lib.dfx_walker_transition_forward
         with torch.cuda.device(dev):
-            code = lib.dfx_walker_transition_forward(
+            code = fwd(
                 ctypes.byref(params), n, _ptr(q), _ptr(qd), _ptr(actions), _ptr(progress), _ptr(start_q), _ptr(start_qd),
                 _ptr(obs_before), _ptr(rew), _ptr(reset), _ptr(q_next), _ptr(qd_next), _ptr(actions_next),
                 _ptr(progress_next), _ptr(obs_next), _stream(dev))
-        _capi.check(code, "dfx_walker_transition_forward")
+        _capi.check(code, "dfx_*_transition_forward")
         ctx.params, ctx.n = params, n
         ctx.set_materialize_grads(False)      # absent cotangents arrive as None (NULL in the C ABI), not as zero fills
         ctx.save_for_backward(q, qd, actions, reset)
@@ -132,11 +151,12 @@ class WalkerTransitionFunction(torch.autograd.Function):
         gq, gqd = torch.empty_like(q), torch.empty_like(qd)
         gact = torch.empty_like(actions) if ctx.needs_input_grad[7] else None
         cot = [None if g is None else _c(g) for g in (g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next)]
+        bwd = lib.dfx_planar_transition_backward if isinstance(ctx.params, DfxPlanarParams) else lib.dfx_walker_transition_backward
         with torch.cuda.device(dev):
-            code = lib.dfx_walker_transition_backward(
+            code = bwd(
                 ctypes.byref(ctx.params), ctx.n, _ptr(q), _ptr(qd), _ptr(actions), _ptr(reset),
                 *[_ptr(g) for g in cot], _ptr(gq), _ptr(gqd), _ptr(gact), _stream(dev))
-        _capi.check(code, "dfx_walker_transition_backward")
+        _capi.check(code, "dfx_*_transition_backward")
         return None, None, None, None, None, gq, gqd, gact
 
 

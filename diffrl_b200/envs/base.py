@@ -147,6 +147,39 @@ class DFlexEnv:
                 self.reset(env_ids)
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
+    def _fused_step(self, actions):
+        """env.step() as three launches: policy output -> actuation (``dfx_action_map_forward``), the simulation step,
+        and the transition (progress counter, observation, reward, termination, masked re-initialisation, next
+        observation: ``dfx_walker_transition_forward`` / ``dfx_planar_transition_forward``).  The env provides
+        ``_action_map()`` and ``_transition_params()``; results equal the op-by-op ``step`` (tests/test_gpu_envs.py)."""
+        from ..env_ops import ActionMapFunction, WalkerTransitionFunction
+        n = self.num_envs
+        if getattr(self, "_amap", None) is None:
+            self._amap = self._action_map()
+            self._tparams = self._transition_params()
+        width, offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = self._amap
+        used, drive = ActionMapFunction.apply(n, width, offset, pre_scale, pre_bias, drive_scale, strength,
+                                              actions.view((n, self.num_actions)))
+        if self.nan_guard:
+            self._nan_guard(used)
+        self.actions = used
+        if is_muscle:
+            self.model.muscle_activation = drive
+        else:
+            self.state.joint_act = drive
+        self.state = self.integrator.forward(self.model, self.state, self.sim_dt, self.sim_substeps, self.MM_caching_frequency)
+        self.sim_time += self.sim_dt
+        self.num_frames += 1
+        start_q, start_qd = self._start_state()
+        (obs_before, self.rew_buf, self.reset_buf, q_next, qd_next, self.actions, self.progress_buf,
+         self.obs_buf) = WalkerTransitionFunction.apply(self._tparams, n, self.progress_buf, start_q, start_qd,
+                                                        self.state.joint_q, self.state.joint_qd, self.actions)
+        self.state.joint_q, self.state.joint_qd = q_next.view(-1), qd_next.view(-1)
+        if not self.no_grad:
+            self.obs_buf_before_reset = obs_before
+            self.extras = {"obs_before_reset": obs_before, "episode_end": self.termination_buf}
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
     def _reset_masked(self, reset_buf):
         """Re-initialise terminated environments without reading reset_buf on the host: the start state is formed
         for every row (``_start_state()``: the same distributions as ``_reset_state``) and selected by mask."""

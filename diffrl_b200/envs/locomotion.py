@@ -103,44 +103,21 @@ class _FreeRootWalker(DFlexEnv):
             start_qd = 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
         return start_q, start_qd
 
-    # ---- fused step: policy output -> actuation (1 launch), simulation step (1 launch), transition (1 launch) ----
+    # ---- fused step (DFlexEnv._fused_step): action map, simulation step, transition = 3 launches ----
     fused_transition = True
 
     def _action_map(self):
         """(width, offset, pre_scale, pre_bias, drive_scale, strength [A], is_muscle) of dfx_action_map_forward."""
         raise NotImplementedError
 
+    def _transition_params(self):
+        return self._walker_params()
+
     def step(self, actions):
         if not (self.fused_transition and self.fused_epilogue and self.sync_free_reset
                 and torch.device(self.device).type == "cuda"):
             return super().step(actions)
-        from ..env_ops import ActionMapFunction, WalkerTransitionFunction
-        n = self.num_envs
-        if getattr(self, "_amap", None) is None:
-            self._amap = self._action_map()
-            self._wparams = self._walker_params()
-        width, offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = self._amap
-        used, drive = ActionMapFunction.apply(n, width, offset, pre_scale, pre_bias, drive_scale, strength,
-                                              actions.view((n, self.num_actions)))
-        if self.nan_guard:
-            self._nan_guard(used)
-        self.actions = used
-        if is_muscle:
-            self.model.muscle_activation = drive
-        else:
-            self.state.joint_act = drive
-        self.state = self.integrator.forward(self.model, self.state, self.sim_dt, self.sim_substeps, self.MM_caching_frequency)
-        self.sim_time += self.sim_dt
-        self.num_frames += 1
-        start_q, start_qd = self._start_state()
-        (obs_before, self.rew_buf, self.reset_buf, q_next, qd_next, self.actions, self.progress_buf,
-         self.obs_buf) = WalkerTransitionFunction.apply(self._wparams, n, self.progress_buf, start_q, start_qd,
-                                                        self.state.joint_q, self.state.joint_qd, self.actions)
-        self.state.joint_q, self.state.joint_qd = q_next.view(-1), qd_next.view(-1)
-        if not self.no_grad:
-            self.obs_buf_before_reset = obs_before
-            self.extras = {"obs_before_reset": obs_before, "episode_end": self.termination_buf}
-        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+        return self._fused_step(actions)
 
     def _torso_features(self):
         q = self.state.joint_q.view(self.num_envs, -1)
@@ -370,6 +347,29 @@ class CartPoleSwingUpEnv(DFlexEnv):
             start_qd = start_qd + 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
         return start_q, start_qd
 
+    # ---- fused step (DFlexEnv._fused_step) ----
+    fused_transition = True
+
+    def _action_map(self):
+        strength = torch.full((self.num_actions,), float(self.action_strength), device=self.device)
+        return self.num_joint_qd, 0, 1.0, 0.0, 1.0, strength, False
+
+    def _transition_params(self):
+        from ..env_ops import DfxPlanarParams
+        p = DfxPlanarParams()
+        p.num_q, p.num_qd, p.num_act, p.num_obs = 2, 2, 1, 5
+        p.kind, p.early_termination, p.zero_actions_on_reset = 2, 0, int(self.clone_actions)
+        p.episode_length = int(self.episode_length)
+        p.action_penalty = float(self.cart_action_penalty)
+        p.pole_angle_penalty, p.pole_velocity_penalty = float(self.pole_angle_penalty), float(self.pole_velocity_penalty)
+        p.cart_position_penalty, p.cart_velocity_penalty = float(self.cart_position_penalty), float(self.cart_velocity_penalty)
+        return p
+
+    def step(self, actions):
+        if not (self.fused_transition and self.sync_free_reset and torch.device(self.device).type == "cuda"):
+            return super().step(actions)
+        return self._fused_step(actions)
+
     def clear_grad(self, checkpoint=None):
         with torch.no_grad():
             q, qd, act = self.state.joint_q.clone(), self.state.joint_qd.clone(), self.state.joint_act.clone()
@@ -442,6 +442,32 @@ class _PlanarHopper(DFlexEnv):
             start_qd = a_vel * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
         return start_q, start_qd
 
+    # ---- fused step (DFlexEnv._fused_step) ----
+    fused_transition = True
+    planar_kind = 0
+
+    def _action_map(self):
+        strength = torch.full((self.num_actions,), float(self.action_strength), device=self.device)
+        return self.num_joint_qd, 3, 1.0, 0.0, 1.0, strength, False
+
+    def _transition_params(self):
+        from ..env_ops import DfxPlanarParams
+        p = DfxPlanarParams()
+        p.num_q, p.num_qd, p.num_act, p.num_obs = self.num_joint_q, self.num_joint_qd, self.num_actions, self.num_observations
+        p.kind, p.early_termination = int(self.planar_kind), int(self.early_termination)
+        p.zero_actions_on_reset, p.episode_length = int(self.clone_actions), int(self.episode_length)
+        p.termination_height = float(getattr(self, "termination_height", 0.0))
+        p.termination_height_tolerance = float(getattr(self, "termination_height_tolerance", 0.0))
+        p.termination_angle = float(getattr(self, "termination_angle", 1.0))
+        p.height_rew_scale = float(getattr(self, "height_rew_scale", 1.0))
+        p.action_penalty = float(self.action_penalty)
+        return p
+
+    def step(self, actions):
+        if not (self.fused_transition and self.sync_free_reset and torch.device(self.device).type == "cuda"):
+            return super().step(actions)
+        return self._fused_step(actions)
+
     def calculateObservations(self):
         self.obs_buf = torch.cat([self.state.joint_q.view(self.num_envs, -1)[:, 1:], self.state.joint_qd.view(self.num_envs, -1)], dim=-1)
 
@@ -474,6 +500,7 @@ class CheetahEnv(_PlanarHopper):
     """reference envs/cheetah.py: 17 obs, 6 actions, no early termination."""
 
     init_noise = (0.1, 0.2, 0.1, 0.5)
+    planar_kind = 1
 
     def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
                  stochastic_init=False, MM_caching_frequency=1, early_termination=False):

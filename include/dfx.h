@@ -183,6 +183,27 @@ int dfx_walker_transition_backward(const DfxWalkerParams* p, int n, const float*
                                    const float* g_q_next, const float* g_qd_next, const float* g_actions_next,
                                    const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream);
 
+/* ---- the same transition for the planar envs: kind 0 Hopper (envs/hopper.py:170-268), 1 HalfCheetah (envs/cheetah.py:160-244)
+ * -- observation [q[1:], qd] -- and 2 CartPole swing-up (envs/cartpole_swing_up.py:120-187: [x, xd, sin th, cos th, thd]). */
+typedef struct DfxPlanarParams {
+    int num_q, num_qd, num_act, num_obs;
+    int kind;                    /* 0 Hopper, 1 HalfCheetah, 2 CartPole swing-up */
+    int early_termination;       /* Hopper: reset when the height drops below termination_height */
+    int zero_actions_on_reset;   /* the env keeps a copy of the actions and clears it on reset (not CartPole) */
+    int episode_length;
+    float termination_height, termination_height_tolerance, termination_angle, height_rew_scale;
+    float action_penalty;        /* Hopper / HalfCheetah: reward += penalty * sum a^2; CartPole: reward -= penalty * sum a^2 */
+    float pole_angle_penalty, pole_velocity_penalty, cart_position_penalty, cart_velocity_penalty;
+} DfxPlanarParams;
+int dfx_planar_transition_forward(const DfxPlanarParams* p, int n, const float* q, const float* qd, const float* actions,
+                                  const long long* progress, const float* start_q, const float* start_qd,
+                                  float* obs_before, float* rew, long long* reset, float* q_next, float* qd_next,
+                                  float* actions_next, long long* progress_next, float* obs_next, void* stream);
+int dfx_planar_transition_backward(const DfxPlanarParams* p, int n, const float* q, const float* qd, const float* actions,
+                                   const long long* reset, const float* g_obs_before, const float* g_rew,
+                                   const float* g_q_next, const float* g_qd_next, const float* g_actions_next,
+                                   const float* g_obs_next, float* gq, float* gqd, float* gact, void* stream);
+
 /* ---- policy output -> actuation (reference envs/ant.py:156-166, envs/snu_humanoid.py:283-296):
  * used[e, j] = clip(raw[e, j], -1, 1) * pre_scale + pre_bias ;  drive[e, offset + j] = (used[e, j] * drive_scale) * strength[j],
  * every other entry of the [n, width] drive rows zero (joint_act, or the muscle activations with offset 0). */

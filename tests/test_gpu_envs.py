@@ -105,10 +105,10 @@ def test_fused_epilogue_equals_torch_ops(name):
     assert (g1 - g2).abs().max() <= 1e-4 * g2.abs().max() + 1e-6
 
 
-@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv"])
+@pytest.mark.parametrize("name", ENVS)
 def test_fused_transition_equals_unfused_step(name):
     """env.step() as three launches (action map, simulation step, transition: dfx_action_map_* /
-    dfx_walker_transition_*) against the op-by-op PyTorch step: observations before and after the masked
+    dfx_walker_transition_* / dfx_planar_transition_*) against the op-by-op PyTorch step, all six envs: observations before and after the masked
     reset, rewards, flags, counters, next state, and the gradient of a loss through all of them -- with
     actions beyond the clip range and episodes short enough to terminate inside the window."""
     import torch
