@@ -169,7 +169,10 @@ def test_masked_reset_equals_indexed_reset(name):
         assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[3], b[3], atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "HopperEnv"])
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "HopperEnv", "CheetahEnv",
+                                  pytest.param("CartPoleSwingUpEnv", marks=pytest.mark.xfail(
+                                      reason="capture of the CartPole rollout has been seen invalidated (DESIGN.md section 7)",
+                                      strict=False))])
 def test_graphed_rollout_equals_eager(name):
     """One CUDA graph for horizon env-steps + backward reproduces the eager rollout (loss, action gradients,
     final state) and chains across calls."""
@@ -178,7 +181,7 @@ def test_graphed_rollout_equals_eager(name):
     from diffrl_b200.rollout import GraphedRollout
     n, T = 48, 6
     g = torch.Generator().manual_seed(2)
-    num_act = {"AntEnv": 8, "HumanoidEnv": 21, "HopperEnv": 3, "CartPoleSwingUpEnv": 1}[name]
+    num_act = {"AntEnv": 8, "HumanoidEnv": 21, "HopperEnv": 3, "CheetahEnv": 6, "CartPoleSwingUpEnv": 1}[name]
     acts = [torch.rand((T, n, num_act), generator=g) * 2 - 1 for _ in range(2)]
 
     def make():
