@@ -91,6 +91,19 @@ class GraphedRollout:
         self.final_actions = env.actions.detach()
         self.host_grad.copy_(self.actions.grad, non_blocking=True)
         self.host_loss.copy_(self.loss, non_blocking=True)
+        # leave nothing on the env that keeps this body's autograd graph alive: the next body (the captured one after
+        # the warm-ups) must build a fresh AccumulateGrad node for self.actions on ITS stream -- a stale node makes the
+        # engine synchronise with the warm-up stream, which invalidates a capture
+        env.state.joint_q, env.state.joint_qd = self.final_q, self.final_qd
+        env.actions = self.final_actions
+        env.obs_buf, env.rew_buf = env.obs_buf.detach(), env.rew_buf.detach()
+        env.extras = {}
+        musc = getattr(env.model, "muscle_activation", None)
+        if musc is not None and musc.requires_grad:
+            env.model.muscle_activation = musc.detach()
+        if hasattr(env, "obs_buf_before_reset"):
+            env.obs_buf_before_reset = env.obs_buf_before_reset.detach()
+        del loss, rew_all, obs_l, rew_l, done_l
 
     def __call__(self, host_actions=None, sync=True):
         """Replay the captured rollout.  ``host_actions``: [T, N, A] tensor, copied into the pinned staging buffer
