@@ -88,4 +88,25 @@ int emu_step_backward(const EmuPack* p, int n, int substeps, int mm_freq, double
     return 0;
 }
 
+// ---- the fixed-point scatter-add of dfx_phases.h in isolation (tests/test_fixed_point.py): n contributions
+// vals[k] are scattered in the order perm[k] into ONE accumulator with `scale`; returns the low / high words,
+// the read-back value and whether the poison bit was raised
+int emu_fx_accumulate(const float* vals, const int* perm, int n, float scale, int* lo_out, int* hi_out, float* value) {
+    float lo_f[DFX_ES] = {0.0f};           // one strided slot each, as in the kernels (the low word lives in an fp32 array)
+    float hi_f[DFX_ES] = {0.0f};
+    float poison_f[DFX_ES] = {0.0f};
+    const SP lo{lo_f}, hi{hi_f}, poison{poison_f};
+    GroupSerial g{0};
+    for (int k = 0; k < n; ++k) {
+        const float w[1] = {vals[perm[k]]};
+        fx_scatter(sp_int(lo), sp_int(hi), sp_uint(poison), 0, w, scale, g);
+    }
+    *lo_out = sp_int(lo)[0];
+    *hi_out = sp_int(hi)[0];
+    *value = fx_value(*lo_out, *hi_out, 1.0f / scale);
+    return (int)(sp_uint(poison)[0] & 1u);
+}
+
+float emu_fx_pow2_scale(float m) { return fx_pow2_scale(m); }
+
 }  // extern "C"
