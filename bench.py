@@ -375,11 +375,21 @@ def run_ours(args):
     b_fwd, b_bwd = algorithmic_bytes(Q, D, A, S, row=row, nseg=(S + mm - 1) // mm)
     s_fwd, s_bwd = algorithmic_bytes(Q, D, A, S)
     achieved = N * b_bwd / (bwd_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, fp32 = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(env_name, {}).get("bwd_dram_bytes_per_launch")
+            prof = json.load(f).get(env_name, {})
+        traffic = prof.get("bwd_dram_bytes_per_launch")
+        if "bwd_fp32_flop_per_launch" in prof and N == 4096:
+            # SURVEY.md 8d's second yardstick: fp32 FLOP actually executed (counted by ncu for this launch shape) per
+            # second against the CUDA-core peak 148 SMs x 128 lanes x 2 FLOP x the SM clock sampled during the run
+            flop = prof["fwd_fp32_flop_per_launch"] + prof["bwd_fp32_flop_per_launch"]
+            mhz = clocks.summary().get("sm_mhz") or 1965.0
+            peak = 148 * 128 * 2 * mhz * 1e6
+            fp32 = {"achieved_tflops": flop / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "peak_tflops": peak / 1e12,
+                    "frac": flop / ((fwd_ms + bwd_ms) * 1e-3) / peak, "flop_per_env_step": flop / N,
+                    "source": "profiles/r01_traffic.json (ncu instruction counts)"}
     cpu = cpu_reference_arm(env_name) if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": "differentiable env-steps/s (fwd+bwd)", "value": value, "unit": "env-steps/s", "n_gpus": world,
@@ -403,6 +413,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": N * b_bwd,
                      "survey_8d_state_only_bytes_per_launch": N * s_bwd,
                      "forward_kernel": {"achieved": N * b_fwd / (fwd_ms * 1e-3) / 1e9, "algorithmic_bytes_per_launch": N * b_fwd},
+                     "fp32": fp32,
                      "note": "algorithmic bytes = this design's tape rows (q, qd + forward intermediates, 4*row B per env-substep) "
                              "+ H^-1 blocks + state I/O; the fused path is FP32-issue/latency bound, not HBM bound "
                              "(profiles/r01_ant_full.md, DESIGN.md section 3); launch durations are averages over the timed rollouts"},
