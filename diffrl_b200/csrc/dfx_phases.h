@@ -1,6 +1,9 @@
 // dfx_phases.h -- the phases of one semi-implicit substep of the articulated rigid-body
-// simulator and their hand-derived adjoints, written once for a cooperative "group" of G lanes
-// that owns one environment whose working set lives in a scratch block (shared memory on the GPU).
+// simulator and their hand-derived adjoints, written once against two abstractions: the group policy `Grp`
+// (which items of a loop this thread takes, what a barrier is, how tape blocks move) and the scratch pointer `SP`
+// (dfx_math.h: an environment's working set, contiguous or strided).  Instantiated by the tile kernels
+// (dfx_tile.cu: lane = environment, warp = item), the lane-group kernels (dfx_kernels.cu: lanes = items of one
+// environment) and the host emulation (tests/host_emu).
 //
 // What is computed follows the reference step (NVlabs/DiffRL dflex/dflex/sim.py:2316-2601):
 //   kin_*         eval_rigid_fk :1681 + the velocity half of eval_rigid_id :1716-1763
@@ -14,11 +17,13 @@
 // HOW it is computed is different by design: the joint-space inertia H = J^T M J is accumulated
 // with the composite-rigid-body recursion instead of two dense GEMMs, the 6x6 world inertia
 // T^T I T is never formed per substep (it is applied in factored form), q'' = H^-1 tau uses an explicitly formed
-// H^-1 (one mat-vec per substep instead of two triangular sweeps), scatter-adds are replaced by
-// deterministic gathers, and nothing but (q, qd) per substep is taped: the adjoint recomputes
-// the substep in scratch memory.
+// H^-1 (one mat-vec per substep instead of two triangular sweeps), scatter-adds are order-independent
+// fixed-point integer adds in shared memory, and each substep tapes the block [q .. q''] of its scratch (the
+// entering state AND the forward intermediates): the adjoint reads it back instead of re-running the forward.
 //
-// `Grp` provides: static G, lane, sync(), cta_tasks(), cta_compact(), fx_add(int*, int), atomic_add(float*, float), group_max(float, SP slot), atomic_or(unsigned*, unsigned).
+// `Grp` provides: static G, lane, kPathPasses, kConcurrentItems, sync(), cta_tasks(), cta_compact(), cta_compact_with(),
+// fx_add(int*, int), atomic_add(float*, float), atomic_or(unsigned*, unsigned), group_max(float, SP slot),
+// block_in() / row_in() / block_out() / copy_wait_first() / copy_wait_all() for the tape.
 #pragma once
 
 #include "dfx_math.h"

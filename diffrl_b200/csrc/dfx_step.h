@@ -1,12 +1,14 @@
 // dfx_step.h -- one environment's whole env-step (all substeps) forward and backward, for a
-// cooperative group owning the environment's scratch block.  Shared verbatim by the CUDA
-// kernels (dfx_kernels.cu) and the host emulation used by CPU-side unit tests.
+// group policy owning the environment's scratch.  Shared verbatim by the tile kernels (dfx_tile.cu), the
+// lane-group kernels (dfx_kernels.cu) and the host emulation used by CPU-side unit tests.
 //
-// Tape (written by forward when taping, read by backward), all fp32:
-//   [substep][env][tape_row]  per substep: the (q, qd) ENTERING it and the forward intermediates the adjoint
-//                             needs -- X_sc, X_sm, S, v, a, total link wrenches, q'' (32 L + 8 D + Q floats)
-//   [segment][env][D * D]     H^-1 of each mass-matrix update
-// The path is FP32-issue bound with HBM idle, so the adjoint trades bandwidth for instructions: it reads these
+// Tape (written by forward when taping, read by backward), all fp32, one block per substep / per update:
+//   rows   per substep: the (q, qd) ENTERING it and the forward intermediates the adjoint
+//          needs -- X_sc, X_sm, S, v, a, total link wrenches, q'' (32 L + 8 D + Q floats, padded to 4)
+//   H^-1   D * D floats per mass-matrix update
+// laid out [block][env][n] (lane-group kernels, host) or [block][tile of 32 envs][n][32] (tile kernels): the
+// group policy's block_in / row_in / block_out hide the difference.
+// The path is issue / latency bound with HBM idle, so the adjoint trades bandwidth for instructions: it reads these
 // rows back (coalesced, tile-contiguous per substep) instead of re-running the forward dynamics.  Ant: 1.7 KB
 // per env-substep vs the reference's ~3.7 KB (it keeps every State tensor alive).
 #pragma once
