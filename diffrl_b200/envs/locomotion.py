@@ -319,8 +319,11 @@ class CartPoleSwingUpEnv(DFlexEnv):
         self.sim_dt, self.ground = self.dt, False
         self.num_joint_q = self.num_joint_qd = 2
         self._build_model("CartPoleSwingUpEnv")
-        self.start_joint_q = self.state.joint_q.clone()
-        self.start_joint_qd = self.state.joint_qd.clone()
+        # constants: detached (the reference clones the grad-requiring State tensors, cartpole_swing_up.py:74-75, which ties
+        # every reset to the autograd leaf of the construction-time state -- on the default stream, so that a rollout
+        # containing it cannot be captured into a CUDA graph)
+        self.start_joint_q = self.state.joint_q.detach().clone()
+        self.start_joint_qd = self.state.joint_qd.detach().clone()
         self.action_strength = 1000.0
         self.pole_angle_penalty, self.pole_velocity_penalty = 1.0, 0.1
         self.cart_position_penalty, self.cart_velocity_penalty, self.cart_action_penalty = 0.05, 0.1, 0.0

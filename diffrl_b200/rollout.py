@@ -9,8 +9,9 @@ the actions and the device->host copies of the loss and the action gradients, an
     roll = GraphedRollout(env, horizon=32)
     loss, grad_actions = roll(host_actions)        # host_actions: pinned [horizon, num_envs, num_actions]
 
-Capture is exercised for the walker envs and the planar Hopper / HalfCheetah; CartPoleSwingUpEnv's capture is known to
-be invalidated (open issue) -- use its eager ``step`` loop.
+Capture is exercised for all six envs (tests/test_gpu_envs.py).  Anything the rollout touches must be free of autograd
+leaves created on another stream (e.g. a grad-requiring reset state): the engine would synchronise with that stream
+and invalidate the capture.
 
 Each call starts from the env's current state (``env.state.joint_q/qd``, ``progress_buf``, last actions)
 and leaves the env at the end of the rollout with the graph cut (as ``env.clear_grad()`` would), so

@@ -169,10 +169,7 @@ def test_masked_reset_equals_indexed_reset(name):
         assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[3], b[3], atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "HopperEnv", "CheetahEnv",
-                                  pytest.param("CartPoleSwingUpEnv", marks=pytest.mark.xfail(
-                                      reason="capture of the CartPole rollout has been seen invalidated (DESIGN.md section 7)",
-                                      strict=False))])
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "HopperEnv", "CheetahEnv", "CartPoleSwingUpEnv"])
 def test_graphed_rollout_equals_eager(name):
     """One CUDA graph for horizon env-steps + backward reproduces the eager rollout (loss, action gradients,
     final state) and chains across calls."""
