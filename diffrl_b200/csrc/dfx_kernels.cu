@@ -133,6 +133,14 @@ struct GroupCuda {
             for (int i = lane; i < n; i += G_) dst[i] = src[i];
         }
     }
+    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, const float* src, int n, int head, bool first) const {
+        (void)head;
+        if (!first) block_out(base, b, N, env, src, n, true);     // no asynchronous stores here: the whole row at once
+    }
+    __device__ __forceinline__ void row_reusable() const {}
+    __device__ __forceinline__ void finish() const {}
+    static constexpr bool kBulkRows = false;
+    __device__ __forceinline__ HinvView hinv_view(const float* base, long long b, int N, int env, int n) const { return HinvView{base + (b * N + env) * n, 1}; }
     // (rows are 60-120 B here and the head is not 16-byte aligned: one part, issued with the first call)
     __device__ __forceinline__ void row_in(float* dst, const float* base, long long b, int N, int env, int n, int head, int tail, bool first) const {
         (void)head; (void)tail;
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
 using namespace dfx;
 
 struct dfx_pack {
-    bool tile;       // stepped by the 32-environment tile kernels (dfx_tile.cu); fixes the tape layout
+    int tile;        // 0: lane-group kernels; E = 8 / 16 / 32: stepped by the E-environment tile kernels (dfx_tile.cu); fixes the tape layout
     PackHost host;
     int device;
     int* d_ints;
@@ -204,6 +212,16 @@ static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
 static int g_flags = 9;   // include/dfx.h dfx_set_flags: 2 phase barriers, 4 generic kernels, 8 CTA-wide task loops, 32 no tile kernels
+static int g_tile_envs = 0;   // dfx_set_tile_envs: 0 = the widest tile kernel that exists for the articulation
+
+static int tile_mode(int E, const Pack& h) {
+    switch (E) {
+        case 8: return dfx_tile_mode_e8(h.L, h.D, h.Q, h.C, h.M);
+        case 16: return dfx_tile_mode_e16(h.L, h.D, h.Q, h.C, h.M);
+        case 32: return dfx_tile_mode_e32(h.L, h.D, h.Q, h.C, h.M);
+    }
+    return -1;
+}
 
 static void set_err(char* err, int n, const std::string& m) {
     if (err && n > 0) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
@@ -214,6 +232,11 @@ extern "C" {
 const char* dfx_version(void) { return "diffrl_b200 dfx 0.1 (sm_100a)"; }
 long long dfx_launch_count(void) { return g_launches.load(); }
 int dfx_set_flags(int flags) { g_flags = flags; return 0; }
+int dfx_set_tile_envs(int envs) {
+    if (envs != 0 && envs != 8 && envs != 16 && envs != 32) return 1;
+    g_tile_envs = envs;
+    return 0;
+}
 int dfx_set_group_size(int lanes) {
     if (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32) return 1;
     g_group = lanes;
@@ -239,7 +262,15 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
     for (int i = 0; i < 17; ++i) { p->blob.int_off[i] = (int)p->host.int_off[i]; p->blob.float_off[i] = (int)p->host.float_off[i]; }
     // flag bit 5 (32) keeps a supported articulation on the lane-group kernels (A/B runs); fixed per pack because
     // the two kernel families lay the tape out differently
-    p->tile = !(g_flags & 32) && dfx_tile_supported(p->header.L, p->header.D, p->header.Q, p->header.C, p->header.M);
+    p->tile = 0;
+    if (!(g_flags & 32)) {
+        static const int kWidths[3] = {32, 16, 8};
+        for (int k = 0; k < 3 && !p->tile; ++k) {
+            const int E = kWidths[k];
+            if ((g_tile_envs == 0 || g_tile_envs == E) && tile_mode(E, p->header) >= 0) p->tile = E;
+        }
+    }
+    if (p->tile) p->host.set_layout_mode(tile_mode(p->tile, p->header));
     return p;
 }
 
@@ -258,10 +289,10 @@ int dfx_pack_query(const dfx_pack_t* p, int what) {
         case DFX_QUERY_CONTACTS: return p->header.C;
         case DFX_QUERY_MUSCLES: return p->header.M;
         case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
-        case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
+        case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout_bwd.bwd_size;
         case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
         case DFX_QUERY_TREE_DEPTH: return p->header.nlev;
-        case DFX_QUERY_TAPE_TILE: return p->tile ? 32 : 0;
+        case DFX_QUERY_TAPE_TILE: return p->tile;
     }
     return -1;
 }
@@ -272,8 +303,8 @@ int dfx_pack_set_gravity(dfx_pack_t* p, float gx, float gy, float gz, int ground
     return 0;
 }
 
-// environments as laid out in the tape: tile kernels pad to whole 32-environment tiles
-static int tape_envs(const dfx_pack* p, int n) { return p->tile ? ((n + 31) / 32) * 32 : n; }
+// environments as laid out in the tape: tile kernels pad to whole tiles
+static int tape_envs(const dfx_pack* p, int n) { return p->tile ? ((n + p->tile - 1) / p->tile) * p->tile : n; }
 
 long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq) {
     return tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).total;
@@ -292,7 +323,7 @@ static int cta_area(const dfx_pack* p, int envs_per_cta) {
 }
 static LaunchPlan plan_launch(const dfx_pack* p, int G, bool bwd) {
     LaunchPlan lp{};
-    const int per_env = bwd ? p->host.layout.bwd_size : p->host.layout.fwd_size;
+    const int per_env = bwd ? p->host.layout_bwd.bwd_size : p->host.layout.fwd_size;
     // multiple of 4 floats (16-byte cp.async rows) that is not a multiple of 32 (bank spreading between groups)
     lp.scratch_stride = (per_env + 3) & ~3;
     if (lp.scratch_stride % 32 == 0) lp.scratch_stride += 4;
@@ -321,7 +352,7 @@ static cudaError_t launch_impl(const dfx_pack* p, const StepArgs& step, cudaStre
     KernelArgs ka;
     ka.header = p->header;
     ka.blob = p->blob;
-    ka.layout = p->host.layout;
+    ka.layout = BWD ? p->host.layout_bwd : p->host.layout;
     ka.step = step;
     const LaunchPlan lp = plan_launch(p, G, BWD);
     ka.scratch_stride = lp.scratch_stride;
@@ -331,12 +362,9 @@ static cudaError_t launch_impl(const dfx_pack* p, const StepArgs& step, cudaStre
     if (envs_per_cta == 0) return cudaErrorInvalidConfiguration;
     const size_t smem = lp.smem;
     auto kern = dfx_step_kernel<G, BWD, SL, SD, SQ, SC, SM>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    // (the opt-in to > 48 KB of dynamic shared memory is per device: set it on every launch, it is cheap)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int grid = (step.N + envs_per_cta - 1) / envs_per_cta;
     kern<<<grid, envs_per_cta * G, smem, stream>>>(ka);
     g_launches.fetch_add(1);
@@ -370,9 +398,14 @@ static cudaError_t launch_tile(const dfx_pack* p, const StepArgs& step, bool bac
     ka.header = p->header;
     ka.blob = p->blob;
     ka.step = step;
-    cudaError_t e = dfx_tile_launch(ka, backward, stream);
+    int e = (int)cudaErrorInvalidConfiguration;
+    switch (p->tile) {
+        case 8: e = dfx_tile_launch_e8(&ka, backward, stream); break;
+        case 16: e = dfx_tile_launch_e16(&ka, backward, stream); break;
+        case 32: e = dfx_tile_launch_e32(&ka, backward, stream); break;
+    }
     g_launches.fetch_add(1);
-    return e;
+    return (cudaError_t)e;
 }
 
 static int pick_group(const dfx_pack* p) {
@@ -385,13 +418,13 @@ extern "C" {
 
 int dfx_launch_plan(const dfx_pack_t* p, int backward, int out[6]) {
     if (!p || !out) return (int)cudaErrorInvalidValue;
-    if (p->tile) {      // one CTA per SM: a tile of 32 environments, lane = environment
+    if (p->tile) {      // one CTA = a tile of E environments
         KernelArgs ka;
         ka.header = p->header;
         ka.blob = p->blob;
-        const size_t smem = dfx_tile_smem(ka, backward != 0);
-        const Layout& Y = p->host.layout;
-        out[0] = 32; out[1] = 32; out[2] = (int)((227 * 1024) / (smem + 1024)); out[3] = (int)smem;
+        const size_t smem = p->tile == 8 ? dfx_tile_smem_e8(&ka, backward) : p->tile == 16 ? dfx_tile_smem_e16(&ka, backward) : dfx_tile_smem_e32(&ka, backward);
+        const Layout& Y = backward ? p->host.layout_bwd : p->host.layout;
+        out[0] = 32; out[1] = p->tile; out[2] = (int)((227 * 1024) / (smem + 1024)); out[3] = (int)smem;
         out[4] = ((backward ? Y.bwd_size : Y.fwd_size) + 3) & ~3;
         out[5] = (int)smem - out[4] * 32 * 4;
         return 0;

@@ -51,9 +51,13 @@ struct KernelArgs {
 
 }  // namespace dfx
 
-// ---- tile kernels (dfx_tile.cu): one CTA = 32 environments, lane = environment, warp = link / dof / contact
-// true when a size-specialised tile kernel exists for this articulation
-bool dfx_tile_supported(int L, int D, int Q, int C, int M);
-// dynamic shared memory of the tile kernel (bytes): pack + task list + 32 x scratch
-size_t dfx_tile_smem(const dfx::KernelArgs& ka, bool backward);
-cudaError_t dfx_tile_launch(dfx::KernelArgs& ka, bool backward, cudaStream_t stream);
+// ---- tile kernels (dfx_tile.cu, compiled once per tile width E = 8, 16, 32 with its own namespace): one CTA = E
+// environments.  KernelArgs is a plain struct with the same layout in every build; it crosses as void*.
+#define DFX_DECLARE_TILE(E)                                                                                           \
+    int dfx_tile_mode_e##E(int L, int D, int Q, int C, int M);      /* layout mode, or -1: no kernel of this width */  \
+    size_t dfx_tile_smem_e##E(const void* kernel_args, int backward); /* dynamic shared memory (bytes) */             \
+    int dfx_tile_launch_e##E(void* kernel_args, int backward, void* stream);
+DFX_DECLARE_TILE(8)
+DFX_DECLARE_TILE(16)
+DFX_DECLARE_TILE(32)
+#undef DFX_DECLARE_TILE

@@ -65,14 +65,14 @@ struct Pack {
 };
 
 // Offsets (in floats) of the per-environment scratch block.  Forward kernels use [0, fwd_size),
-// backward kernels additionally [fwd_size, bwd_size).
+// backward kernels [0, bwd_size).  A field that a layout does not hold has offset -1.
 struct Layout {
     // primal
     int q, qd, act, musc, tau, qdd, Xl, vj;
     int Xsc, Xsm, S, v, a, f, ft;
     int cmask, fxs, fx, fxH;   // poison bits + int64 fixed-point accumulators of the deterministic scatter-adds
-    int A;     // H, then H^-1 (D,D)
-    int Lm;    // Cholesky factor (D,D); reused as adj_H in backward
+    int A;     // H, then H^-1 (D,D); -1: the adjoint reads H^-1 from the tape in global memory (kLayoutHinvGlobal)
+    int Lm;    // forward: Cholesky factor (D,D); backward: the symmetrised cotangent of H, packed upper triangle (D(D+1)/2)
     int Icmp;  // composite inertias (L,21) + F (D,6) during CRBA
     int fwd_size;
     int tape_row;  // floats of the contiguous [q, qd, X_sc, X_sm, S, v, a, f_tot, qdd] block
@@ -80,6 +80,7 @@ struct Layout {
     int aq, aqd, aqdd, aact, amusc;
     int aXsc, aXsm, aS, av, aa, af, aIbar /* (L,12): dL/dR (9) + dL/du (3) */, pX;
     int bwd_size;
+    int overlay;   // forward: the mass-matrix temporaries (Lm, Icmp) share the region of (Xl, vj, f, fx) -- see make_layout
 };
 
 #if defined(__CUDACC__)
@@ -88,8 +89,19 @@ struct Layout {
 #define DFX_LAYOUT_FN constexpr
 #endif
 DFX_LAYOUT_FN int dfx_round_up(int x, int m) { return (x + m - 1) / m * m; }
+DFX_LAYOUT_FN int dfx_max(int a, int b) { return a > b ? a : b; }
+DFX_LAYOUT_FN int dfx_sym_count(int D) { return D * (D + 1) / 2; }
 
-DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M) {
+// layout modes
+constexpr int kLayoutLegacy = 0;       // one layout for forward and backward (forward-only and adjoint-only fields share a region)
+constexpr int kLayoutCompact = 1;      // separate forward / backward layouts, sized for the large articulations (Humanoid, SNU):
+                                       //   forward : the mass-matrix temporaries (Lm, Icmp: live only inside crba_fwd + chol_inverse) OVERLAY
+                                       //             the per-substep temporaries (Xl, vj, f, fx: dead by then; fx is re-zeroed afterwards)
+                                       //   backward: no forward-only fields at all
+constexpr int kLayoutHinvGlobal = 2;   // backward: H^-1 is not staged in shared memory; solve_adj reads its rows from the tape (L2)
+
+DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M, int mode = kLayoutLegacy, bool bwd = false) {
+    (void)C;
     Layout y{};
     int o = 0;
 #define DFX_TAKE(n) (o += (n), o - (n))
@@ -101,22 +113,49 @@ DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M) {
     o = dfx_round_up(o, 4);          // rows are copied with 16-byte transactions
     y.tape_row = o;
     y.act = DFX_TAKE(D); y.musc = DFX_TAKE(M); y.tau = DFX_TAKE(D);
-    y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
-    y.A = DFX_TAKE(D * D); y.Lm = DFX_TAKE(D * D);
     y.cmask = DFX_TAKE(1);               // poison bits of the fixed-point scatter-adds (bit = body & 31)
     y.fxs = DFX_TAKE(1);                 // fixed-point scale of the cotangent scatter of the current substep
-    // ---- from here on the forward-only and the adjoint-only fields share the same region
-    const int shared_end = o;
-    y.Icmp = DFX_TAKE(L * 21 + D * 6);
-    y.f = DFX_TAKE(L * 6);
-    y.fx = DFX_TAKE(L * 12);             // fixed-point accumulators of the contact + muscle wrenches: (L,6) low words, (L,6) high words
-    y.fwd_size = o;
-    o = shared_end;
+    o = dfx_round_up(o, 4);              // (the H^-1 block is copied with 16-byte transactions in the tile kernels)
+    const int adj_floats = Q + 3 * D + M + L * (7 + 6 + 7 + 6 + 6 + 12 + 7) + D * 6 + (M > 0 ? L * 13 : 0);
+    if (!(mode & kLayoutCompact)) {
+        y.A = DFX_TAKE(D * D); y.Lm = DFX_TAKE(D * D);
+        y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6);   // kinematics temporaries (joint-local transform, joint velocity)
+        // ---- from here on the forward-only and the adjoint-only fields share the same region
+        const int shared_end = o;
+        y.Icmp = DFX_TAKE(L * 21 + D * 6);
+        y.f = DFX_TAKE(L * 6);
+        y.fx = DFX_TAKE(L * 12);             // fixed-point accumulators of the contact + muscle wrenches: (L,6) low words, (L,6) high words
+        y.fwd_size = o;
+        o = shared_end;
+        y.overlay = 0;
+    } else if (!bwd) {
+        y.A = DFX_TAKE(D * D);
+        const int u0 = o;
+        y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6); y.f = DFX_TAKE(L * 6); y.fx = DFX_TAKE(L * 12);
+        const int u1 = o;
+        o = u0;
+        y.Lm = DFX_TAKE(D * D); y.Icmp = DFX_TAKE(L * 21 + D * 6);
+        o = dfx_max(o, u1);
+        y.fwd_size = o;
+        y.overlay = 1;
+        // (adjoint fields: unused by the forward kernels; offsets past the end keep host-side sizing honest)
+        y.aq = y.aqd = y.aqdd = y.aact = y.amusc = y.aXsc = y.av = y.aXsm = y.aS = y.aa = y.af = y.aIbar = y.pX = y.fxH = -1;
+        y.bwd_size = o;
+        return y;
+    } else {
+        y.A = (mode & kLayoutHinvGlobal) ? -1 : DFX_TAKE(D * D);
+        y.Lm = DFX_TAKE(dfx_round_up(dfx_sym_count(D), 4));
+        y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6);
+        y.Icmp = y.f = y.fx = -1;
+        y.fwd_size = o + adj_floats;
+        y.overlay = 0;
+    }
     y.aq = DFX_TAKE(Q); y.aqd = DFX_TAKE(D); y.aqdd = DFX_TAKE(D); y.aact = DFX_TAKE(D); y.amusc = DFX_TAKE(M);
     y.aXsc = DFX_TAKE(L * 7); y.av = DFX_TAKE(L * 6); y.aXsm = DFX_TAKE(L * 7); y.aS = DFX_TAKE(D * 6); y.aa = DFX_TAKE(L * 6);
     y.af = DFX_TAKE(L * 6); y.aIbar = DFX_TAKE(L * 12); y.pX = DFX_TAKE(L * 7);
     y.fxH = DFX_TAKE(M > 0 ? L * 13 : 0);            // high words of the fixed-point cotangent scatter into aXsc (L,7) and av (L,6); the low words live in aXsc / av
     y.bwd_size = o;
+    (void)adj_floats;
 #undef DFX_TAKE
     return y;
 }

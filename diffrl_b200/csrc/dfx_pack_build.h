@@ -21,7 +21,14 @@ struct PackHost {
     // offsets into ints / floats, in the order of the pointer fields of Pack
     std::vector<size_t> int_off, float_off;
     Pack header;  // scalar fields filled; pointer fields filled by bind()
-    Layout layout;
+    Layout layout;       // forward kernels (legacy mode: also the backward kernels)
+    Layout layout_bwd;   // backward kernels
+    int layout_mode = kLayoutLegacy;
+    void set_layout_mode(int mode) {
+        layout_mode = mode;
+        layout = make_layout(header.L, header.D, header.Q, header.C, header.M, mode, false);
+        layout_bwd = make_layout(header.L, header.D, header.Q, header.C, header.M, mode, true);
+    }
 
     // point the Pack's pointer fields at (ibase, fbase)
     Pack bind(const int* ibase, const float* fbase) const {
@@ -194,7 +201,7 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
     push_f(vec(d.joint_armature, D));
     push_f(cpoint); push_f(cdist); push_f(cmat);
     push_f(vec(d.muscle_points, W * 3));
-    out.layout = make_layout(L, D, Q, C, M);
+    out.set_layout_mode(kLayoutLegacy);
     return true;
 }
 

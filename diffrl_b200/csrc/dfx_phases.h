@@ -31,6 +31,13 @@
 
 namespace dfx {
 
+// A view of H^-1: in the scratch (stride = the scratch element stride) or, when the layout does not stage it
+// (Y.A < 0), in the tape block in global memory (element stride hs)
+struct HinvView {
+    const float* g;   // global rows, or nullptr
+    int hs;
+};
+
 struct GroupSerial {  // host / single-lane execution
     static constexpr int G = 1;
 #ifndef DFX_EMU_PATH_PASSES
@@ -65,6 +72,17 @@ struct GroupSerial {  // host / single-lane execution
         float* d = base + (b * N + env) * n;
         for (int i = 0; i < n; ++i) d[i] = src[i];
     }
+    // a tape row in two stores: `first`: elements [0, head) -- the state entering the substep, known when it starts;
+    // then [head, n) once the substep's intermediates exist.  (Policies without asynchronous stores write the whole row
+    // with the second call.)
+    DFX_HD void block_out_part(float* base, long long b, int N, int env, SP src, int n, int head, bool first) const {
+        float* d = base + (b * N + env) * n;
+        if (first) { for (int i = 0; i < head; ++i) d[i] = src[i]; }
+        else { for (int i = head; i < n; ++i) d[i] = src[i]; }
+    }
+    DFX_HD void row_reusable() const {}        // every asynchronous store has finished READING the scratch
+    DFX_HD void finish() const {}
+    static constexpr bool kBulkRows = false;   // true: env_step_backward moves rows with rows_in() (TMA bulk copies)
     DFX_HD void block_in(SP dst, const float* base, long long b, int N, int env, int n, bool rows) const {
         (void)rows;
         const float* t = base + (b * N + env) * n;
@@ -75,6 +93,8 @@ struct GroupSerial {  // host / single-lane execution
         const float* t = base + (b * N + env) * n;
         for (int i = 0; i < n; ++i) if (((i < head) || (i >= tail)) == first) dst[i] = t[i];
     }
+    // where block b of environment env starts in a [b][env][n] tape, and its element stride
+    DFX_HD HinvView hinv_view(const float* base, long long b, int N, int env, int n) const { return HinvView{base + (b * N + env) * n, 1}; }
     DFX_HD void copy_wait_first() const {}     // all asynchronous copies but the most recent one have landed
     DFX_HD void copy_wait_all() const {}
 };
@@ -226,6 +246,7 @@ DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // 
 template <class Grp>
 DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
+    g.row_reusable();      // (K1 wrote temporaries only; from the next pass on the tape row of the previous substep is overwritten)
     g.sync();
     if constexpr (Grp::kPathPasses) {
         // every barrier is CTA-wide here: each link walks its own path from the root, three barriers in all
@@ -1061,30 +1082,46 @@ DFX_HD void solve_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     }
     g.sync();
 }
-// atau = H^-1 aqdd (written over tau);  aH -= atau (x) qdd   (aH lives in the Lm slot during backward)
+// the cotangent of H is kept SYMMETRISED and packed (upper triangle, row-major): only aH + aH^T enters crba_adj, because
+// every use of H there is through a symmetric bilinear form.  Hs[i][i] = aH[i][i], Hs[i][j] = aH[i][j] + aH[j][i] (i < j).
+DFX_HD int symD_idx(int D, int i, int j) { return i * D - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+
+// atau = H^-1 aqdd (written over tau);  Hs -= sym(atau (x) qdd)   (Hs lives in the Lm slot during backward)
 template <class Grp>
-DFX_HD void solve_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
+DFX_HD void solve_adj(const Pack& P, const Layout& Y, SP s, HinvView hv, const Grp& g) {
     const int D = P.D;
-    DFX_FOR(i, D) {
-        float acc = 0.0f;
-        for (int j = 0; j < D; ++j) acc += s[Y.A + i * D + j] * s[Y.aqdd + j];
-        s[Y.tau + i] = acc;
+    if (hv.g) {
+        DFX_FOR(i, D) {
+            const float* row = hv.g + (long long)i * D * hv.hs;
+            float acc = 0.0f;
+#pragma unroll 4
+            for (int j = 0; j < D; ++j) acc += row[(long long)j * hv.hs] * s[Y.aqdd + j];
+            s[Y.tau + i] = acc;
+        }
+    } else {
+        DFX_FOR(i, D) {
+            float acc = 0.0f;
+            for (int j = 0; j < D; ++j) acc += s[Y.A + i * D + j] * s[Y.aqdd + j];
+            s[Y.tau + i] = acc;
+        }
     }
     g.sync();
-    DFX_FOR(e, D * D) {
-        const int i = e / D, j = e - i * D;
-        s[Y.Lm + e] -= s[Y.tau + i] * s[Y.qdd + j];
+    DFX_FOR(i, D) {                 // row i of the packed triangle: entries (i, i..D-1)
+        const float ti = s[Y.tau + i], qi = s[Y.qdd + i];
+        const SP row = s + Y.Lm + symD_idx(D, i, i);
+        row[0] -= ti * qi;
+        for (int j = i + 1; j < D; ++j) row[j - i] -= ti * s[Y.qdd + j] + s[Y.tau + j] * qi;
     }
     g.sync();
 }
 
-// adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), aH in the Lm slot
+// adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), from the symmetrised cotangent Hs
 template <class Grp>
 DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D, L = P.L;
-    const SP aH = s + Y.Lm;
-    // body inertia parameters: for each link l and each ancestor dof a:  z = sum_b aH[a][b] S_b ;
-    // cotangent S_a on  I_l z
+    const SP Hs = s + Y.Lm;
+    // body inertia parameters: for each link l and each ancestor dof a:  z = sum_b c_ab S_b with c_aa = Hs_aa,
+    // c_ab = Hs_ab / 2 ; cotangent S_a on  I_l z   (sum_ab aH_ab Phi(S_a, S_b) with Phi symmetric)
     DFX_FOR(l, L) {
         const BodyInertia B = body_inertia(P, s + Y.Xsm + l * 7, l);
         M3 aR = m3_zero();
@@ -1095,7 +1132,8 @@ DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
             SV z = sv_zero();
             for (int kb = P.anc_start[l]; kb < P.anc_start[l + 1]; ++kb) {
                 const int b = P.anc_dofs[kb];
-                z += ld6(s + Y.S + b * 6) * aH[a * D + b];
+                const float c = (a == b) ? Hs[symD_idx(D, a, a)] : 0.5f * Hs[a < b ? symD_idx(D, a, b) : symD_idx(D, b, a)];
+                z += ld6(s + Y.S + b * 6) * c;
             }
             inertia_apply_adj(B, z, ld6(s + Y.S + a * 6), aR, au, dummy);
         }
@@ -1114,7 +1152,8 @@ DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
             SV y = sv_zero();
             for (int kb = P.anc_start[l]; kb < P.anc_start[l + 1]; ++kb) {
                 const int b = P.anc_dofs[kb];
-                y += ld6(s + Y.S + b * 6) * (aH[a * D + b] + aH[b * D + a]);
+                const float c = (a == b) ? 2.0f * Hs[symD_idx(D, a, a)] : Hs[a < b ? symD_idx(D, a, b) : symD_idx(D, b, a)];
+                y += ld6(s + Y.S + b * 6) * c;
             }
             acc += inertia_apply(B, y);
         }
@@ -1219,33 +1258,18 @@ DFX_HD void integrate_adj(const Pack& P, const Layout& Y, SP s, float dt, const 
 // =====================================================================================
 // one substep, forward and adjoint
 // =====================================================================================
-// forward dynamics up to q'' (everything the adjoint needs to re-create); scratch q, qd, act, musc set.
-template <class Grp>
-DFX_HD void substep_eval(const Pack& P, const Layout& Y, SP s, bool update_mass, const Grp& g) {
-    kin_fwd(P, Y, s, g);
-    body_and_contact_fwd(P, Y, s, g);
-    muscle_fwd(P, Y, s, g);
-    wrench_collect(P, Y, s, g);
-    tau_fwd(P, Y, s, g);
-    if (update_mass) {
-        crba_fwd(P, Y, s, g);
-        chol_inverse(P, Y, s, g);
-    }
-    solve_fwd(P, Y, s, g);
-}
-
 // adjoint of one substep.  Pre: scratch [q .. qdd] = the substep's taped block (entering q, qd and the
 // forward intermediates), act, musc, A = H^-1 of the segment; aq, aqd = cotangents of the substep output.  Post: aq, aqd = cotangents of the substep input;
 // aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
 template <class Grp>
-DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool apply_crba, const Grp& g) {
+DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool apply_crba, HinvView hv, const Grp& g) {
     zero_range(s + Y.aXsc, Y.af - Y.aXsc, g);      // aXsc, av, aXsm, aS, aa are adjacent (af is overwritten by tau_adj)
     zero_range(s + Y.aIbar, P.L * 12, g);
     g.sync();
     // phase_sync(): CTA-wide barrier that keeps the warps of a CTA inside the same phase, so that the
     // instruction working set per SM is one or two phases (~10 KB each) instead of the whole 140 KB body
     integrate_adj(P, Y, s, dt, g);
-    solve_adj(P, Y, s, g);                  // tau slot <- atau
+    solve_adj(P, Y, s, hv, g);              // tau slot <- atau
     g.copy_wait_all();                      // the bulk of the tape row (transforms, S, v, a, wrenches) is needed from here on
     g.sync();
     if (apply_crba) crba_adj(P, Y, s, g);

@@ -34,9 +34,14 @@ struct StepArgs {
     int flags;   // bit 1: CTA-wide phase barriers
 };
 
+// derived State fields of the last substep (reference model.py:375-388); `late` = the ones that exist only after the solve
 template <class Grp>
-DFX_HD void dump_derived(const Pack& P, const Layout& Y, SP s, const DfxDerived& d, int env, const Grp& g) {
+DFX_HD void dump_derived(const Pack& P, const Layout& Y, SP s, const DfxDerived& d, int env, bool late, const Grp& g) {
     const int L = P.L, D = P.D;
+    if (late) {
+        if (d.joint_qdd) DFX_FOR(i, D) d.joint_qdd[(long long)env * D + i] = s[Y.qdd + i];
+        return;
+    }
     if (d.body_X_sc) DFX_FOR(i, L * 7) d.body_X_sc[(long long)env * L * 7 + i] = s[Y.Xsc + i];
     if (d.body_X_sm) DFX_FOR(i, L * 7) d.body_X_sm[(long long)env * L * 7 + i] = s[Y.Xsm + i];
     if (d.joint_S_s) DFX_FOR(i, D * 6) d.joint_S_s[(long long)env * D * 6 + i] = s[Y.S + i];
@@ -45,7 +50,6 @@ DFX_HD void dump_derived(const Pack& P, const Layout& Y, SP s, const DfxDerived&
     if (d.body_f_s) DFX_FOR(i, L * 6) d.body_f_s[(long long)env * L * 6 + i] = s[Y.f + i];
     if (d.body_ft_s) DFX_FOR(i, L * 6) d.body_ft_s[(long long)env * L * 6 + i] = s[Y.ft + i] - s[Y.f + i];
     if (d.joint_tau) DFX_FOR(i, D) d.joint_tau[(long long)env * D + i] = s[Y.tau + i];
-    if (d.joint_qdd) DFX_FOR(i, D) d.joint_qdd[(long long)env * D + i] = s[Y.qdd + i];
 }
 
 template <class Grp>
@@ -60,6 +64,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
+        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, QD, Q + D, true);    // (q, qd) ENTERING this substep
         kin_fwd(P, Y, s, g);
         g.phase_sync();
         body_and_contact_fwd(P, Y, s, g);
@@ -68,17 +73,23 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
         g.phase_sync();
         tau_fwd(P, Y, s, g);
         g.phase_sync();
+        if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, false, g);
         if (upd) {
+            if (Y.overlay) g.sync();               // (Lm, Icmp) overlay (Xl, vj, f, fx): every reader of those is done
             crba_fwd(P, Y, s, g);
             if (a.has_derived && a.derived.H) DFX_FOR(e, DD) a.derived.H[(long long)env * DD + e] = s[Y.A + e];
             g.sync();
             chol_inverse(P, Y, s, g);
             if (a.has_derived && a.derived.L) DFX_FOR(e, DD) a.derived.L[(long long)env * DD + e] = s[Y.Lm + e];
             if (a.tape) g.block_out(a.tape + a.hinv_base, sub / a.mm_freq, a.N, env, s + Y.A, DD, false);
+            if (Y.overlay) {                       // the fixed-point accumulators must read zero again
+                g.sync();
+                DFX_FOR(i, P.L * 12) s[Y.fx + i] = 0.0f;
+            }
         }
         solve_fwd(P, Y, s, g);
-        if (a.tape) g.block_out(a.tape, sub, a.N, env, s + Y.q, QD, true);   // q, qd still hold the values that ENTERED this substep
-        if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, g);
+        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, QD, Q + D, false);   // the forward intermediates and q''
+        if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, true, g);
         g.phase_sync();   // (also orders the tape / dump copies above before integrate_fwd overwrites q, qd)
         g.sync();
         integrate_fwd(P, Y, s, a.dt_sub, g);
@@ -102,15 +113,21 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g
         const bool seg_last = (sub == a.substeps - 1) || ((sub + 1) % a.mm_freq == 0);   // first visited of its segment
         // the row arrives in two asynchronous parts: (q, qd, q'') -- all that the first two adjoint phases read -- then
         // the rest, which substep_adj() waits for only before the phases that need it
-        g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, true);
-        if (seg_last) {
-            g.block_in(s + Y.A, a.tape_in + a.hinv_base, seg, a.N, env, DD, false);
-            DFX_FOR(e, DD) s[Y.Lm + e] = 0.0f;
+        if constexpr (Grp::kBulkRows) {
+            const bool want_hinv = seg_last && Y.A >= 0;
+            g.rows_in(s + Y.q, a.tape_in, sub, QD, Q + D, Y.qdd - Y.q, s + (want_hinv ? Y.A : 0),
+                      want_hinv ? g.block_ptr(a.tape_in + a.hinv_base, seg, DD) : nullptr, DD);
+        } else {
+            g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, true);
+            if (seg_last && Y.A >= 0) g.block_in(s + Y.A, a.tape_in + a.hinv_base, seg, a.N, env, DD, false);
         }
-        g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, false);
+        if (seg_last) DFX_FOR(e, dfx_sym_count(D)) s[Y.Lm + e] = 0.0f;      // symmetrised cotangent of H (packed)
+        // layouts that do not stage H^-1 read its rows from the tape block in place (L2)
+        const HinvView hv = (Y.A >= 0) ? HinvView{nullptr, 0} : g.hinv_view(a.tape_in + a.hinv_base, seg, a.N, env, DD);
+        if constexpr (!Grp::kBulkRows) g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, false);
         g.copy_wait_first();
         g.sync();
-        substep_adj(P, Y, s, a.dt_sub, sub == s0, g);
+        substep_adj(P, Y, s, a.dt_sub, sub == s0, hv, g);
     }
     if (a.gq) DFX_FOR(i, Q) a.gq[(long long)env * Q + i] = s[Y.aq + i];
     if (a.gqd) DFX_FOR(i, D) a.gqd[(long long)env * D + i] = s[Y.aqd + i];

@@ -101,7 +101,7 @@ enum {
     DFX_QUERY_BWD_SCRATCH_FLOATS = 6, /* shared-memory floats per environment, backward */
     DFX_QUERY_TREE_DEPTH = 7,
     DFX_QUERY_TAPE_ROW_FLOATS = 8,    /* floats per (substep, environment) tape row */
-    DFX_QUERY_TAPE_TILE = 9           /* 0: tape blocks are [block][env][n]; 32: [block][tile of 32 envs][n][32] (tile kernels) */
+    DFX_QUERY_TAPE_TILE = 9           /* 0: tape blocks are [block][env][n]; E = 8 / 16 / 32: [block][tile of E envs][n][E] (tile kernels) */
 };
 
 /* Build the device-resident pack for CUDA device `device` (>= 0).  Returns NULL on failure and
@@ -218,9 +218,13 @@ int dfx_set_group_size(int lanes);
 /* Tuning flags (default 9; for A/B timing and tests).  Lane-group kernels: bit 1 (2) = extra CTA-wide barriers between
  * phases (instruction-cache locality; no longer a gain now that the task loops synchronise the CTA anyway); bit 2 (4) =
  * generic kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases.
- * Bit 5 (32), read when a pack is CREATED: keep an articulation that has a 32-environment tile kernel on the
+ * Bit 5 (32), read when a pack is CREATED: keep an articulation that has a tile kernel on the
  * lane-group kernels (the two families lay the tape out differently, DFX_QUERY_TAPE_TILE). */
 int dfx_set_flags(int flags);
+/* Tile width knob, read when a pack is CREATED: 0 (default) = the widest tile kernel that exists for the articulation
+ * (32 environments per CTA for Ant / Hopper / HalfCheetah / CartPole, 8 for the two humanoids); 8, 16 or 32 = only a
+ * kernel of that width (an articulation without one falls back to the lane-group kernels).  For A/B timing and tests. */
+int dfx_set_tile_envs(int envs);
 /* Launch geometry the step kernel would use for this pack (host arithmetic, no GPU needed):
  * out[0] lanes per environment, out[1] environments per CTA, out[2] CTAs per SM (shared-memory / register bound),
  * out[3] dynamic shared memory per CTA in bytes, out[4] scratch floats per environment, out[5] bytes of the staged pack + CTA task list. */

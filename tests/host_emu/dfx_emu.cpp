@@ -5,6 +5,7 @@
 // arithmetic and the hand-derived adjoints can be checked against the reference's golden
 // vectors in a container that has no GPU.  It is test infrastructure: nothing in the product
 // (diffrl_b200/) loads it, and the product fails loudly when the CUDA library is missing.
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +30,9 @@ EmuPack* emu_pack_create(const DfxModelDesc* desc, char* err, int err_len) {
         return nullptr;
     }
     p->pack = p->host.bind(p->host.ints.data(), p->host.floats.data());
+#ifdef DFX_EMU_LAYOUT_MODE
+    p->host.set_layout_mode(DFX_EMU_LAYOUT_MODE);     // the compact layouts of the large-articulation tile kernels
+#endif
     return p;
 }
 void emu_pack_destroy(EmuPack* p) { delete p; }
@@ -40,7 +44,7 @@ int emu_pack_query(const EmuPack* p, int what) {
         case DFX_QUERY_CONTACTS: return p->pack.C;
         case DFX_QUERY_MUSCLES: return p->pack.M;
         case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
-        case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout.bwd_size;
+        case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout_bwd.bwd_size;
         case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
         case DFX_QUERY_TREE_DEPTH: return p->pack.nlev;
     }
@@ -65,7 +69,8 @@ int emu_step_forward(const EmuPack* p, int n, int substeps, int mm_freq, double 
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
     a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
-    std::vector<float> scratch((size_t)(p->host.layout.bwd_size + 16) * DFX_ES, 0.0f);
+    // (filled with NaN: a field the layout overlays or drops must never be read before it is written)
+    std::vector<float> scratch((size_t)(p->host.layout.fwd_size + 16) * DFX_ES, nanf(""));
     GroupSerial g{0};
     for (int env = 0; env < n; ++env) env_step_forward(p->pack, p->host.layout, SP{scratch.data()}, g, env, a);
     return 0;
@@ -82,9 +87,9 @@ int emu_step_backward(const EmuPack* p, int n, int substeps, int mm_freq, double
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
     a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
-    std::vector<float> scratch((size_t)(p->host.layout.bwd_size + 16) * DFX_ES, 0.0f);
+    std::vector<float> scratch((size_t)(p->host.layout_bwd.bwd_size + 16) * DFX_ES, nanf(""));
     GroupSerial g{0};
-    for (int env = 0; env < n; ++env) env_step_backward(p->pack, p->host.layout, SP{scratch.data()}, g, env, a);
+    for (int env = 0; env < n; ++env) env_step_backward(p->pack, p->host.layout_bwd, SP{scratch.data()}, g, env, a);
     return 0;
 }
 
