@@ -426,7 +426,7 @@ int dfx_launch_plan(const dfx_pack_t* p, int backward, int out[6]) {
         const Layout& Y = backward ? p->host.layout_bwd : p->host.layout;
         out[0] = 32; out[1] = p->tile; out[2] = (int)((227 * 1024) / (smem + 1024)); out[3] = (int)smem;
         out[4] = ((backward ? Y.bwd_size : Y.fwd_size) + 3) & ~3;
-        out[5] = (int)smem - out[4] * 32 * 4;
+        out[5] = (int)smem - out[4] * p->tile * 4;
         return 0;
     }
     const int G = pick_group(p);

@@ -307,6 +307,15 @@ using namespace dfx;
     X(4, 4, 4, true, 3, 9, 14, 15, 25, 0)     /* Ant, four CTAs per SM */
 #endif
 
+// alternative instantiations, picked by flag bit 6 (64) of dfx_set_flags (A/B timing): level-by-level tree recursions
+#if DFX_TILE_E == 8
+#define DFX_TILE_MODELS_ALT(X)                                    \
+    X(8, 8, 2, false, 3, 22, 27, 28, 35, 0)    /* Humanoid */     \
+    X(8, 8, 2, false, 3, 11, 24, 29, 88, 152)  /* SNU humanoid */
+#else
+#define DFX_TILE_MODELS_ALT(X)
+#endif
+
 #define DFX_CAT2(a, b) a##b
 #define DFX_CAT(a, b) DFX_CAT2(a, b)
 #define DFX_TILE_FN(name) DFX_CAT(DFX_CAT(name, _e), DFX_TILE_E)
@@ -336,6 +345,7 @@ int DFX_TILE_FN(dfx_tile_launch)(void* kargs, int backward, void* stream) {
     if (h.L == l && h.D == d && h.Q == q && h.C == c && h.M == m)                                      \
         return (int)(backward ? tile_launch_impl<nwb, minb, true, path, mode, l, d, q, c, m>(ka, st)   \
                               : tile_launch_impl<nwf, minb, false, path, mode, l, d, q, c, m>(ka, st));
+    if (ka.step.flags & 64) { DFX_TILE_MODELS_ALT(X) }
     DFX_TILE_MODELS(X)
 #undef X
     return (int)cudaErrorInvalidConfiguration;

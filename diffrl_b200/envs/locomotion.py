@@ -201,7 +201,7 @@ class HumanoidEnv(_FreeRootWalker):
 
     nan_guard = True
     target_x = 200.0
-    height_mode, check_invalid = 1, True
+    height_mode, check_invalid, zero_reward_on_invalid = 1, True, True      # reference envs/humanoid.py:359-369
     MOTOR_STRENGTHS = [200, 200, 200, 200, 200, 600, 400, 100, 100, 200, 200, 600, 400, 100, 100, 100, 100, 200, 100, 100, 200]
 
     def __init__(self, render=False, device="cuda:0", num_envs=4096, seed=0, episode_length=1000, no_grad=True,
@@ -245,7 +245,9 @@ class HumanoidEnv(_FreeRootWalker):
             torch.sum(self.actions ** 2, dim=-1) * self.action_penalty
         self.reset_buf = torch.where(o[:, 0] < self.termination_height, torch.ones_like(self.reset_buf), self.reset_buf)
         self.reset_buf = torch.where(self.progress_buf > self.episode_length - 1, torch.ones_like(self.reset_buf), self.reset_buf)
-        self.reset_buf = torch.where(self._invalid_state_mask(), torch.ones_like(self.reset_buf), self.reset_buf)
+        invalid = self._invalid_state_mask()
+        self.reset_buf = torch.where(invalid, torch.ones_like(self.reset_buf), self.reset_buf)
+        self.rew_buf[invalid] = 0.0          # reference envs/humanoid.py:369: a NaN / Inf state must not poison the loss
 
 
 class SNUHumanoidEnv(_FreeRootWalker):

@@ -64,6 +64,15 @@ class GraphedRollout:
             if gc_was_enabled:
                 gc.enable()
         torch.cuda.synchronize(dev)
+        # The captured body ended by pointing the env at `final_*` tensors of the graph's private pool, and capture runs
+        # no kernels: those were never written.  Put the env back where it was when the rollout was built, so that the
+        # first roll(actions) really "starts from the env's current state" (q0 / qd0 / progress0 / prev_actions still
+        # hold it: the warm-up bodies only read them).
+        env.state = env.model.state()
+        env.state.joint_q, env.state.joint_qd = self.q0.clone(), self.qd0.clone()
+        env.progress_buf, env.actions = self.progress0.clone(), self.prev_actions.clone()
+        with torch.no_grad():
+            env.calculateObservations()
 
     def _body(self):
         env = self.env

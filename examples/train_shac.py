@@ -32,12 +32,13 @@ import diffrl_b200.envs as envs  # noqa: E402
 from diffrl_b200.parallel import allreduce_gradients, allreduce_moments  # noqa: E402
 
 MM = {"AntEnv": 16, "HumanoidEnv": 48, "SNUHumanoidEnv": 8, "CartPoleSwingUpEnv": 4, "HopperEnv": 16, "CheetahEnv": 16}
-PRESETS = {   # examples/cfg/shac/*.yaml of the reference
-    "AntEnv": dict(actor=[128, 64, 32], critic=[64, 64], lr=2e-3, alpha=0.2, betas=(0.7, 0.95), epochs=2000, num_envs=64),
-    "HumanoidEnv": dict(actor=[256, 128], critic=[128, 128], lr=2e-3, alpha=0.995, betas=(0.7, 0.95), epochs=2000, num_envs=64),
-    "HopperEnv": dict(actor=[128, 64, 32], critic=[64, 64], lr=2e-3, alpha=0.2, betas=(0.7, 0.95), epochs=2000, num_envs=256),
-    "CheetahEnv": dict(actor=[128, 64, 32], critic=[64, 64], lr=2e-3, alpha=0.2, betas=(0.7, 0.95), epochs=2000, num_envs=64),
-    "CartPoleSwingUpEnv": dict(actor=[64, 64], critic=[64, 64], lr=1e-2, alpha=0.2, betas=(0.7, 0.95), epochs=500, num_envs=64),
+PRESETS = {   # examples/cfg/shac/*.yaml of the reference (actor / critic learning rates are separate there)
+    "AntEnv": dict(actor=[128, 64, 32], critic=[64, 64], lr=2e-3, critic_lr=2e-3, alpha=0.2, betas=(0.7, 0.95), epochs=2000, num_envs=64),
+    "HumanoidEnv": dict(actor=[256, 128], critic=[128, 128], lr=2e-3, critic_lr=5e-4, alpha=0.995, betas=(0.7, 0.95), epochs=2000, num_envs=64),
+    "SNUHumanoidEnv": dict(actor=[512, 256], critic=[256, 256], lr=2e-3, critic_lr=5e-4, alpha=0.995, betas=(0.7, 0.95), epochs=2000, num_envs=64),
+    "HopperEnv": dict(actor=[128, 64, 32], critic=[64, 64], lr=2e-3, critic_lr=2e-4, alpha=0.2, betas=(0.7, 0.95), epochs=2000, num_envs=256),
+    "CheetahEnv": dict(actor=[128, 64, 32], critic=[64, 64], lr=2e-3, critic_lr=2e-3, alpha=0.2, betas=(0.7, 0.95), epochs=2000, num_envs=64),
+    "CartPoleSwingUpEnv": dict(actor=[64, 64], critic=[64, 64], lr=1e-2, critic_lr=1e-3, alpha=0.2, betas=(0.7, 0.95), epochs=500, num_envs=64),
 }
 
 
@@ -102,6 +103,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--log-interval", type=int, default=50)
     ap.add_argument("--out", default="")
+    ap.add_argument("--profile-epochs", type=int, default=0,
+                    help="time the phases of the last K epochs with CUDA events (eager mode): rollout forward, backward, the actor "
+                         "all-reduce, the critic phase and its 64 all-reduces; written to --out as 'epoch_split_ms'")
     ap.add_argument("--graph", type=int, default=-1,
                     help="1: capture one whole training iteration (rollout, backward, actor step, critic training) in ONE "
                          "CUDA graph and replay it per epoch; 0: eager; default: on for single-GPU runs")
@@ -131,9 +135,11 @@ def main():
     target_critic = copy.deepcopy(critic)
     torch.manual_seed(args.seed + 1000 * (rank + 1))   # different exploration noise / resets per rank
     use_graph = (world == 1) if args.graph < 0 else bool(args.graph)
-    lr0 = torch.tensor(cfg["lr"], device=dev) if use_graph else cfg["lr"]      # a tensor lr can change under a captured graph
-    a_opt = torch.optim.Adam(actor.parameters(), lr=lr0, betas=cfg["betas"], capturable=use_graph)
-    c_opt = torch.optim.Adam(critic.parameters(), lr=lr0.clone() if use_graph else lr0, betas=cfg["betas"], capturable=use_graph)
+    # (a tensor lr can change under a captured graph)
+    a_opt = torch.optim.Adam(actor.parameters(), lr=torch.tensor(cfg["lr"], device=dev) if use_graph else cfg["lr"],
+                             betas=cfg["betas"], capturable=use_graph)
+    c_opt = torch.optim.Adam(critic.parameters(), lr=torch.tensor(cfg["critic_lr"], device=dev) if use_graph else cfg["critic_lr"],
+                             betas=cfg["betas"], capturable=use_graph)
     obs_rms = RunningMeanStd((obs_dim,), dev)
 
     obs_buf = torch.zeros((T, n, obs_dim), device=dev)
@@ -149,8 +155,30 @@ def main():
              "progress": env.progress_buf.clone(), "actions": env.actions.detach().clone(),
              "ep_ret": torch.zeros(n, device=dev), "ep_len": torch.zeros(n, device=dev)}
 
+    class Split:
+        """CUDA-event stopwatch of the phases of an iteration: mark(name) closes the segment that started at the previous mark."""
+        def __init__(self):
+            self.on, self.marks, self.total, self.count = False, [], {}, 0
+
+        def mark(self, name):
+            if self.on:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                self.marks.append((name, ev))
+
+        def close(self):
+            if not self.on or not self.marks:
+                return
+            torch.cuda.synchronize()
+            for (_, e0), (name, e1) in zip(self.marks[:-1], self.marks[1:]):
+                self.total[name] = self.total.get(name, 0.0) + e0.elapsed_time(e1)
+            self.marks, self.count = [], self.count + 1
+
+    split = Split()
+
     def train_iteration():
         # ---------------------------------------------------------------- actor: short-horizon rollout
+        split.mark("start")
         a_opt.zero_grad(set_to_none=True)
         frozen = obs_rms.frozen()                         # normalise with the statistics entering the rollout
         env.state = env.model.state()                     # == env.initialize_trajectory() on the carried state
@@ -194,10 +222,14 @@ def main():
                 ep_ret = torch.where(done_b, torch.zeros_like(ep_ret), ep_ret)
                 ep_len_cnt = torch.where(done_b, torch.zeros_like(ep_len_cnt), ep_len_cnt)
         actor_loss = actor_loss / (T * n * world)          # global batch normalisation (reference shac.py:291)
+        split.mark("rollout_forward")
         actor_loss.backward()
+        split.mark("rollout_backward")
         allreduce_gradients(list(actor.parameters()), average=False)     # the one collective per rollout
+        split.mark("actor_allreduce")
         torch.nn.utils.clip_grad_norm_(actor.parameters(), 1.0)
         a_opt.step()
+        split.mark("actor_step")
         with torch.no_grad():
             actor_loss_s.copy_(actor_loss.detach())
             carry["q"].copy_(env.state.joint_q.detach().view(-1)); carry["qd"].copy_(env.state.joint_qd.detach().view(-1))
@@ -223,24 +255,29 @@ def main():
                 loss_c.backward()
                 for p in critic.parameters():
                     p.grad.nan_to_num_(0.0, 0.0, 0.0)
-                allreduce_gradients(list(critic.parameters()), average=True)
+                split.mark("critic_compute")
+                allreduce_gradients(list(critic.parameters()), average=True)      # 64 per epoch (reference shac.py:463-476), one flat buffer each
+                split.mark("critic_allreduce")
                 torch.nn.utils.clip_grad_norm_(critic.parameters(), 1.0)
                 c_opt.step()
         with torch.no_grad():
             for p, pt in zip(critic.parameters(), target_critic.parameters()):
                 pt.mul_(cfg["alpha"]).add_((1.0 - cfg["alpha"]) * p)
+        split.mark("critic_compute")
 
     graph, warm_epochs = None, 3
     for epoch in range(max_epochs):
-        lr = (1e-5 - cfg["lr"]) * epoch / max_epochs + cfg["lr"]
-        for opt in (a_opt, c_opt):
+        for opt, base in ((a_opt, cfg["lr"]), (c_opt, cfg["critic_lr"])):      # linear schedule, each from its own base (shac.py:420-431)
+            lr = (1e-5 - base) * epoch / max_epochs + base
             for group in opt.param_groups:
                 if use_graph:
                     group["lr"].fill_(lr)
                 else:
                     group["lr"] = lr
+        split.on = (not use_graph) and args.profile_epochs > 0 and epoch >= max_epochs - args.profile_epochs
         if not use_graph:
             train_iteration()
+            split.close()
         elif epoch < warm_epochs:         # warm-up on a side stream, as the capture will run on one
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -272,7 +309,14 @@ def main():
             fin_ret.zero_(); fin_cnt.zero_()
     if rank == 0 and args.out:
         with open(args.out, "w") as f:
-            json.dump({"env": args.env, "num_envs": total_envs, "world": world, "cuda_graph": bool(use_graph), "history": history}, f, indent=1)
+            rec = {"env": args.env, "num_envs": total_envs, "world": world, "cuda_graph": bool(use_graph), "history": history}
+            if split.count:
+                rec["epoch_split_ms"] = {k: v / split.count for k, v in split.total.items()}
+                rec["epoch_split_ms"]["epochs_timed"] = split.count
+                rec["epoch_split_note"] = ("rank 0, CUDA events: rollout_forward = %d x (policy + env.step + critic bootstrap), rollout_backward = "
+                                           "loss.backward(), actor_allreduce = the ONE policy-gradient all-reduce of the rollout, critic_allreduce = "
+                                           "sum of the 64 per-minibatch critic all-reduces" % T)
+            json.dump(rec, f, indent=1)
     if world > 1:
         torch.distributed.destroy_process_group()
 

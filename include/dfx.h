@@ -151,7 +151,7 @@ typedef struct DfxWalkerParams {
     int action_penalty_abs;     /* 0: sum a^2 ; 1: sum |a| (SNU) */
     int early_termination;      /* reset when h < termination_height */
     int check_invalid;          /* reset on NaN / Inf / |x| > 1e6 (Humanoid, SNU) */
-    int zero_reward_on_invalid; /* SNU */
+    int zero_reward_on_invalid; /* reward of an invalid environment is 0 (Humanoid: envs/humanoid.py:369, SNU: envs/snu_humanoid.py) */
     int episode_length;
     float joint_vel_scale, termination_height, termination_tolerance, height_rew_scale, action_penalty;
     float target[3];            /* targets + start_pos */
@@ -218,6 +218,7 @@ int dfx_set_group_size(int lanes);
 /* Tuning flags (default 9; for A/B timing and tests).  Lane-group kernels: bit 1 (2) = extra CTA-wide barriers between
  * phases (instruction-cache locality; no longer a gain now that the task loops synchronise the CTA anyway); bit 2 (4) =
  * generic kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases.
+ * Bit 6 (64): tile kernels of the large articulations use level-by-level tree recursions instead of path / subtree passes.
  * Bit 5 (32), read when a pack is CREATED: keep an articulation that has a tile kernel on the
  * lane-group kernels (the two families lay the tape out differently, DFX_QUERY_TAPE_TILE). */
 int dfx_set_flags(int flags);

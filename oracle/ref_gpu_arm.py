@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--rollouts", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--stamp", action="store_true", help="also report time.time() at the start / end of the timed rollouts (pool wall clock)")
     a = ap.parse_args()
     if not os.path.isdir(os.path.join(REF, "refdflex", "dflex")):
         print(json.dumps({"unavailable": "baseline/_ref missing: run `python oracle/install_reference.py` in the build container"}))
@@ -45,6 +46,9 @@ def main():
     sys.path[:0] = [os.path.join(HERE, "refshim"), os.path.join(REF, "refdflex"), REF]
     if a.device == "cpu":
         os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    # the reference caches its generated kernels by comparing source strings, and the source differs with / without the CUDA
+    # half: always generate both, so that the ONE prebuilt kernels.so (CPU + sm_100) is reused on every box and device
+    os.environ["DFLEX_FORCE_CUDA_BUILD"] = "1"
     import torch
     import dflex  # noqa: F401  (the reference's; loads its prebuilt kernels.so)
     assert os.path.realpath(dflex.__file__).startswith(os.path.realpath(REF)), dflex.__file__
@@ -82,16 +86,20 @@ def main():
     for _ in range(a.warmup):
         rollout()
     tf = tb = 0.0
+    t_start = time.time()
     for _ in range(a.rollouts):
         f, b, loss, gsum = rollout()
         tf += f
         tb += b
+    t_end = time.time()
     steps = a.num_envs * a.horizon * a.rollouts
     out = {"impl": "reference", "device": a.device, "env": a.env, "num_envs": a.num_envs, "horizon": a.horizon,
            "rollouts": a.rollouts, "forward_s": tf, "backward_s": tb, "env_steps_per_s": steps / (tf + tb),
            "loss": loss, "grad_abs_sum": gsum, "finite": bool(np.isfinite(loss) and np.isfinite(gsum)),
            "api": "reference envs.%s.step -> reference dflex.sim.SemiImplicitIntegrator (%s codegen kernels)" % (a.env, "CUDA sm_100" if cuda else "CPU"),
            "peak_mem_gb": (torch.cuda.max_memory_allocated() / 1e9) if cuda else None}
+    if a.stamp:
+        out["t_start"], out["t_end"] = t_start, t_end
     print(json.dumps(out))
 
 

@@ -1,0 +1,203 @@
+"""GPU parity at the sizes BASELINE.json names (C2 Humanoid 8192, C3 SNU 4096 x BPTT-128, C4 Ant 8192 per GPU), through the
+C ABI, against the CPU oracles -- plus the per-phase State fields of the GPU kernels against the reference goldens and
+fp64 finite differences of the adjoint for all six articulations.
+
+Element-wise tolerance: |a - b| <= rtol * |b| + atol_frac * max|b| per component, per environment; an
+environment may only fail when the test shows a switching surface (contact height, joint limit) within rounding
+distance for it (the reference's own branch would flip under the same perturbation).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from emu_util import EmuSim, load_golden
+from tolerances import GRAD_RTOL, fwd_rtol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+pytestmark = pytest.mark.gpu
+
+
+def _batch(name, N, seed, noise=(2e-3, 2e-2)):
+    d, model = load_golden(name)
+    from oracle import Oracle
+    n0 = int(d["meta/num_envs"])
+    o = Oracle.from_model(model, n0)
+    Q, D, M = o.desc.Q, o.desc.D, o.desc.M
+    rng = np.random.default_rng(seed)
+    p = "case%d/" % (int(d["meta/num_cases"]) - 1)
+    pick = rng.integers(0, n0, N)
+    q0 = (d[p + "q0"].reshape(n0, Q)[pick] + noise[0] * rng.standard_normal((N, Q))).astype(np.float32)
+    qd0 = (d[p + "qd0"].reshape(n0, D)[pick] + noise[1] * rng.standard_normal((N, D))).astype(np.float32)
+    act = (d[p + "act"].reshape(n0, D)[pick] * rng.uniform(0.5, 1.5, (N, D))).astype(np.float32)
+    musc = (d[p + "musc"].reshape(n0, M)[pick] * rng.uniform(0.5, 1.5, (N, M))).astype(np.float32) if M else None
+    cfg = dict(S=int(d["meta/substeps"]), mm=int(d["meta/mass_matrix_freq"]), dt=float(d["meta/dt"]))
+    return d, model, o, q0, qd0, act, musc, cfg
+
+
+def elementwise_bad_envs(a, b, width, rtol, atol_frac=1e-6):
+    """environments with a component outside |a - b| <= rtol |b| + atol_frac max|b| (+ rtol * per-env scale: components
+    that are differences of O(scale) terms carry the rounding of the scale, not of their own magnitude)"""
+    a = np.asarray(a, np.float64).reshape(-1, width); b = np.asarray(b, np.float64).reshape(-1, width)
+    scale = np.abs(b).max(axis=1, keepdims=True)
+    ok = np.abs(a - b) <= rtol * np.abs(b) + rtol * scale + atol_frac * np.abs(b).max()
+    return np.nonzero(~ok.all(axis=1))[0]
+
+
+@pytest.mark.parametrize("name,N", [("HumanoidEnv", 8192), ("SNUHumanoidEnv", 4096), ("AntEnv", 8192)])
+def test_cuda_matches_oracles_at_named_size(name, N):
+    """The whole batch is stepped on the GPU (forward + adjoint); a spread sample of 256 environments goes through the
+    C oracle (forward, bit-exact restatement of the reference) and the host emulation (adjoint)."""
+    import torch
+    from diffrl_b200.engine import ArticulationEngine
+    d, model, o, q0, qd0, act, musc, c = _batch(name, N, 31)
+    Q, D, M = o.desc.Q, o.desc.D, o.desc.M
+    eng = ArticulationEngine(o.desc, N, "cuda:0")
+    t = lambda a: None if a is None else torch.tensor(np.ascontiguousarray(a).ravel(), device="cuda:0")
+    rng = np.random.default_rng(4)
+    gq_out, gqd_out = rng.standard_normal((N, Q)).astype(np.float32), rng.standard_normal((N, D)).astype(np.float32)
+    q, qd, tape, _ = eng.forward(t(q0), t(qd0), t(act), t(musc), c["S"], c["mm"], c["dt"])
+    gq, gqd, gact, gm = eng.backward(t(act), t(musc), tape, t(gq_out), t(gqd_out), c["S"], c["mm"], c["dt"])
+    torch.cuda.synchronize()
+    assert all(bool(torch.isfinite(x).all()) for x in (q, qd, gq, gqd, gact))
+    sample = np.linspace(0, N - 1, 256).astype(np.int64)          # first, last and a spread of tiles
+    ms = None if musc is None else musc[sample]
+    oq, oqd = o.forward(q0[sample], qd0[sample], act[sample], ms, c["S"], c["mm"], c["dt"])
+    tol = fwd_rtol(name)
+    bad_q = elementwise_bad_envs(q.cpu().numpy().reshape(N, Q)[sample], oq, Q, tol)
+    bad_qd = elementwise_bad_envs(qd.cpu().numpy().reshape(N, D)[sample], oqd, D, tol)
+    bad = sorted(set(bad_q) | set(bad_qd))
+    # every failing environment must sit on a switching surface: perturbing ITS state by one ulp-scale step moves the
+    # oracle's own result by more than the tolerance as well
+    for e in bad:
+        i = sample[e]
+        q_p = q0[i:i + 1] * (1.0 + 2e-7)
+        oq_p, oqd_p = o.forward(q_p, qd0[i:i + 1], act[i:i + 1], None if musc is None else musc[i:i + 1], c["S"], c["mm"], c["dt"])
+        moved = max(np.abs(oq_p - oq.reshape(-1, Q)[e]).max() / np.abs(oq).max(), np.abs(oqd_p - oqd.reshape(-1, D)[e]).max() / np.abs(oqd).max())
+        assert moved > tol, (name, "env %d differs from the oracle but is not on a switching surface" % i, moved)
+    assert len(bad) <= 8, (name, len(bad))
+    # adjoint: host emulation of the same phase code (serial, contiguous scratch, level recursions) on the sample
+    emu = EmuSim(model, int(d["meta/num_envs"]))
+    emu.N = len(sample)
+    eq, eqd, etape, _ = emu.forward(q0[sample].ravel(), qd0[sample].ravel(), act[sample].ravel(), None if ms is None else ms.ravel(), c["S"], c["mm"], c["dt"])
+    egq, egqd, egact, egm = emu.backward(act[sample].ravel(), None if ms is None else ms.ravel(), etape, gq_out[sample].ravel(), gqd_out[sample].ravel(), c["S"], c["mm"], c["dt"])
+    good = np.setdiff1d(np.arange(len(sample)), bad)
+    for got, ref, w in ((gq, egq, Q), (gqd, egqd, D), (gact, egact, D)) + (((gm, egm, M),) if M else ()):
+        g = got.cpu().numpy().reshape(N, w)[sample][good]
+        r = ref.reshape(-1, w)[good]
+        nb = elementwise_bad_envs(g, r, w, 4 * GRAD_RTOL)
+        assert len(nb) <= 2, (name, w, len(nb), float(np.abs(g - r).max() / np.abs(r).max()))
+
+
+def test_snu_bptt128_rollout_matches_reference_kernels():
+    """C3's shape: a 128-env-step BPTT window of the muscle humanoid on 4 environments, the GPU kernels against the
+    reference's OWN generated CPU kernels (oracle/_ref/kernels.so through oracle/ref_driver.py).  Forward: every env-step
+    from the reference's state (the chaotic dynamics would amplify a 1e-7 rounding difference over 6144 substeps; the
+    per-step comparison is the one that can hold 1e-5-class tolerances), plus the free-running GPU trajectory for the
+    first steps.  Adjoint: the full 128-step chain of cotangents through both implementations' tapes."""
+    import torch
+    import ref_driver
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref/kernels.so not built (build container: python oracle/make_golden.py)")
+    from diffrl_b200.engine import ArticulationEngine
+    from diffrl_b200.modelpack import articulation_from_model
+    name, n, T = "SNUHumanoidEnv", 4, 128
+    d, model = load_golden(name)
+    arrays = dict(np.load(os.path.join(ROOT, "diffrl_b200", "assets", name + ".npz")))
+    S, mm, dt = int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    rm = ref_driver.RefModel(arrays, n, ground=True)
+    desc, _ = articulation_from_model(model, int(d["meta/num_envs"]))
+    eng = ArticulationEngine(desc, n, "cuda:0")
+    Q, D, M = desc.Q, desc.D, desc.M
+    g = torch.Generator().manual_seed(5)
+    q, qd = rm.m.joint_q.clone(), rm.m.joint_qd.clone()
+    act = torch.zeros(n * D)
+    cu = lambda x: x.to("cuda:0").contiguous()
+    ref_states, muscs, tapes_gpu = [], [], []
+    worst_step, free_q, free_qd = 0.0, cu(q), cu(qd)
+    tol = fwd_rtol(name)
+    free_err = []
+    for t in range(T):
+        musc = torch.rand(n * M, generator=g) * 40.0          # activation x strength range of the env (envs/snu_humanoid.py:283-296)
+        q_ref, qd_ref, _, _ = ref_driver.env_step(rm, q, qd, act, musc, dt, S, mm)
+        gq_, gqd_, tape, _ = eng.forward(cu(q), cu(qd), cu(act), cu(musc), S, mm, dt)        # from the REFERENCE's state
+        err = max(float((gq_.cpu() - q_ref).abs().max() / q_ref.abs().max()), float((gqd_.cpu() - qd_ref).abs().max() / (qd_ref.abs().max() + 1.0)))
+        worst_step = max(worst_step, err)
+        if t < 8:
+            free_q, free_qd, _, _ = eng.forward(free_q, free_qd, cu(act), cu(musc), S, mm, dt, want_tape=False)
+            free_err.append(float((free_q.cpu() - q_ref).abs().max() / q_ref.abs().max()))
+        ref_states.append((q, qd)); muscs.append(musc); tapes_gpu.append(tape)
+        q, qd = q_ref.detach(), qd_ref.detach()
+    assert worst_step < tol, worst_step
+    assert free_err[0] < tol and free_err[-1] < 1e-3, free_err        # free-running: bounded growth over the first 8 env-steps
+    # adjoint chain over the whole window (cotangent 1 on the final state)
+    gq_r, gqd_r = torch.ones(n * Q), torch.ones(n * D)
+    gq_g, gqd_g = cu(gq_r), cu(gqd_r)
+    worst_grad = 0.0
+    for t in reversed(range(T)):
+        q0, qd0 = ref_states[t]
+        _, _, grads, _ = ref_driver.env_step(rm, q0, qd0, act, muscs[t], dt, S, mm, gq_out=gq_r, gqd_out=gqd_r)
+        gq_r, gqd_r, _, gm_r = grads
+        gq_g, gqd_g, _, gm_g = eng.backward(cu(act), cu(muscs[t]), tapes_gpu[t], gq_g, gqd_g, S, mm, dt)
+        scale = float(max(gq_r.abs().max(), gqd_r.abs().max()))
+        if not np.isfinite(scale) or scale > 1e12:
+            break                                   # the reference's own cotangents overflowed fp32: nothing left to compare
+        worst_grad = max(worst_grad, float((gq_g.cpu() - gq_r).abs().max()) / scale, float((gqd_g.cpu() - gqd_r).abs().max()) / scale,
+                         float((gm_g.cpu() - gm_r).abs().max() / (gm_r.abs().max() + 1e-30)))
+        # re-synchronise the cotangents (the chain's own conditioning would otherwise dominate): per-step adjoint parity
+        gq_g, gqd_g = cu(gq_r), cu(gqd_r)
+    assert worst_grad < 4 * GRAD_RTOL, worst_grad
+
+
+@pytest.mark.parametrize("name", ["CartPoleSwingUpEnv", "AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "HopperEnv", "CheetahEnv"])
+def test_gpu_derived_state_matches_reference_goldens(name):
+    """Every per-phase State field the GPU kernels can dump (DfxDerived: X_sc ... H, L) against the reference's State
+    tensors of the first and of the last substep (tests/golden caseK/first|last/*)."""
+    import torch
+    from diffrl_b200.engine import ArticulationEngine
+    d, model = load_golden(name)
+    N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    eng = ArticulationEngine.from_model(model, "cuda:0", N)
+    t = lambda a: torch.tensor(a, device="cuda:0")
+    rel = lambda a, b: float(np.abs(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel()).max() / (np.abs(b).max() + 1e-30))
+    fields = ["body_X_sc", "body_X_sm", "joint_S_s", "body_v_s", "body_a_s", "body_f_s", "body_ft_s", "joint_tau", "joint_qdd"]
+    for k in range(int(d["meta/num_cases"])):
+        p = "case%d/" % k
+        musc = t(d[p + "musc"]) if (p + "musc") in d.files else None
+        # first substep: a 1-substep step of dt/S with a fresh mass matrix
+        _, _, _, dv = eng.forward(t(d[p + "q0"]), t(d[p + "qd0"]), t(d[p + "act"]), musc, 1, 1, dt / S, want_tape=False, derived=fields + ["H", "L"])
+        for f in fields[:-1] + ["H", "L"]:
+            assert rel(dv[f].cpu().numpy(), d[p + "first/" + f]) < 2e-5, (name, k, "first", f)
+        assert rel(dv["joint_qdd"].cpu().numpy(), d[p + "first/joint_qdd"]) < 2e-4, (name, k)      # conditioned by H
+        # last substep of the full env-step
+        _, _, _, dv = eng.forward(t(d[p + "q0"]), t(d[p + "qd0"]), t(d[p + "act"]), musc, S, mm, dt, want_tape=False, derived=fields)
+        for f in fields[:-1]:
+            assert rel(dv[f].cpu().numpy(), d[p + "last/" + f]) < 20 * fwd_rtol(name), (name, k, "last", f)
+
+
+@pytest.mark.parametrize("name", ["CartPoleSwingUpEnv", "AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "HopperEnv", "CheetahEnv"])
+def test_cuda_adjoint_matches_fp64_finite_differences_all_envs(name):
+    import torch
+    from diffrl_b200.engine import ArticulationEngine
+    N = 4
+    d, model, o, q0, qd0, act, musc, c = _batch(name, N, 9, noise=(1e-3, 1e-2))
+    Q, D, M = o.desc.Q, o.desc.D, o.desc.M
+    rng = np.random.default_rng(3)
+    gq_out, gqd_out = rng.standard_normal((N, Q)).astype(np.float32), rng.standard_normal((N, D)).astype(np.float32)
+    eng = ArticulationEngine(o.desc, N, "cuda:0")
+    t = lambda a: None if a is None else torch.tensor(a.ravel(), device="cuda:0")
+    _, _, tape, _ = eng.forward(t(q0), t(qd0), t(act), t(musc), c["S"], c["mm"], c["dt"])
+    gq, gqd, gact, gm = eng.backward(t(act), t(musc), tape, t(gq_out), t(gqd_out), c["S"], c["mm"], c["dt"])
+    errs = []
+    for e in range(N):
+        f = o.fd_gradient(q0[e], qd0[e], act[e], None if musc is None else musc[e], gq_out[e], gqd_out[e], c["S"], c["mm"], c["dt"])
+        scale = max(np.abs(f[0]).max(), np.abs(f[1]).max(), np.abs(f[2]).max())
+        err = max(np.abs(gq.cpu().numpy().reshape(N, Q)[e] - f[0]).max(), np.abs(gqd.cpu().numpy().reshape(N, D)[e] - f[1]).max(),
+                  np.abs(gact.cpu().numpy().reshape(N, D)[e] - f[2]).max()) / scale
+        if M:
+            err = max(err, np.abs(gm.cpu().numpy().reshape(N, M)[e] - f[3]).max() / (np.abs(f[3]).max() + 1e-30))
+        errs.append(err)
+    # fp32 adjoint vs fp64 central differences of a stiff contact model (48 substeps for the humanoids)
+    assert np.median(errs) < (1e-3 if name not in ("HumanoidEnv", "SNUHumanoidEnv") else 5e-3), (name, errs)

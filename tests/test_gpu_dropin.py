@@ -65,6 +65,7 @@ np.Inf = np.inf
 ROOT, REF = sys.argv[1], sys.argv[2]
 sys.path[:0] = [ROOT, ROOT + "/oracle/refshim", REF]
 import torch
+import torch_compat                                                         # oracle/refshim: torch >= 2 indexing compat, harness only
 import dflex
 assert dflex.__file__.startswith(ROOT + "/dflex"), dflex.__file__
 import algorithms.shac as shac                                              # the reference's trainer, unchanged

@@ -169,7 +169,7 @@ def test_masked_reset_equals_indexed_reset(name):
         assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[3], b[3], atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "HopperEnv", "CheetahEnv", "CartPoleSwingUpEnv"])
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "HopperEnv", "CheetahEnv", "CartPoleSwingUpEnv"])
 def test_graphed_rollout_equals_eager(name):
     """One CUDA graph for horizon env-steps + backward reproduces the eager rollout (loss, action gradients,
     final state) and chains across calls."""
@@ -178,7 +178,7 @@ def test_graphed_rollout_equals_eager(name):
     from diffrl_b200.rollout import GraphedRollout
     n, T = 48, 6
     g = torch.Generator().manual_seed(2)
-    num_act = {"AntEnv": 8, "HumanoidEnv": 21, "HopperEnv": 3, "CheetahEnv": 6, "CartPoleSwingUpEnv": 1}[name]
+    num_act = {"AntEnv": 8, "HumanoidEnv": 21, "SNUHumanoidEnv": 152, "HopperEnv": 3, "CheetahEnv": 6, "CartPoleSwingUpEnv": 1}[name]
     acts = [torch.rand((T, n, num_act), generator=g) * 2 - 1 for _ in range(2)]
 
     def make():
@@ -198,10 +198,31 @@ def test_graphed_rollout_equals_eager(name):
         loss.backward()
         eager.append((float(loss), a_dev.grad.cpu(), env.state.joint_q.detach().cpu().clone()))
     env2 = make()
-    roll = GraphedRollout(env2, T)
-    env2.clear_grad(); env2.reset(); env2.initialize_trajectory()       # capture warm-up advanced the env: restart
+    roll = GraphedRollout(env2, T)       # (leaves the env where it was: the first roll() starts from the reset state)
     for k, a in enumerate(acts):
         loss, grad = roll(a)
         assert abs(float(loss) - eager[k][0]) <= 1e-4 * abs(eager[k][0]) + 1e-3
         assert (grad - eager[k][1]).abs().max() <= 2e-4 * eager[k][1].abs().max() + 1e-6
         assert torch.allclose(env2.state.joint_q.cpu(), eager[k][2], rtol=1e-5, atol=1e-5)
+
+
+def test_humanoid_invalid_state_gives_zero_reward():
+    """reference envs/humanoid.py:359-369: an environment whose state went NaN / Inf / > 1e6 is reset AND its reward is
+    zeroed, so that sum(rew).backward() stays finite -- fused transition and op-by-op path alike."""
+    import torch
+    import diffrl_b200.envs as envs
+    for fused in (True, False):
+        env = envs.HumanoidEnv(num_envs=8, device="cuda:0", no_grad=False, MM_caching_frequency=48)
+        env.fused_transition = fused
+        env.fused_epilogue = fused
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        with torch.no_grad():
+            q = env.state.joint_q.clone()
+            q.view(8, -1)[3, 9] = float("nan")         # poison one joint angle of environment 3
+            env.state.joint_q = q
+        a = torch.zeros((8, env.num_actions), device="cuda:0", requires_grad=True)
+        obs, rew, done, _ = env.step(a)
+        assert bool(done[3]) and float(rew[3]) == 0.0, (fused, rew)
+        assert torch.isfinite(rew).all()
+        rew.sum().backward()
+        assert torch.isfinite(a.grad[torch.arange(8) != 3]).all()
