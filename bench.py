@@ -140,13 +140,14 @@ def _run_ref_arm(cmd, timeout):
 def cpu_reference_baseline(env_name):
     """The reference's CPU path through its stock API on ONE host core (it is a serial loop), bounded sample."""
     n, steps = CPU_SAMPLE[env_name]
-    r = _run_ref_arm(_ref_arm_cmd(env_name, n, steps * 2, 2, 1, "cpu"), 600)
+    steps = steps * 6          # ~10-20 s of single-core work over the two timed rollouts
+    r = _run_ref_arm(_ref_arm_cmd(env_name, n, steps, 2, 1, "cpu"), 900)
     if "unavailable" in r:
         return {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "reference", "sample": r["unavailable"]}
     return {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": 1, "kind": "reference",
             "sample": "%s: 2 rollouts of %d envs x %d env-steps (forward + sum(rew).backward()) through the UNMODIFIED reference's "
                       "envs.%s.step on its own generated CPU kernels, %.1f s; host has %d cores"
-                      % (env_name, n, steps * 2, env_name, r["forward_s"] + r["backward_s"], os.cpu_count()),
+                      % (env_name, n, steps, env_name, r["forward_s"] + r["backward_s"], os.cpu_count()),
             "seconds": r["forward_s"] + r["backward_s"], "api": r["api"]}
 
 

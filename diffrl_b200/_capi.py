@@ -39,6 +39,7 @@ def lib():
     L.dfx_set_group_size.argtypes = [ctypes.c_int]
     if hasattr(L, "dfx_set_tile_envs"):
         L.dfx_set_tile_envs.argtypes = [ctypes.c_int]
+        L.dfx_set_tape_dtype.argtypes = [ctypes.c_int]
     L.dfx_pack_create.restype = ctypes.c_void_p
     L.dfx_pack_create.argtypes = [ctypes.POINTER(DfxModelDesc), ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
     L.dfx_pack_destroy.argtypes = [ctypes.c_void_p]

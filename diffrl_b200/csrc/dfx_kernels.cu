@@ -133,10 +133,11 @@ struct GroupCuda {
             for (int i = lane; i < n; i += G_) dst[i] = src[i];
         }
     }
-    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, const float* src, int n, int head, bool first) const {
-        (void)head;
-        if (!first) block_out(base, b, N, env, src, n, true);     // no asynchronous stores here: the whole row at once
+    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, const float* src, const RowFmt& f, const float* stage, bool first) const {
+        (void)stage;
+        if (!first) block_out(base, b, N, env, src, f.n, true);     // no asynchronous stores here: the whole row at once (always fp32)
     }
+    __device__ __forceinline__ void row_unpack(float* dst, float* stage, const RowFmt& f) const { (void)dst; (void)stage; (void)f; }
     __device__ __forceinline__ void row_reusable() const {}
     __device__ __forceinline__ void finish() const {}
     static constexpr bool kBulkRows = false;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kMaxThreads) dfx_step_kernel(const __grid_cons
 using namespace dfx;
 
 struct dfx_pack {
+    int bf16;        // tape rows keep their middle (the forward intermediates) as bf16 -- tile kernels only
     int tile;        // 0: lane-group kernels; E = 8 / 16 / 32: stepped by the E-environment tile kernels (dfx_tile.cu); fixes the tape layout
     PackHost host;
     int device;
@@ -212,6 +214,7 @@ static std::atomic<long long> g_launches{0};
 long long dfx_count_launch(void) { return g_launches.fetch_add(1); }
 static int g_group = 0;
 static int g_flags = 9;   // include/dfx.h dfx_set_flags: 2 phase barriers, 4 generic kernels, 8 CTA-wide task loops, 32 no tile kernels
+static int g_tape_bf16 = 0;   // dfx_set_tape_dtype
 static int g_tile_envs = 0;   // dfx_set_tile_envs: 0 = the widest tile kernel that exists for the articulation
 
 static int tile_mode(int E, const Pack& h) {
@@ -232,6 +235,7 @@ extern "C" {
 const char* dfx_version(void) { return "diffrl_b200 dfx 0.1 (sm_100a)"; }
 long long dfx_launch_count(void) { return g_launches.load(); }
 int dfx_set_flags(int flags) { g_flags = flags; return 0; }
+int dfx_set_tape_dtype(int bf16) { g_tape_bf16 = bf16 ? 1 : 0; return 0; }
 int dfx_set_tile_envs(int envs) {
     if (envs != 0 && envs != 8 && envs != 16 && envs != 32) return 1;
     g_tile_envs = envs;
@@ -271,6 +275,7 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
         }
     }
     if (p->tile) p->host.set_layout_mode(tile_mode(p->tile, p->header));
+    p->bf16 = (p->tile && g_tape_bf16) ? 1 : 0;
     return p;
 }
 
@@ -291,8 +296,10 @@ int dfx_pack_query(const dfx_pack_t* p, int what) {
         case DFX_QUERY_FWD_SCRATCH_FLOATS: return p->host.layout.fwd_size;
         case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout_bwd.bwd_size;
         case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
+        case DFX_QUERY_TAPE_ROW_UNITS: return dfx_row_units(p->host.layout.tape_row, p->header.L, p->header.D, p->bf16 != 0);
         case DFX_QUERY_TREE_DEPTH: return p->header.nlev;
         case DFX_QUERY_TAPE_TILE: return p->tile;
+        case DFX_QUERY_TAPE_BF16: return p->bf16;
     }
     return -1;
 }
@@ -307,7 +314,7 @@ int dfx_pack_set_gravity(dfx_pack_t* p, float gx, float gy, float gz, int ground
 static int tape_envs(const dfx_pack* p, int n) { return p->tile ? ((n + p->tile - 1) / p->tile) * p->tile : n; }
 
 long long dfx_tape_floats(const dfx_pack_t* p, int n, int substeps, int mm_freq) {
-    return tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).total;
+    return tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq, p->bf16 != 0).total;
 }
 
 }  // extern "C"
@@ -447,7 +454,8 @@ int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, doub
     a.dt_sub = (float)(dt / (double)substeps);
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
-    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq, p->bf16 != 0).hinv_base;
+    a.tape_bf16 = p->bf16;
     a.flags = g_flags;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->tile) return (int)launch_tile(p, a, false, st);
@@ -470,7 +478,8 @@ int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, dou
     a.dt_sub = (float)(dt / (double)substeps);
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
-    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq).hinv_base;
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq, p->bf16 != 0).hinv_base;
+    a.tape_bf16 = p->bf16;
     a.flags = g_flags;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->tile) return (int)launch_tile(p, a, true, st);

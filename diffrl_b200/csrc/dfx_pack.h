@@ -81,6 +81,7 @@ struct Layout {
     int aXsc, aXsm, aS, av, aa, af, aIbar /* (L,12): dL/dR (9) + dL/du (3) */, pX;
     int bwd_size;
     int overlay;   // forward: the mass-matrix temporaries (Lm, Icmp) share the region of (Xl, vj, f, fx) -- see make_layout
+    int stage;     // staging area of the bf16 tape (tile kernels): (tail - head) / 2 floats that are dead while a row is in flight
 };
 
 #if defined(__CUDACC__)
@@ -91,6 +92,14 @@ struct Layout {
 DFX_LAYOUT_FN int dfx_round_up(int x, int m) { return (x + m - 1) / m * m; }
 DFX_LAYOUT_FN int dfx_max(int a, int b) { return a > b ? a : b; }
 DFX_LAYOUT_FN int dfx_sym_count(int D) { return D * (D + 1) / 2; }
+// a tape row is [q, qd, X_sc, X_sm, S | v, a, f_tot | q'', padding]; with a bf16 tape the middle -- link velocities, bias
+// accelerations and total link wrenches: quantities that enter the adjoint as multipliers -- is stored as bf16.  The state,
+// q'' and everything that carries POSITIONS stay fp32: the link transforms (contact depths are millimetres of metre-sized
+// positions) and the motion subspace S (its linear part is p x w) -- measured on the host emulation, rounding S alone costs
+// 1-3 % of the state gradients, rounding (v, a, f_tot) 0.1-0.7 %
+DFX_LAYOUT_FN int dfx_row_middle(int L, int D) { (void)D; return L * 18; }      // v, a, f_tot (L,6 each)
+// floats (4-byte units) one row occupies in the tape
+DFX_LAYOUT_FN int dfx_row_units(int tape_row, int L, int D, bool bf16) { return bf16 ? tape_row - dfx_row_middle(L, D) / 2 : tape_row; }
 
 // layout modes
 constexpr int kLayoutLegacy = 0;       // one layout for forward and backward (forward-only and adjoint-only fields share a region)
@@ -128,11 +137,14 @@ DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M, int mode = k
         y.fwd_size = o;
         o = shared_end;
         y.overlay = 0;
+        // bf16 staging: forward kernels stage in Icmp (live only inside crba_fwd), backward kernels in (Xl, vj, pX, af)
+        y.stage = bwd ? y.Xl : y.Icmp;
     } else if (!bwd) {
         y.A = DFX_TAKE(D * D);
         const int u0 = o;
         y.Xl = DFX_TAKE(L * 7); y.vj = DFX_TAKE(L * 6); y.f = DFX_TAKE(L * 6); y.fx = DFX_TAKE(L * 12);
-        const int u1 = o;
+        y.stage = dfx_round_up(o, 4);        // past fx (which must keep reading zero), inside the region of (Lm, Icmp)
+        const int u1 = y.stage + dfx_row_middle(L, D) / 2;
         o = u0;
         y.Lm = DFX_TAKE(D * D); y.Icmp = DFX_TAKE(L * 21 + D * 6);
         o = dfx_max(o, u1);
@@ -149,10 +161,14 @@ DFX_LAYOUT_FN Layout make_layout(int L, int D, int Q, int C, int M, int mode = k
         y.Icmp = y.f = y.fx = -1;
         y.fwd_size = o + adj_floats;
         y.overlay = 0;
+        y.stage = y.Xl;
     }
+    // (Xl, vj, pX, af) are contiguous: all four are dead from the moment a substep's adjoint starts until its tape row has
+    // landed -- the staging area of the bf16 tape (26 L >= 16 L + 3 D floats for every tree)
+    y.pX = DFX_TAKE(L * 7); y.af = DFX_TAKE(L * 6);
     y.aq = DFX_TAKE(Q); y.aqd = DFX_TAKE(D); y.aqdd = DFX_TAKE(D); y.aact = DFX_TAKE(D); y.amusc = DFX_TAKE(M);
     y.aXsc = DFX_TAKE(L * 7); y.av = DFX_TAKE(L * 6); y.aXsm = DFX_TAKE(L * 7); y.aS = DFX_TAKE(D * 6); y.aa = DFX_TAKE(L * 6);
-    y.af = DFX_TAKE(L * 6); y.aIbar = DFX_TAKE(L * 12); y.pX = DFX_TAKE(L * 7);
+    y.aIbar = DFX_TAKE(L * 12);
     y.fxH = DFX_TAKE(M > 0 ? L * 13 : 0);            // high words of the fixed-point cotangent scatter into aXsc (L,7) and av (L,6); the low words live in aXsc / av
     y.bwd_size = o;
     (void)adj_floats;

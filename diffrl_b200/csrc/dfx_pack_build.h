@@ -211,9 +211,9 @@ struct TapeGeom {
     long long hinv_base;  // float offset of the H^-1 blocks
     long long total;
 };
-inline TapeGeom tape_geom(int L, int Q, int D, int N, int substeps, int mm_freq) {
+inline TapeGeom tape_geom(int L, int Q, int D, int N, int substeps, int mm_freq, bool bf16 = false) {
     TapeGeom t;
-    t.N = N; t.S = substeps; t.QD = make_layout(L, D, Q, 0, 0).tape_row; t.DD = D * D;
+    t.N = N; t.S = substeps; t.QD = dfx_row_units(make_layout(L, D, Q, 0, 0).tape_row, L, D, bf16); t.DD = D * D;
     t.nseg = (substeps + mm_freq - 1) / mm_freq;
     t.hinv_base = (long long)substeps * N * t.QD;
     t.total = t.hinv_base + (long long)t.nseg * N * t.DD;

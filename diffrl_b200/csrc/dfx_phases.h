@@ -26,6 +26,8 @@
 // block_in() / row_in() / block_out() / copy_wait_first() / copy_wait_all() for the tape.
 #pragma once
 
+#include <string.h>
+
 #include "dfx_math.h"
 #include "dfx_pack.h"
 
@@ -37,6 +39,37 @@ struct HinvView {
     const float* g;   // global rows, or nullptr
     int hs;
 };
+
+// Geometry of a tape row of n scratch floats: [0, early) = (q, qd), known when the substep starts and all that the first two
+// adjoint phases need (with q''); [early, tail) = the forward intermediates; [tail, n) = q'' + padding.  With a bf16 tape the
+// sub-range [head, tail) = (v, a, f_tot) is stored as bf16 ([early, head) = the link transforms and S stay fp32); otherwise
+// head == early.  `units` = 4-byte units the row occupies in the tape: n, or n - (tail - head) / 2.
+struct RowFmt {
+    int n, early, head, tail, units;
+    bool bf16;
+};
+DFX_HD RowFmt row_fmt(const Pack& P, const Layout& Y, bool bf16) {
+    const int early = P.Q + P.D;
+    return RowFmt{Y.tape_row, early, bf16 ? Y.v - Y.q : early, Y.qdd - Y.q, dfx_row_units(Y.tape_row, P.L, P.D, bf16), bf16};
+}
+// fp32 -> bf16 -> fp32 (round to nearest even), what a bf16 tape does to a value
+DFX_HD float bf16_round(float x) {
+    unsigned u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(x);
+#else
+    memcpy(&u, &x, 4);
+#endif
+    if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);     // (NaN / Inf keep their payload)
+    u &= 0xffff0000u;
+    float r;
+#if defined(__CUDA_ARCH__)
+    r = __uint_as_float(u);
+#else
+    memcpy(&r, &u, 4);
+#endif
+    return r;
+}
 
 struct GroupSerial {  // host / single-lane execution
     static constexpr int G = 1;
@@ -75,11 +108,15 @@ struct GroupSerial {  // host / single-lane execution
     // a tape row in two stores: `first`: elements [0, head) -- the state entering the substep, known when it starts;
     // then [head, n) once the substep's intermediates exist.  (Policies without asynchronous stores write the whole row
     // with the second call.)
-    DFX_HD void block_out_part(float* base, long long b, int N, int env, SP src, int n, int head, bool first) const {
-        float* d = base + (b * N + env) * n;
-        if (first) { for (int i = 0; i < head; ++i) d[i] = src[i]; }
-        else { for (int i = head; i < n; ++i) d[i] = src[i]; }
+    // (the host emulation keeps the fp32 tape layout and only ROUNDS the middle through bf16 when f.bf16 is set: the
+    //  same values the tile kernels read back from a bf16 tape)
+    DFX_HD void block_out_part(float* base, long long b, int N, int env, SP src, const RowFmt& f, SP stage, bool first) const {
+        (void)stage;
+        float* d = base + (b * N + env) * f.n;
+        if (first) { for (int i = 0; i < f.early; ++i) d[i] = src[i]; }
+        else { for (int i = f.early; i < f.n; ++i) d[i] = (f.bf16 && i >= f.head && i < f.tail) ? bf16_round(src[i]) : src[i]; }
     }
+    DFX_HD void row_unpack(SP dst, SP stage, const RowFmt& f) const { (void)dst; (void)stage; (void)f; }
     DFX_HD void row_reusable() const {}        // every asynchronous store has finished READING the scratch
     DFX_HD void finish() const {}
     static constexpr bool kBulkRows = false;   // true: env_step_backward moves rows with rows_in() (TMA bulk copies)
@@ -1262,8 +1299,8 @@ DFX_HD void integrate_adj(const Pack& P, const Layout& Y, SP s, float dt, const 
 // forward intermediates), act, musc, A = H^-1 of the segment; aq, aqd = cotangents of the substep output.  Post: aq, aqd = cotangents of the substep input;
 // aact, amusc, aH (Lm slot) accumulated.  `apply_crba` is set on the substep that built H.
 template <class Grp>
-DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool apply_crba, HinvView hv, const Grp& g) {
-    zero_range(s + Y.aXsc, Y.af - Y.aXsc, g);      // aXsc, av, aXsm, aS, aa are adjacent (af is overwritten by tau_adj)
+DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool apply_crba, HinvView hv, const RowFmt& rf, const Grp& g) {
+    zero_range(s + Y.aXsc, P.L * 32 + P.D * 6, g);      // aXsc, av, aXsm, aS, aa are adjacent (af is overwritten by tau_adj)
     zero_range(s + Y.aIbar, P.L * 12, g);
     g.sync();
     // phase_sync(): CTA-wide barrier that keeps the warps of a CTA inside the same phase, so that the
@@ -1271,6 +1308,7 @@ DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool app
     integrate_adj(P, Y, s, dt, g);
     solve_adj(P, Y, s, hv, g);              // tau slot <- atau
     g.copy_wait_all();                      // the bulk of the tape row (transforms, S, v, a, wrenches) is needed from here on
+    g.row_unpack(s + Y.q, s + Y.stage, rf); // (bf16 tape: the staged halves become the fp32 scratch fields)
     g.sync();
     if (apply_crba) crba_adj(P, Y, s, g);
     tau_adj(P, Y, s, s + Y.tau, g);

@@ -32,6 +32,7 @@ struct StepArgs {
     float* gq; float* gqd; float* gact; float* gmusc;
     long long hinv_base;
     int flags;   // bit 1: CTA-wide phase barriers
+    int tape_bf16;   // the middle of every tape row (the forward intermediates) is stored as bf16 (tile kernels)
 };
 
 // derived State fields of the last substep (reference model.py:375-388); `late` = the ones that exist only after the solve
@@ -54,7 +55,8 @@ DFX_HD void dump_derived(const Pack& P, const Layout& Y, SP s, const DfxDerived&
 
 template <class Grp>
 DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a) {
-    const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
+    const int Q = P.Q, D = P.D, M = P.M, DD = D * D;
+    const RowFmt rf = row_fmt(P, Y, a.tape_bf16 != 0);
     DFX_FOR(i, Q) s[Y.q + i] = a.q[(long long)env * Q + i];
     DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
     DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
@@ -64,7 +66,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
-        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, QD, Q + D, true);    // (q, qd) ENTERING this substep
+        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, rf, s + Y.stage, true);    // (q, qd) ENTERING this substep
         kin_fwd(P, Y, s, g);
         g.phase_sync();
         body_and_contact_fwd(P, Y, s, g);
@@ -88,7 +90,7 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
             }
         }
         solve_fwd(P, Y, s, g);
-        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, QD, Q + D, false);   // the forward intermediates and q''
+        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, rf, s + Y.stage, false);   // the forward intermediates and q''
         if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, true, g);
         g.phase_sync();   // (also orders the tape / dump copies above before integrate_fwd overwrites q, qd)
         g.sync();
@@ -100,7 +102,8 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
 
 template <class Grp>
 DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a) {
-    const int Q = P.Q, D = P.D, M = P.M, QD = Y.tape_row, DD = D * D;
+    const int Q = P.Q, D = P.D, M = P.M, DD = D * D;
+    const RowFmt rf = row_fmt(P, Y, a.tape_bf16 != 0);
     DFX_FOR(i, D) { s[Y.act + i] = a.act[(long long)env * D + i]; s[Y.aact + i] = 0.0f; }
     DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
     if (g.lane == 0) s[Y.cmask] = 0.0f;
@@ -115,19 +118,19 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g
         // the rest, which substep_adj() waits for only before the phases that need it
         if constexpr (Grp::kBulkRows) {
             const bool want_hinv = seg_last && Y.A >= 0;
-            g.rows_in(s + Y.q, a.tape_in, sub, QD, Q + D, Y.qdd - Y.q, s + (want_hinv ? Y.A : 0),
+            g.rows_in(s + Y.q, a.tape_in, sub, rf, s + Y.stage, s + (want_hinv ? Y.A : 0),
                       want_hinv ? g.block_ptr(a.tape_in + a.hinv_base, seg, DD) : nullptr, DD);
         } else {
-            g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, true);
+            g.row_in(s + Y.q, a.tape_in, sub, a.N, env, rf.n, rf.early, rf.tail, true);
             if (seg_last && Y.A >= 0) g.block_in(s + Y.A, a.tape_in + a.hinv_base, seg, a.N, env, DD, false);
         }
         if (seg_last) DFX_FOR(e, dfx_sym_count(D)) s[Y.Lm + e] = 0.0f;      // symmetrised cotangent of H (packed)
         // layouts that do not stage H^-1 read its rows from the tape block in place (L2)
         const HinvView hv = (Y.A >= 0) ? HinvView{nullptr, 0} : g.hinv_view(a.tape_in + a.hinv_base, seg, a.N, env, DD);
-        if constexpr (!Grp::kBulkRows) g.row_in(s + Y.q, a.tape_in, sub, a.N, env, QD, Q + D, Y.qdd - Y.q, false);
+        if constexpr (!Grp::kBulkRows) g.row_in(s + Y.q, a.tape_in, sub, a.N, env, rf.n, rf.early, rf.tail, false);
         g.copy_wait_first();
         g.sync();
-        substep_adj(P, Y, s, a.dt_sub, sub == s0, hv, g);
+        substep_adj(P, Y, s, a.dt_sub, sub == s0, hv, rf, g);
     }
     if (a.gq) DFX_FOR(i, Q) a.gq[(long long)env * Q + i] = s[Y.aq + i];
     if (a.gqd) DFX_FOR(i, D) a.gqd[(long long)env * D + i] = s[Y.aqd + i];

@@ -24,6 +24,8 @@
 #define DFX_TILE_E 32
 #endif
 #define DFX_ES DFX_TILE_E
+#include <cuda_bf16.h>
+
 #include "dfx_launch.h"
 
 namespace dfx {
@@ -162,16 +164,31 @@ struct GroupTile {
             bulk_commit();
         }
     }
-    // a tape row as two bulk stores: (q, qd) when the substep starts, the intermediates and q'' when they exist
-    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, SP src, int n, int head, bool first) const {
+    // a tape row as bulk stores: (q, qd) when the substep starts; the intermediates and q'' when they exist.  With a bf16
+    // tape the middle is first converted into the staging area (flat: the tile's [head, tail) x E floats are contiguous).
+    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, SP src, const RowFmt& f, SP stage, bool first) const {
         (void)N; (void)env;
+        float* sm = sp_raw(src) - e;
+        float* st = sp_raw(stage) - e;
+        if (!first && f.bf16) {
+            const float2* in = reinterpret_cast<const float2*>(sm + f.head * E);
+            __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(st);
+            for (int i = threadIdx.x; i < (f.tail - f.head) * E / 2; i += NW * 32) out[i] = __float22bfloat162_rn(in[i]);
+        }
         fence_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
-            float* d = base + ((b * ntiles + tile) * n) * E;
-            const float* sm = sp_raw(src) - e;
-            if (first) bulk_store(d, sm, (unsigned)(head * E * 4));
-            else bulk_store(d + head * E, sm + head * E, (unsigned)((n - head) * E * 4));
+            float* d = base + ((b * ntiles + tile) * f.units) * E;
+            if (first) {
+                bulk_store(d, sm, (unsigned)(f.early * E * 4));
+            } else if (!f.bf16) {
+                bulk_store(d + f.early * E, sm + f.early * E, (unsigned)((f.n - f.early) * E * 4));
+            } else {
+                const int mid_units = (f.tail - f.head) / 2;
+                bulk_store(d + f.early * E, sm + f.early * E, (unsigned)((f.head - f.early) * E * 4));     // link transforms + S, fp32
+                bulk_store(d + f.head * E, st, (unsigned)(mid_units * E * 4));                               // v, a, f_tot as bf16
+                bulk_store(d + (f.head + mid_units) * E, sm + f.tail * E, (unsigned)((f.n - f.tail) * E * 4));
+            }
             bulk_commit();
         }
     }
@@ -186,19 +203,29 @@ struct GroupTile {
     __device__ __forceinline__ void row_in(SP dst, const float* base, long long b, int N, int env, int n, int head, int tail, bool first) const {
         (void)N; (void)env; (void)dst; (void)base; (void)b; (void)n; (void)head; (void)tail; (void)first;   // (see rows_in)
     }
-    __device__ __forceinline__ void rows_in(SP dst, const float* base, long long b, int n, int head, int tail,
+    __device__ __forceinline__ void rows_in(SP dst, const float* base, long long b, const RowFmt& f, SP stage,
                                             SP hinv_dst, const float* hinv_src, int dd) const {
         if (threadIdx.x != 0) return;
-        const float* src = base + ((b * ntiles + tile) * n) * E;
+        const float* src = base + ((b * ntiles + tile) * f.units) * E;
         float* d = sp_raw(dst) - e;
-        const unsigned b_head = (unsigned)(head * E * 4), b_tail = (unsigned)((n - tail) * E * 4), b_mid = (unsigned)((tail - head) * E * 4);
+        const int mid_units = f.bf16 ? (f.tail - f.head) / 2 : (f.tail - f.head);
+        const unsigned b_early = (unsigned)(f.early * E * 4), b_tail = (unsigned)((f.n - f.tail) * E * 4);
+        const unsigned b_xf = (unsigned)((f.head - f.early) * E * 4), b_mid = (unsigned)(mid_units * E * 4);
         const unsigned b_hinv = hinv_src ? (unsigned)(dd * E * 4) : 0u;
-        mbar_arrive_expect_tx(&mbar[0], b_head + b_tail + b_hinv);
-        bulk_load(d, src, b_head, &mbar[0]);
-        if (b_tail) bulk_load(d + tail * E, src + tail * E, b_tail, &mbar[0]);
+        mbar_arrive_expect_tx(&mbar[0], b_early + b_tail + b_hinv);
+        bulk_load(d, src, b_early, &mbar[0]);
+        if (b_tail) bulk_load(d + f.tail * E, src + (f.head + mid_units) * E, b_tail, &mbar[0]);
         if (b_hinv) bulk_load(sp_raw(hinv_dst) - e, hinv_src, b_hinv, &mbar[0]);
-        mbar_arrive_expect_tx(&mbar[1], b_mid);
-        bulk_load(d + head * E, src + head * E, b_mid, &mbar[1]);
+        mbar_arrive_expect_tx(&mbar[1], b_xf + b_mid);
+        if (b_xf) bulk_load(d + f.early * E, src + f.early * E, b_xf, &mbar[1]);
+        bulk_load(f.bf16 ? sp_raw(stage) - e : d + f.head * E, src + f.head * E, b_mid, &mbar[1]);
+    }
+    // bf16 tape: after copy_wait_all() the staged halves are widened into the scratch fields [head, tail)
+    __device__ __forceinline__ void row_unpack(SP dst, SP stage, const RowFmt& f) const {
+        if (!f.bf16) return;
+        const __nv_bfloat162* in = reinterpret_cast<const __nv_bfloat162*>(sp_raw(stage) - e);
+        float2* out = reinterpret_cast<float2*>(sp_raw(dst) - e + f.head * E);
+        for (int i = threadIdx.x; i < (f.tail - f.head) * E / 2; i += NW * 32) out[i] = __bfloat1622float2(in[i]);
     }
     __device__ __forceinline__ const float* block_ptr(const float* base, long long b, int n) const { return base + ((b * ntiles + tile) * n) * E; }
     __device__ __forceinline__ void block_in(SP dst, const float* base, long long b, int N, int env, int n, bool rows) const {

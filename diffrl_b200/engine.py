@@ -64,6 +64,7 @@ class ArticulationEngine:
         if not self.pack:
             raise _capi.DfxError("dfx_pack_create: " + err.value.decode())
         self.L, self.D, self.Q, self.C, self.M = desc.L, desc.D, desc.Q, desc.C, desc.M
+        self.tape_bf16 = bool(self.lib.dfx_pack_query(self.pack, 10))
         self._gravity = (desc.gravity, desc.ground)
 
     @classmethod
@@ -97,7 +98,15 @@ class ArticulationEngine:
         if not tile:
             return tape[: substeps * self.N * row].view(substeps, self.N, row).clone()
         ntiles = (self.N + tile - 1) // tile
-        t = tape[: substeps * ntiles * row * tile].view(substeps, ntiles, row, tile)
+        units = int(self.lib.dfx_pack_query(self.pack, 11))       # 4-byte units per row in the tape (< row with a bf16 tape)
+        t = tape[: substeps * ntiles * units * tile].view(substeps, ntiles, units, tile)
+        if units != row:
+            # bf16 tape: [q, qd, X_sc, X_sm, S | (v, a, f_tot) as bf16 pairs | q'', padding]
+            mid = 18 * self.L
+            head = self.Q + self.D + 14 * self.L + 6 * self.D
+            lo = t[:, :, :head]
+            halves = t[:, :, head:head + mid // 2].contiguous().view(torch.bfloat16).view(substeps, ntiles, mid, tile).float()
+            t = torch.cat([lo, halves, t[:, :, head + mid // 2:]], dim=2)
         return t.permute(0, 1, 3, 2).reshape(substeps, ntiles * tile, row)[:, : self.N].contiguous()
 
     def tape_floats(self, substeps, mm_freq):

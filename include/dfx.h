@@ -101,7 +101,9 @@ enum {
     DFX_QUERY_BWD_SCRATCH_FLOATS = 6, /* shared-memory floats per environment, backward */
     DFX_QUERY_TREE_DEPTH = 7,
     DFX_QUERY_TAPE_ROW_FLOATS = 8,    /* floats per (substep, environment) tape row */
-    DFX_QUERY_TAPE_TILE = 9           /* 0: tape blocks are [block][env][n]; E = 8 / 16 / 32: [block][tile of E envs][n][E] (tile kernels) */
+    DFX_QUERY_TAPE_TILE = 9,          /* 0: tape blocks are [block][env][n]; E = 8 / 16 / 32: [block][tile of E envs][n][E] (tile kernels) */
+    DFX_QUERY_TAPE_BF16 = 10,         /* 1: the middle of every tape row (the forward intermediates) is stored as bf16 */
+    DFX_QUERY_TAPE_ROW_UNITS = 11     /* 4-byte units per (substep, environment) row IN THE TAPE (== row floats unless bf16) */
 };
 
 /* Build the device-resident pack for CUDA device `device` (>= 0).  Returns NULL on failure and
@@ -222,6 +224,13 @@ int dfx_set_group_size(int lanes);
  * Bit 5 (32), read when a pack is CREATED: keep an articulation that has a tile kernel on the
  * lane-group kernels (the two families lay the tape out differently, DFX_QUERY_TAPE_TILE). */
 int dfx_set_flags(int flags);
+/* Tape storage, read when a pack is CREATED (tile kernels; ignored by the lane-group kernels): 0 (default) = fp32;
+ * 1 = the link velocities, bias accelerations and total link wrenches a row carries for the adjoint (v, a, f_tot: 18 L of the
+ * row's floats) are stored as bf16; the state (q, qd), q'', the link transforms and the motion subspace stay fp32 (they carry
+ * positions: contact depths are millimetres of metre-sized numbers).  Cuts the tape by 20 % (Humanoid: 182 -> 144 KB per
+ * env-step); arithmetic stays fp32.  The reference has no counterpart (it rejects fp16,
+ * dflex/dflex/adjoint.py:1985); the gradient tolerance against the fp32 oracle is stated in tests/tolerances.py. */
+int dfx_set_tape_dtype(int bf16);
 /* Tile width knob, read when a pack is CREATED: 0 (default) = the widest tile kernel that exists for the articulation
  * (32 environments per CTA for Ant / Hopper / HalfCheetah / CartPole, 8 for the two humanoids); 8, 16 or 32 = only a
  * kernel of that width (an articulation without one falls back to the lane-group kernels).  For A/B timing and tests. */

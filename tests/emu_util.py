@@ -75,8 +75,11 @@ class EmuSim:
         if not self.pack:
             raise RuntimeError(err.value.decode())
 
+    tape_bf16 = False     # emulate the tile kernels' bf16 tape (the middle of every row rounded through bf16)
+
     def forward(self, q, qd, act, musc, substeps, mm_freq, dt, tape=True, derived=False):
         N, d = self.N, self.desc
+        self.lib.emu_set_tape_bf16(int(self.tape_bf16))
         q = np.ascontiguousarray(q, np.float32); qd = np.ascontiguousarray(qd, np.float32)
         act = np.ascontiguousarray(act, np.float32)
         musc = None if musc is None else np.ascontiguousarray(musc, np.float32)

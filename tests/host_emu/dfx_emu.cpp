@@ -19,7 +19,12 @@ struct EmuPack {
     Pack pack;
 };
 
+static int g_tape_bf16 = 0;
+
 extern "C" {
+
+// round the middle of every tape row through bf16, as the tile kernels' bf16 tape does (dfx_set_tape_dtype)
+void emu_set_tape_bf16(int on) { g_tape_bf16 = on ? 1 : 0; }
 
 EmuPack* emu_pack_create(const DfxModelDesc* desc, char* err, int err_len) {
     EmuPack* p = new EmuPack();
@@ -68,6 +73,7 @@ int emu_step_forward(const EmuPack* p, int n, int substeps, int mm_freq, double 
     a.dt_sub = (float)(dt / (double)substeps);
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
+    a.tape_bf16 = g_tape_bf16;
     a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
     // (filled with NaN: a field the layout overlays or drops must never be read before it is written)
     std::vector<float> scratch((size_t)(p->host.layout.fwd_size + 16) * DFX_ES, nanf(""));
@@ -86,6 +92,7 @@ int emu_step_backward(const EmuPack* p, int n, int substeps, int mm_freq, double
     a.dt_sub = (float)(dt / (double)substeps);
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
+    a.tape_bf16 = g_tape_bf16;
     a.hinv_base = tape_geom(p->pack.L, p->pack.Q, p->pack.D, n, substeps, mm_freq).hinv_base;
     std::vector<float> scratch((size_t)(p->host.layout_bwd.bwd_size + 16) * DFX_ES, nanf(""));
     GroupSerial g{0};

@@ -17,3 +17,11 @@ _ILL_CONDITIONED = {"HumanoidEnv": 3e-5, "SNUHumanoidEnv": 3e-5}
 
 def fwd_rtol(env_name):
     return _ILL_CONDITIONED.get(env_name, FWD_RTOL)
+
+
+# bf16 tape (dfx_set_tape_dtype(1), config C2 "bf16 states"): v, a, f_tot of every tape row stored as bf16, arithmetic fp32.
+# The forward pass is untouched (bit-identical); gradients against the fp32 reference goldens, relative to the largest
+# component (measured on the host emulation: Humanoid 2.5e-3, SNU 2.7e-2 through the muscle wrenches; actions <= 4e-4).
+BF16_TAPE_STATE_GRAD_RTOL = {"SNUHumanoidEnv": 5e-2}
+BF16_TAPE_STATE_GRAD_RTOL_DEFAULT = 5e-3
+BF16_TAPE_ACTION_GRAD_RTOL = 1e-3
