@@ -16,7 +16,7 @@ struct PackBlob {
     const float* floats;
     int n_ints, n_floats;
     // offsets of each pointer field (same order as PackHost::bind)
-    int int_off[17];
+    int int_off[22];
     int float_off[17];
 };
 
@@ -27,6 +27,8 @@ __device__ __forceinline__ Pack bind_pack(const Pack& header, const PackBlob& b,
     p.qd_start = ib + b.int_off[ii++]; p.level_start = ib + b.int_off[ii++]; p.level_links = ib + b.int_off[ii++];
     p.child_start = ib + b.int_off[ii++]; p.child_idx = ib + b.int_off[ii++]; p.anc_start = ib + b.int_off[ii++];
     p.anc_dofs = ib + b.int_off[ii++]; p.sub_start = ib + b.int_off[ii++]; p.sub_links = ib + b.int_off[ii++];
+    p.path_start = ib + b.int_off[ii++]; p.path_links = ib + b.int_off[ii++]; p.round_start = ib + b.int_off[ii++];
+    p.chain_start = ib + b.int_off[ii++]; p.chain_links = ib + b.int_off[ii++];
     p.dof_link = ib + b.int_off[ii++]; p.cbody_start = ib + b.int_off[ii++]; p.cbody = ib + b.int_off[ii++];
     p.mstart = ib + b.int_off[ii++]; p.mlinks = ib + b.int_off[ii++];
     p.X_pj = fb + b.float_off[fi++]; p.X_cm = fb + b.float_off[fi++]; p.axis = fb + b.float_off[fi++];

@@ -20,6 +20,7 @@ struct Pack {
     int M;       // muscles
     int W;       // muscle way-points
     int nlev;    // tree depth
+    int nround;  // rounds of the chain decomposition (below)
     int ground;  // model.ground && C > 0
     float gx, gy, gz;
 
@@ -36,6 +37,16 @@ struct Pack {
     const int* anc_dofs;
     const int* sub_start;    // (L+1) subtree (descendant-or-self) link lists
     const int* sub_links;
+    const int* path_start;   // (L+1) the links on the path root -> ... -> i (i included), root first
+    const int* path_links;
+    // Chain decomposition for tree recursions: a chain starts at a leaf or at a link with >= 2 children and runs upwards
+    // while the parent has no other child; a chain's round is 0 for leaf chains, else 1 + the largest round of the chains
+    // hanging below it.  Chains are sorted by round; chain_links lists a chain bottom-up.  A leaves -> root recursion
+    // processes round 0, 1, ... with ONE barrier per round (a chain is walked by one thread), a root -> leaves recursion
+    // the rounds in reverse and every chain top-down: 2-3 barriers instead of one per tree level (Humanoid: 10 levels).
+    const int* round_start;  // (nround+1) offsets into the chain list
+    const int* chain_start;  // (nchain+1) offsets into chain_links
+    const int* chain_links;  // (L)
     const float* X_pj;       // (L,7)
     const float* X_cm;       // (L,7)
     const float* axis;       // (L,3)

@@ -46,6 +46,11 @@ struct PackHost {
         p.anc_dofs = ibase + int_off[ii++];
         p.sub_start = ibase + int_off[ii++];
         p.sub_links = ibase + int_off[ii++];
+        p.path_start = ibase + int_off[ii++];
+        p.path_links = ibase + int_off[ii++];
+        p.round_start = ibase + int_off[ii++];
+        p.chain_start = ibase + int_off[ii++];
+        p.chain_links = ibase + int_off[ii++];
         p.dof_link = ibase + int_off[ii++];
         p.cbody_start = ibase + int_off[ii++];
         p.cbody = ibase + int_off[ii++];
@@ -166,6 +171,50 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
         }
     }
     sub_start[L] = (int)sub_links.size();
+    std::vector<int> path_start(L + 1, 0), path_links;
+    for (int i = 0; i < L; ++i) {
+        path_start[i] = (int)path_links.size();
+        std::vector<int> chain;
+        for (int j = i; j >= 0; j = parent[j]) chain.push_back(j);
+        for (int k = (int)chain.size() - 1; k >= 0; --k) path_links.push_back(chain[k]);
+    }
+    path_start[L] = (int)path_links.size();
+    // chain decomposition (see dfx_pack.h)
+    std::vector<int> nchild(L, 0), chain_of(L, -1), chain_round;
+    for (int i = 0; i < L; ++i) if (parent[i] >= 0) ++nchild[parent[i]];
+    std::vector<std::vector<int>> chains;
+    for (int i = L - 1; i >= 0; --i) {                    // parents precede children: every child's chain exists already
+        if (nchild[i] == 1) continue;                     // inner link of a chain: appended when its bottom is visited
+        std::vector<int> c;
+        int round = 0;
+        for (int k = child_start[i]; k < child_start[i + 1]; ++k) {
+            const int r = chain_round[chain_of[child_idx[k]]] + 1;
+            if (r > round) round = r;
+        }
+        for (int j = i;;) {
+            c.push_back(j);
+            chain_of[j] = (int)chains.size();
+            const int p = parent[j];
+            if (p < 0 || nchild[p] != 1) break;
+            j = p;
+        }
+        chains.push_back(c);
+        chain_round.push_back(round);
+    }
+    int nround = 0;
+    for (int r : chain_round) if (r + 1 > nround) nround = r + 1;
+    std::vector<int> round_start(nround + 1, 0), chain_start, chain_links;
+    for (int r = 0; r < nround; ++r) {
+        round_start[r] = (int)chain_start.size();
+        for (size_t c = 0; c < chains.size(); ++c) {
+            if (chain_round[c] != r) continue;
+            chain_start.push_back((int)chain_links.size());
+            chain_links.insert(chain_links.end(), chains[c].begin(), chains[c].end());
+        }
+    }
+    round_start[nround] = (int)chain_start.size();
+    chain_start.push_back((int)chain_links.size());
+    h.nround = nround;
     // contacts grouped by body, original order preserved inside a body
     std::vector<int> cbody_start(L + 1, 0), cbody, corder;
     for (int i = 0; i < L; ++i) {
@@ -191,7 +240,8 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
     }
     push_i(type); push_i(parent); push_i(qs); push_i(ds); push_i(level_start); push_i(level_links);
     push_i(child_start); push_i(child_idx); push_i(anc_start); push_i(anc_dofs); push_i(sub_start);
-    push_i(sub_links); push_i(dof_link); push_i(cbody_start); push_i(cbody); push_i(mstart); push_i(mlinks);
+    push_i(sub_links); push_i(path_start); push_i(path_links); push_i(round_start); push_i(chain_start); push_i(chain_links);
+    push_i(dof_link); push_i(cbody_start); push_i(cbody); push_i(mstart); push_i(mlinks);
     auto vec = [](const float* p, int n) { return p ? std::vector<float>(p, p + n) : std::vector<float>(n, 0.0f); };
     push_f(vec(d.joint_X_pj, L * 7)); push_f(vec(d.joint_X_cm, L * 7)); push_f(vec(d.joint_axis, L * 3));
     push_f(Ic); push_f(mass);

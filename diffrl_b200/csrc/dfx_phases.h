@@ -150,6 +150,28 @@ DFX_HD void level_tasks(const Pack& P, SP s, int lev, bool lead, const Grp& g, F
     g.cta_tasks(s, e - b, lead, [&](SP se, int k) { f(se, P.level_links[b + k]); });
 }
 
+// Tree recursions by CHAINS (dfx_pack.h): a chain of links without side branches is walked by ONE thread, so consecutive
+// links need no barrier; chains that hang below other chains run in an earlier round.  One barrier per round (2-3) instead
+// of one per tree level (Humanoid: 10), the same per-link operations in the same order.
+template <class Grp, class F>
+DFX_HD void chain_rounds_up(const Pack& P, SP s, const Grp& g, F f) {        // leaves -> root
+    for (int r = 0; r < P.nround; ++r) {
+        const int b = P.round_start[r], e = P.round_start[r + 1];
+        g.cta_tasks(s, e - b, false, [&](SP se, int k) {
+            for (int j = P.chain_start[b + k]; j < P.chain_start[b + k + 1]; ++j) f(se, P.chain_links[j]);
+        });
+    }
+}
+template <class Grp, class F>
+DFX_HD void chain_rounds_down(const Pack& P, SP s, const Grp& g, F f) {      // root -> leaves
+    for (int r = P.nround - 1; r >= 0; --r) {
+        const int b = P.round_start[r], e = P.round_start[r + 1];
+        g.cta_tasks(s, e - b, false, [&](SP se, int k) {
+            for (int j = P.chain_start[b + k + 1] - 1; j >= P.chain_start[b + k]; --j) f(se, P.chain_links[j]);
+        });
+    }
+}
+
 template <class Grp>
 DFX_HD void zero_range(SP p, int n, const Grp& g) {
     DFX_FOR(i, n) p[i] = 0.0f;
@@ -182,18 +204,12 @@ DFX_HD void kin_local_fwd(const Pack& P, const Layout& Y, SP s, int i) {   // K1
     st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
 }
 
-// call f(p) for the links on the path root -> ... -> parent(i) [-> i], in that order.  The path is re-walked
-// from i for every depth (O(depth^2) parent look-ups, all warp-uniform broadcasts from the staged pack): trees here
-// are 3-8 levels deep, and it replaces one barrier per level by none.
+// call f(p) for the links on the path root -> ... -> parent(i) [-> i], in that order (the pack lists every link's path:
+// independent look-ups instead of a chain of dependent parent[] loads per depth)
 template <class F>
 DFX_HD void for_path_root_first(const Pack& P, int i, bool include_self, F f) {
-    int dep = 0;
-    for (int p = P.parent[i]; p >= 0; p = P.parent[p]) ++dep;
-    for (int d = dep; d >= (include_self ? 0 : 1); --d) {
-        int p = i;
-        for (int k = 0; k < d; ++k) p = P.parent[p];
-        f(p);
-    }
+    const int b = P.path_start[i], e = P.path_start[i + 1] - (include_self ? 0 : 1);
+    for (int k = b; k < e; ++k) f(P.path_links[k]);
 }
 
 // K2: X_sc[parent] as the product of the joint-local transforms along the path from the root, multiplied in the
@@ -414,11 +430,9 @@ template <class Grp>
 DFX_HD void kin_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     // all five passes run as CTA-wide (link, environment) tasks, link-major: uniform joint types per warp
     g.cta_tasks(s, P.L, true, [&](SP se, int i) { kin_adj_local(P, Y, se, i); });
-    for (int lev = P.nlev - 1; lev >= 0; --lev)
-        level_tasks(P, s, lev, false, g, [&](SP se, int i) { kin_adj_velocity(P, Y, se, i); });
+    chain_rounds_up(P, s, g, [&](SP se, int i) { kin_adj_velocity(P, Y, se, i); });
     g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_motion(P, Y, se, i); });
-    for (int lev = P.nlev - 1; lev >= 0; --lev)
-        level_tasks(P, s, lev, false, g, [&](SP se, int i) { kin_adj_chain(P, Y, se, i); });
+    chain_rounds_up(P, s, g, [&](SP se, int i) { kin_adj_chain(P, Y, se, i); });
     g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_joint(P, Y, se, i); });
 }
 
@@ -986,11 +1000,7 @@ template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, SP s, SP atau, const Grp& g) {
     const int atau_off = (int)(atau - s);   // (element offset inside the scratch)
     g.cta_tasks(s, P.L, true, [&](SP se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
-    for (int lev = 1; lev < P.nlev; ++lev) {
-        const int b = P.level_start[lev], e = P.level_start[lev + 1];
-        for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_adj(P, Y, s, P.level_links[k]);
-        g.sync();
-    }
+    chain_rounds_down(P, s, g, [&](SP se, int i) { tau_accum_adj(P, Y, se, i); });
 }
 
 // =====================================================================================

@@ -220,6 +220,13 @@ struct GroupTile {
         if (b_xf) bulk_load(d + f.early * E, src + f.early * E, b_xf, &mbar[1]);
         bulk_load(f.bf16 ? sp_raw(stage) - e : d + f.head * E, src + f.head * E, b_mid, &mbar[1]);
     }
+    // pull the row the NEXT iteration will load (the previous substep's) into L2 while this substep's adjoint runs: its
+    // bulk loads then complete from L2 instead of paying the HBM latency at the top of every substep
+    __device__ __forceinline__ void prefetch_row(const float* base, long long b, const RowFmt& f) const {
+        if (threadIdx.x != 0) return;
+        const float* src = base + ((b * ntiles + tile) * f.units) * E;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(f.units * E * 4)) : "memory");
+    }
     // bf16 tape: after copy_wait_all() the staged halves are widened into the scratch fields [head, tail)
     __device__ __forceinline__ void row_unpack(SP dst, SP stage, const RowFmt& f) const {
         if (!f.bf16) return;

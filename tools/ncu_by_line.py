@@ -1,18 +1,22 @@
 """Aggregate an ncu report's per-SASS-instruction counters by CUDA source line / function.
 
-usage: python tools/ncu_by_line.py <report.ncu-rep> <lib.so> <kernel-substring e.g. 'ILi16ELb0'> [top]
+usage: python tools/ncu_by_line.py <report.ncu-rep> <lib.so | build/obj> <kernel-substring e.g. 'ILi16ELb0'> [top]
 Needs the .so compiled with -lineinfo.  (ncu's own CSV export of the CUDA view carries no metrics.)
 """
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
 rep, lib, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-tmp = tempfile.mkdtemp()
-subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
+# <lib.so> may also be a directory of object files (build/obj): dfx_tile.cu is compiled three times (one per tile width) and
+# cuobjdump names extracted cubins after the SOURCE file, so the three would overwrite each other when taken from the .so
+objs = [os.path.join(lib, f) for f in sorted(os.listdir(lib)) if f.endswith(".o")] if os.path.isdir(lib) else [lib]
 dis = ""
-for f in sorted(os.listdir(tmp)):
-    if f.endswith(".cubin"):
-        dis += subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+for o in objs:
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(o)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for f in sorted(os.listdir(tmp)):
+        if f.endswith(".cubin"):
+            dis += subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
 # ---- offset -> (file, line) of the innermost inlined function, and the whole inline chain, for the chosen kernel
 off2line, off2chain, cur, chain, inside, fresh = {}, {}, None, [], False, True
 for ln in dis.splitlines():
@@ -67,7 +71,7 @@ def func_table(path):
         if m and not ln.startswith(" "):
             tbl.append((n, m.group(1)))
     return tbl
-root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffrl_b200", "csrc")
+root = os.environ.get("DFX_SRC_ROOT") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffrl_b200", "csrc")   # the sources the profiled library was built from
 ftab = {f: func_table(os.path.join(root, f)) for f in os.listdir(root)}
 def func_of(file, line):
     best = "?"
