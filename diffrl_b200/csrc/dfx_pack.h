@@ -72,6 +72,12 @@ struct Pack {
     // ---- muscles ----
     const int* mstart;       // (M+1)
     const int* mlinks;       // (W) local link index
+    // only the segments whose two way-points sit on DIFFERENT links pull (reference sim.py:1231: l0 == l1 -> skip): the pack
+    // lists them per muscle (the SNU model: 198 of 484 segments, 1-2 per muscle), and orders the muscles by their count
+    // so that the item slots of a warp run the same number of iterations
+    const int* aseg_start;   // (M+1) offsets into aseg_way
+    const int* aseg_way;     // way-point index i of an active segment (i, i+1)
+    const int* morder;       // (M) item k works on muscle morder[k]
     const float* mpoints;    // (W,3)
 };
 

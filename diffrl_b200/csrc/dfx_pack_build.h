@@ -56,6 +56,9 @@ struct PackHost {
         p.cbody = ibase + int_off[ii++];
         p.mstart = ibase + int_off[ii++];
         p.mlinks = ibase + int_off[ii++];
+        p.aseg_start = ibase + int_off[ii++];
+        p.aseg_way = ibase + int_off[ii++];
+        p.morder = ibase + int_off[ii++];
         p.X_pj = fbase + float_off[fi++];
         p.X_cm = fbase + float_off[fi++];
         p.axis = fbase + float_off[fi++];
@@ -232,6 +235,14 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
     std::vector<int> mstart(M + 1, 0), mlinks(W);
     for (int i = 0; i <= M && M > 0; ++i) mstart[i] = d.muscle_start[i];
     for (int i = 0; i < W; ++i) mlinks[i] = d.muscle_links[i];
+    std::vector<int> aseg_start(M + 1, 0), aseg_way, morder;
+    for (int m = 0; m < M; ++m) {
+        aseg_start[m] = (int)aseg_way.size();
+        for (int i = mstart[m]; i < mstart[m + 1] - 1; ++i) if (mlinks[i] != mlinks[i + 1]) aseg_way.push_back(i);
+    }
+    if (M > 0) aseg_start[M] = (int)aseg_way.size();
+    for (int cnt = 0, placed = 0; placed < M; ++cnt)
+        for (int m = 0; m < M; ++m) if (aseg_start[m + 1] - aseg_start[m] == cnt) { morder.push_back(m); ++placed; }
     std::vector<float> Ic(L * 9), mass(L);
     for (int i = 0; i < L; ++i) {
         const float* I = d.body_I_m + i * 36;
@@ -241,7 +252,7 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
     push_i(type); push_i(parent); push_i(qs); push_i(ds); push_i(level_start); push_i(level_links);
     push_i(child_start); push_i(child_idx); push_i(anc_start); push_i(anc_dofs); push_i(sub_start);
     push_i(sub_links); push_i(path_start); push_i(path_links); push_i(round_start); push_i(chain_start); push_i(chain_links);
-    push_i(dof_link); push_i(cbody_start); push_i(cbody); push_i(mstart); push_i(mlinks);
+    push_i(dof_link); push_i(cbody_start); push_i(cbody); push_i(mstart); push_i(mlinks); push_i(aseg_start); push_i(aseg_way); push_i(morder);
     auto vec = [](const float* p, int n) { return p ? std::vector<float>(p, p + n) : std::vector<float>(n, 0.0f); };
     push_f(vec(d.joint_X_pj, L * 7)); push_f(vec(d.joint_X_cm, L * 7)); push_f(vec(d.joint_axis, L * 3));
     push_f(Ic); push_f(mass);

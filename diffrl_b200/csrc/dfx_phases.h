@@ -832,11 +832,12 @@ DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const SPi lo = sp_int(s + Y.fx);
     const SPi hi = lo + P.L * 6;
     const SPu poison = sp_uint(s + Y.cmask);
-    DFX_FOR(m, P.M) {
+    DFX_FOR(k, P.M) {
+        const int m = P.morder[k];
         const float act = s[Y.musc + m];
-        for (int i = P.mstart[m]; i < P.mstart[m + 1] - 1; ++i) {
+        for (int j = P.aseg_start[m]; j < P.aseg_start[m + 1]; ++j) {      // the segments that span two links
+            const int i = P.aseg_way[j];
             const int l0 = P.mlinks[i], l1 = P.mlinks[i + 1];
-            if (l0 == l1) continue;
             const V3 p0 = xf_point(ld7(s + Y.Xsc + l0 * 7), ld3(P.mpoints + i * 3));
             const V3 p1 = xf_point(ld7(s + Y.Xsc + l1 * 7), ld3(P.mpoints + (i + 1) * 3));
             const V3 d = p1 - p0;
@@ -858,12 +859,13 @@ DFX_HD void muscle_adj(const Pack& P, const Layout& Y, SP s, float scale, const 
     const SPi lo = sp_int(s + Y.aXsc);   // still all-zero in this phase: doubles as the low words
     const SPi hi = sp_int(s + Y.fxH);
     const SPu poison = sp_uint(s + Y.cmask);
-    DFX_FOR(m, P.M) {
+    DFX_FOR(k, P.M) {
+        const int m = P.morder[k];
         const float act = s[Y.musc + m];
         float aact = 0.0f;
-        for (int i = P.mstart[m]; i < P.mstart[m + 1] - 1; ++i) {
+        for (int j = P.aseg_start[m]; j < P.aseg_start[m + 1]; ++j) {
+            const int i = P.aseg_way[j];
             const int l0 = P.mlinks[i], l1 = P.mlinks[i + 1];
-            if (l0 == l1) continue;
             const Xf X0 = ld7(s + Y.Xsc + l0 * 7), X1 = ld7(s + Y.Xsc + l1 * 7);
             const V3 r0 = ld3(P.mpoints + i * 3), r1 = ld3(P.mpoints + (i + 1) * 3);
             const V3 p0 = xf_point(X0, r0), p1 = xf_point(X1, r1);

@@ -89,11 +89,30 @@ def test_cuda_matches_oracles_at_named_size(name, N):
     eq, eqd, etape, _ = emu.forward(q0[sample].ravel(), qd0[sample].ravel(), act[sample].ravel(), None if ms is None else ms.ravel(), c["S"], c["mm"], c["dt"])
     egq, egqd, egact, egm = emu.backward(act[sample].ravel(), None if ms is None else ms.ravel(), etape, gq_out[sample].ravel(), gqd_out[sample].ravel(), c["S"], c["mm"], c["dt"])
     good = np.setdiff1d(np.arange(len(sample)), bad)
+    suspects = set()
     for got, ref, w in ((gq, egq, Q), (gqd, egqd, D), (gact, egact, D)) + (((gm, egm, M),) if M else ()):
         g = got.cpu().numpy().reshape(N, w)[sample][good]
         r = ref.reshape(-1, w)[good]
-        nb = elementwise_bad_envs(g, r, w, 4 * GRAD_RTOL)
-        assert len(nb) <= 2, (name, w, len(nb), float(np.abs(g - r).max() / np.abs(r).max()))
+        suspects |= set(good[elementwise_bad_envs(g, r, w, 4 * GRAD_RTOL)])
+    # A gradient outside the tolerance is only acceptable on a SWITCHING SURFACE of the contact / limit model (c >= 0,
+    # min(vn, 0), min(kf |vt|, mu c ke), q < lower: the derivative jumps there while the forward value is continuous): the
+    # emulation's OWN gradient of that environment must jump by a comparable amount when its input moves by one fp32 ulp.
+    assert len(suspects) <= 8, (name, len(suspects))
+    one = EmuSim(model, int(d["meta/num_envs"]))
+    one.N = 1
+    for e in sorted(suspects):
+        i = sample[e]
+        mi = None if musc is None else musc[i]
+        grads = []
+        for sgn in (0.0, 1.0, -1.0):
+            qp, qdp = q0[i] * (1.0 + sgn * 1.2e-7), qd0[i] * (1.0 - sgn * 1.2e-7)
+            _, _, tp, _ = one.forward(qp, qdp, act[i], mi, c["S"], c["mm"], c["dt"])
+            grads.append(np.concatenate([x for x in one.backward(act[i], mi, tp, gq_out[i], gqd_out[i], c["S"], c["mm"], c["dt"]) if x is not None]))
+        scale = np.abs(grads[0]).max()
+        jump = max(np.abs(grads[1] - grads[0]).max(), np.abs(grads[2] - grads[0]).max()) / scale
+        mine = np.concatenate([x.cpu().numpy().reshape(N, -1)[i] for x in (gq, gqd, gact) + ((gm,) if M else ())])
+        err = np.abs(mine - grads[0]).max() / scale
+        assert err <= max(4 * GRAD_RTOL, 8.0 * jump), (name, "env %d: gradient error %.2e, one-ulp jump of the emulation's own gradient %.2e" % (i, err, jump))
 
 
 def test_snu_bptt128_rollout_matches_reference_kernels():
@@ -141,8 +160,9 @@ def test_snu_bptt128_rollout_matches_reference_kernels():
     # adjoint of every env-step gets the reference's incoming cotangents (per-step adjoint parity; the chain's own
     # conditioning would otherwise dominate after a few steps)
     gq_r, gqd_r = torch.ones(n * Q), torch.ones(n * D)
-    rows = []
+    rows, cots = [], {}
     for t in reversed(range(T)):
+        cots[t] = (gq_r, gqd_r)
         q0, qd0 = ref_states[t]
         _, _, grads, _ = ref_driver.env_step(rm, q0, qd0, act, muscs[t], dt, S, mm, gq_out=gq_r, gqd_out=gqd_r)
         gq_n, gqd_n, _, gm_r = grads
@@ -154,10 +174,24 @@ def test_snu_bptt128_rollout_matches_reference_kernels():
                      float((gm_g.cpu() - gm_r).abs().max() / (gm_r.abs().max() + 1e-30)), scale))
         gq_r, gqd_r = gq_n, gqd_n
     assert len(rows) >= 64, len(rows)
-    worst = sorted(rows, key=lambda r: -max(r[1:4]))[:5]
     for col, what in ((1, "gq"), (2, "gqd"), (3, "gmusc")):
         errs = np.array([r[col] for r in rows])
-        assert np.median(errs) < GRAD_RTOL and errs.max() < 8 * GRAD_RTOL, (what, float(np.median(errs)), float(errs.max()), worst)
+        assert np.median(errs) < GRAD_RTOL and np.quantile(errs, 0.9) < 4 * GRAD_RTOL, (what, float(np.median(errs)), float(np.quantile(errs, 0.9)))
+    # a step outside 8 x the tolerance must sit on a switching surface of the contact / limit model: the REFERENCE's own
+    # gradient of that step jumps by a comparable amount when the step's input state moves by one fp32 ulp
+    outliers = [r for r in rows if max(r[1:4]) >= 8 * GRAD_RTOL]
+    assert len(outliers) <= max(2, len(rows) // 20), [(r[0], max(r[1:4])) for r in outliers]
+    for r in outliers:
+        t = r[0]
+        q0, qd0 = ref_states[t]
+        cot = cots[t]
+        base = ref_driver.env_step(rm, q0, qd0, act, muscs[t], dt, S, mm, gq_out=cot[0], gqd_out=cot[1])[2]
+        jump = 0.0
+        for sgn in (1.0, -1.0):
+            pert = ref_driver.env_step(rm, q0 * (1.0 + sgn * 1.2e-7), qd0 * (1.0 - sgn * 1.2e-7), act, muscs[t], dt, S, mm, gq_out=cot[0], gqd_out=cot[1])[2]
+            jump = max(jump, float((pert[0] - base[0]).abs().max()) / r[4], float((pert[1] - base[1]).abs().max()) / r[4],
+                       float((pert[3] - base[3]).abs().max() / (base[3].abs().max() + 1e-30)))
+        assert max(r[1:4]) <= 8.0 * jump, ("step %d: adjoint error %.2e, one-ulp jump of the reference's own gradient %.2e" % (t, max(r[1:4]), jump))
 
 
 @pytest.mark.parametrize("name", ["CartPoleSwingUpEnv", "AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "HopperEnv", "CheetahEnv"])
