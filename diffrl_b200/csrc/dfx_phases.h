@@ -1124,6 +1124,25 @@ DFX_HD void chol_inverse(const Pack& P, const Layout& Y, SP s, const Grp& g) {
 template <class Grp>
 DFX_HD void solve_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D;
+#if defined(DFX_EMU_SWEEPS) && !defined(__CUDACC__)
+    // Host-emulation A/B only (tests/test_emu_golden.py::test_explicit_inverse_is_not_the_parity_floor): the reference's two
+    // triangular sweeps with the Cholesky factor (matnn.h:188-230) instead of the H^-1 mat-vec.  Needs a layout that keeps Lm.
+    if (g.lane == 0) {
+        float y[64];
+        for (int i = 0; i < D; ++i) {
+            float acc = s[Y.tau + i];
+            for (int k = 0; k < i; ++k) acc -= s[Y.Lm + i * D + k] * y[k];
+            y[i] = acc / s[Y.Lm + i * D + i];
+        }
+        for (int i = D - 1; i >= 0; --i) {
+            float acc = y[i];
+            for (int k = i + 1; k < D; ++k) acc -= s[Y.Lm + k * D + i] * s[Y.qdd + k];
+            s[Y.qdd + i] = acc / s[Y.Lm + i * D + i];
+        }
+    }
+    g.sync();
+    return;
+#endif
     DFX_FOR(i, D) {
         float acc = 0.0f;
         for (int j = 0; j < D; ++j) acc += s[Y.A + i * D + j] * s[Y.tau + j];

@@ -120,7 +120,7 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g
             const bool want_hinv = seg_last && Y.A >= 0;
             g.rows_in(s + Y.q, a.tape_in, sub, rf, s + Y.stage, s + (want_hinv ? Y.A : 0),
                       want_hinv ? g.block_ptr(a.tape_in + a.hinv_base, seg, DD) : nullptr, DD);
-            if (sub > 0) g.prefetch_row(a.tape_in, sub - 1, rf);
+            if (sub > 0 && !(a.flags & 128)) g.prefetch_row(a.tape_in, sub - 1, rf);
         } else {
             g.row_in(s + Y.q, a.tape_in, sub, a.N, env, rf.n, rf.early, rf.tail, true);
             if (seg_last && Y.A >= 0) g.block_in(s + Y.A, a.tape_in + a.hinv_base, seg, a.N, env, DD, false);

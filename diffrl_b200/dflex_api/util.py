@@ -181,29 +181,54 @@ def log(s):
 
 
 class ScopedTimer:
-    """``with df.ScopedTimer("name", active):`` wall-clock (+ optional cProfile) timer."""
+    """``with df.ScopedTimer(name, active=True, detailed=False):`` -- the envs wrap their simulate / reset / render
+    sections in it (``envs/cartpole_swing_up.py:114-148``), almost always with ``active=False``.
 
-    indent = -1
+    An inactive timer costs nothing.  An active one reports the wall-clock time of the block; on a CUDA build it brackets
+    the block with a device synchronisation so that the figure covers the kernels the block launched, not just their
+    enqueueing (the fused step returns before the GPU has run it).  ``detailed`` adds a cProfile table.  Nested timers
+    indent their report by depth."""
+
+    _depth = 0
     enabled = True
+    sync_cuda = True
 
     def __init__(self, name, active=True, detailed=False):
-        self.name, self.detailed = name, detailed
-        self.active = active and self.enabled
+        self.name = name
+        self.active = bool(active) and ScopedTimer.enabled
+        self.detailed = bool(detailed)
+        self.elapsed_ms = None
+        self._t0 = self._profile = None
+
+    @staticmethod
+    def _sync():
+        if ScopedTimer.sync_cuda:
+            try:
+                import torch
+                if torch.cuda.is_available() and torch.cuda.is_initialized():
+                    torch.cuda.synchronize()
+            except Exception:
+                pass
 
     def __enter__(self):
-        if self.active:
-            self.start = timeit.default_timer()
-            ScopedTimer.indent += 1
-            if self.detailed:
-                self.cp = cProfile.Profile()
-                self.cp.enable()
+        if not self.active:
+            return self
+        ScopedTimer._depth += 1
+        if self.detailed:
+            self._profile = cProfile.Profile()
+            self._profile.enable()
+        self._sync()
+        self._t0 = timeit.default_timer()
         return self
 
     def __exit__(self, exc_type, exc_value, traceback):
-        if self.active and self.detailed:
-            self.cp.disable()
-            self.cp.print_stats(sort="tottime")
-        if self.active:
-            elapsed = (timeit.default_timer() - self.start) * 1000.0
-            log("{}{} took {:.2f} ms".format("\t" * ScopedTimer.indent, self.name, elapsed))
-            ScopedTimer.indent -= 1
+        if not self.active:
+            return False
+        self._sync()
+        self.elapsed_ms = 1e3 * (timeit.default_timer() - self._t0)
+        if self._profile is not None:
+            self._profile.disable()
+            self._profile.print_stats(sort="tottime")
+        ScopedTimer._depth -= 1
+        log("%s%s took %.2f ms" % ("\t" * ScopedTimer._depth, self.name, self.elapsed_ms))
+        return False

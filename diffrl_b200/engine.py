@@ -3,8 +3,11 @@ kernel launch per env-step, exposed to PyTorch as a single ``autograd.Function``
 
 Replaces the reference's ``SimulateFunc`` + ``Tape`` (``dflex/dflex/sim.py:2086-2154``,
 ``dflex/dflex/adjoint.py:2114-2216``): instead of recording 10-11 launches per substep and keeping
-every State tensor of every substep alive, forward writes a compact (q, qd)-per-substep tape and
-backward is one kernel that re-creates each substep in shared memory.
+every State tensor of every substep alive, forward writes one tape ROW per substep -- the (q, qd) entering it plus
+the forward intermediates the adjoint needs (X_sc, X_sm, S, v, a, total link wrenches, q'') -- and one H^-1 block
+per mass-matrix update; backward is one kernel that streams those rows back (TMA bulk copies in the tile
+kernels) and does NOT re-run the forward dynamics.  The tape is an opaque fp32 tensor sized by
+``dfx_tape_floats`` (optionally with bf16 (v, a, f_tot): ``diffrl_b200.set_tape_dtype``).
 """
 import ctypes
 

@@ -220,6 +220,7 @@ int dfx_set_group_size(int lanes);
 /* Tuning flags (default 9; for A/B timing and tests).  Lane-group kernels: bit 1 (2) = extra CTA-wide barriers between
  * phases (instruction-cache locality; no longer a gain now that the task loops synchronise the CTA anyway); bit 2 (4) =
  * generic kernels instead of the size-specialised ones; bit 3 (8) = CTA-wide task loops for thin / sparse phases.
+ * Bit 7 (128): tile kernels do not prefetch the next tape row into L2 during the adjoint (A/B timing).
  * Bit 6 (64): tile kernels of the large articulations use level-by-level tree recursions instead of path / subtree passes.
  * Bit 5 (32), read when a pack is CREATED: keep an articulation that has a tile kernel on the
  * lane-group kernels (the two families lay the tape out differently, DFX_QUERY_TAPE_TILE). */

@@ -16,21 +16,22 @@ GOLDEN = os.path.join(HERE, "golden")
 _F = ctypes.POINTER(ctypes.c_float)
 
 
-def build_emu(es=1, path_passes=False, layout_mode=0):
+def build_emu(es=1, path_passes=False, layout_mode=0, extra=()):
     """es: element stride of the per-environment scratch (csrc/dfx_math.h DFX_ES).  1 is what the lane-group kernels
     use; any other value exercises the strided addressing of the 32-environment tile kernels on the CPU.
     path_passes: the tile kernels' path / subtree formulation of the tree passes (Grp::kPathPasses)."""
     lib_path = EMU_LIB
-    if es != 1 or path_passes or layout_mode:
-        lib_path = EMU_LIB.replace(".so", "_es%d%s%s.so" % (es, "_path" if path_passes else "", "_lm%d" % layout_mode if layout_mode else ""))
-    return _build_emu(lib_path, es, path_passes, layout_mode)
+    if es != 1 or path_passes or layout_mode or extra:
+        tag = "".join(c if c.isalnum() else "_" for c in "".join(extra))
+        lib_path = EMU_LIB.replace(".so", "_es%d%s%s%s.so" % (es, "_path" if path_passes else "", "_lm%d" % layout_mode if layout_mode else "", tag))
+    return _build_emu(lib_path, es, path_passes, layout_mode, extra)
 
 
-def _build_emu(EMU_LIB, es, path_passes=False, layout_mode=0):
+def _build_emu(EMU_LIB, es, path_passes=False, layout_mode=0, extra=()):
     deps = [EMU_SRC] + [os.path.join(ROOT, "diffrl_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "diffrl_b200", "csrc")) if f.endswith(".h")]
     deps.append(os.path.join(ROOT, "include", "dfx.h"))
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-DDFX_ES=%d" % es, "-DDFX_EMU_PATH_PASSES=%d" % int(path_passes)] + (["-DDFX_EMU_LAYOUT_MODE=%d" % layout_mode] if layout_mode else []) + ["-shared", "-fPIC",
+        subprocess.check_call(["g++", "-O2", "-std=c++17"] + ([] if any("contract" in x for x in extra) else ["-ffp-contract=off"]) + list(extra) + ["-DDFX_ES=%d" % es, "-DDFX_EMU_PATH_PASSES=%d" % int(path_passes)] + (["-DDFX_EMU_LAYOUT_MODE=%d" % layout_mode] if layout_mode else []) + ["-shared", "-fPIC",
                                "-o", EMU_LIB, EMU_SRC])
     lib = ctypes.CDLL(EMU_LIB)
     lib.emu_pack_create.restype = ctypes.c_void_p
@@ -64,10 +65,10 @@ class EmuSim:
                "body_a_s": ("L", 6), "body_f_s": ("L", 6), "body_ft_s": ("L", 6), "joint_tau": ("D", 1),
                "joint_qdd": ("D", 1), "H": ("DD", 1), "L": ("DD", 1)}
 
-    def __init__(self, model, num_envs, es=1, path_passes=False, layout_mode=0):
+    def __init__(self, model, num_envs, es=1, path_passes=False, layout_mode=0, extra=()):
         """layout_mode: csrc/dfx_pack.h kLayoutCompact (1) | kLayoutHinvGlobal (2) -- the scratch layouts of the
         large-articulation tile kernels."""
-        self.lib = build_emu(es, path_passes, layout_mode)
+        self.lib = build_emu(es, path_passes, layout_mode, extra)     # extra: more g++ flags (A/B builds)
         self.desc, self.N = articulation_from_model(model, num_envs)
         err = ctypes.create_string_buffer(256)
         st = self.desc.as_struct()

@@ -245,3 +245,20 @@ def test_ant_65536_envs_equal_their_64_env_pattern():
     for a, b, w in zip(G[:3], g_small[:3], (Q, D, D)):
         ref = b.view(1, 64 * w).expand(rep, -1)
         assert (a.view(rep, 64 * w) - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("name", ["HumanoidEnv", "SNUHumanoidEnv"])
+def test_launch_plan_keeps_two_tiles_of_the_humanoids_per_sm(name):
+    """The large articulations run on 8-environment tiles with the compact scratch layouts (csrc/dfx_pack.h: mass-matrix
+    temporaries overlaid on the per-substep temporaries, H^-1 read from the tape by the adjoint): two CTAs stay resident
+    per SM, forward and adjoint, so that they hide each other's barrier waits."""
+    from diffrl_b200.engine import ArticulationEngine
+    d, model = load_golden(name)
+    eng = ArticulationEngine.from_model(model, "cuda:0", int(d["meta/num_envs"]))
+    assert int(eng.lib.dfx_pack_query(eng.pack, 9)) == 8
+    for bwd in (0, 1):
+        out = (ctypes.c_int * 6)()
+        assert eng.lib.dfx_launch_plan(eng.pack, bwd, out) == 0
+        lanes, envs_per_cta, ctas_per_sm, smem, stride, pack = list(out)
+        assert envs_per_cta == 8 and ctas_per_sm >= 2, list(out)
+        assert smem == pack + envs_per_cta * stride * 4 and (smem + 1024) * 2 <= 227 * 1024

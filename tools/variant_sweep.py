@@ -34,9 +34,11 @@ def select(variant):
     lib = _capi.lib()
     lib.dfx_set_tile_envs(0); lib.dfx_set_group_size(0); lib.dfx_set_flags(9)
     if variant.startswith("tile"):
-        lib.dfx_set_tile_envs(int(variant[4:].rstrip("L")))
+        lib.dfx_set_tile_envs(int(variant[4:].rstrip("LP")))
         if variant.endswith("L"):
             lib.dfx_set_flags(9 | 64)          # level-by-level tree recursions (alternative instantiation)
+        if variant.endswith("P"):
+            lib.dfx_set_flags(9 | 128)         # no L2 prefetch of the next tape row
     elif variant.startswith("group"):
         lib.dfx_set_flags(9 | 32); lib.dfx_set_group_size(int(variant[5:]))
 
@@ -61,7 +63,7 @@ def main():
                 eng = ArticulationEngine.from_model(model, dev, n0)
                 tile = int(eng.lib.dfx_pack_query(eng.pack, 9))
                 family = "tile%d" % tile if tile else "group"
-                if variant != "auto" and variant.startswith("tile") and family != variant.rstrip("L"):
+                if variant != "auto" and variant.startswith("tile") and family != variant.rstrip("LP"):
                     print(json.dumps({"env": name, "variant": variant, "skipped": "no tile kernel of this width"}), flush=True)
                     continue
                 err = {"q": 0.0, "gq": 0.0, "gact": 0.0, "gmusc": 0.0}
