@@ -14,6 +14,8 @@ using namespace dfx;
 
 namespace {
 
+constexpr int kMaxObs = 96;     // largest walker observation: Humanoid 76 (checked on the host before the launch)
+
 __device__ __forceinline__ void walker_features(const DfxWalkerParams& p, const float* q, const float* qd,
                                                 V3& pos, Q4& rot, V3& ang, V3& lin, V3& tt, float& tn, V3& tdir,
                                                 Q4& tq, V3& up, V3& heading) {
@@ -193,13 +195,18 @@ __global__ void walker_transition_forward_kernel(DfxWalkerParams p, int n, const
     const long long pr = progress[e] + 1;
     float r = 0.0f;
     long long rs = 0;
-    walker_eval(p, qe, qde, ae, pr, true, ob, &r, &rs);
+    // the observation is formed in a thread-local buffer (L1-resident local memory) and written out once: forming it in
+    // place in global memory put a store -> load round trip through L2 on the critical path of this latency-bound kernel
+    // (the validity check and the pass-through to obs_next both read it back)
+    float o[kMaxObs];
+    walker_eval(p, qe, qde, ae, pr, true, o, &r, &rs);
     rew[e] = r;
     reset[e] = rs;
     progress_next[e] = rs ? 0 : pr;
     float* qn = q_next + (size_t)e * p.num_q;
     float* qdn = qd_next + (size_t)e * p.num_qd;
     float* an = actions_next + (size_t)e * p.num_act;
+    for (int i = 0; i < p.num_obs; ++i) ob[i] = o[i];
     if (rs) {
         const float* sq = start_q + (size_t)e * p.num_q;
         const float* sqd = start_qd + (size_t)e * p.num_qd;
@@ -207,13 +214,13 @@ __global__ void walker_transition_forward_kernel(DfxWalkerParams p, int n, const
         for (int i = 0; i < p.num_qd; ++i) qdn[i] = sqd[i];
         for (int i = 0; i < p.num_act; ++i) an[i] = 0.0f;
         float r2; long long rs2;
-        walker_eval(p, sq, sqd, nullptr, 0, false, on, &r2, &rs2);
+        walker_eval(p, sq, sqd, nullptr, 0, false, o, &r2, &rs2);
     } else {
         for (int i = 0; i < p.num_q; ++i) qn[i] = qe[i];
         for (int i = 0; i < p.num_qd; ++i) qdn[i] = qde[i];
         for (int i = 0; i < p.num_act; ++i) an[i] = ae[i];
-        for (int i = 0; i < p.num_obs; ++i) on[i] = ob[i];
     }
+    for (int i = 0; i < p.num_obs; ++i) on[i] = o[i];
 }
 
 // cotangents of (obs_before, rew, q_next, qd_next, actions_next, obs_next), any of them NULL == 0, -> gq, gqd, gact.
@@ -442,7 +449,7 @@ int dfx_walker_transition_forward(const DfxWalkerParams* p, int n, const float* 
                                   float* obs_before, float* rew, long long* reset, float* q_next, float* qd_next,
                                   float* actions_next, long long* progress_next, float* obs_next, void* stream) {
     if (!p || n <= 0 || !q || !qd || !actions || !progress || !start_q || !start_qd || !obs_before || !rew || !reset ||
-        !q_next || !qd_next || !actions_next || !progress_next || !obs_next)
+        !q_next || !qd_next || !actions_next || !progress_next || !obs_next || p->num_obs > kMaxObs)
         return (int)cudaErrorInvalidValue;
     walker_transition_forward_kernel<<<(n + kEnvThreads - 1) / kEnvThreads, kEnvThreads, 0, (cudaStream_t)stream>>>(
         *p, n, q, qd, actions, progress, start_q, start_qd, obs_before, rew, reset, q_next, qd_next, actions_next,
