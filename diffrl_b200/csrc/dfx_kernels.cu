@@ -252,7 +252,7 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
     dfx_pack* p = new dfx_pack();
     std::string msg;
     if (!build_pack(*desc, p->host, msg)) { set_err(err, err_len, msg); delete p; return nullptr; }
-    if (p->host.int_off.size() != 25 || p->host.float_off.size() != 17) { set_err(err, err_len, "internal: pack field count"); delete p; return nullptr; }
+    if (p->host.int_off.size() != 26 || p->host.float_off.size() != 17) { set_err(err, err_len, "internal: pack field count"); delete p; return nullptr; }
     p->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_ints, p->host.ints.size() * sizeof(int) + 16);
@@ -263,7 +263,7 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
     p->header = p->host.header;
     p->blob.ints = p->d_ints; p->blob.floats = p->d_floats;
     p->blob.n_ints = (int)p->host.ints.size(); p->blob.n_floats = (int)p->host.floats.size();
-    for (int i = 0; i < 25; ++i) p->blob.int_off[i] = (int)p->host.int_off[i];
+    for (int i = 0; i < 26; ++i) p->blob.int_off[i] = (int)p->host.int_off[i];
     for (int i = 0; i < 17; ++i) p->blob.float_off[i] = (int)p->host.float_off[i];
     // flag bit 5 (32) keeps a supported articulation on the lane-group kernels (A/B runs); fixed per pack because
     // the two kernel families lay the tape out differently

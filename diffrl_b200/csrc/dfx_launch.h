@@ -16,7 +16,7 @@ struct PackBlob {
     const float* floats;
     int n_ints, n_floats;
     // offsets of each pointer field (same order as PackHost::bind)
-    int int_off[25];
+    int int_off[26];
     int float_off[17];
 };
 
@@ -31,7 +31,7 @@ __device__ __forceinline__ Pack bind_pack(const Pack& header, const PackBlob& b,
     p.chain_start = ib + b.int_off[ii++]; p.chain_links = ib + b.int_off[ii++];
     p.dof_link = ib + b.int_off[ii++]; p.cbody_start = ib + b.int_off[ii++]; p.cbody = ib + b.int_off[ii++];
     p.mstart = ib + b.int_off[ii++]; p.mlinks = ib + b.int_off[ii++];
-    p.aseg_start = ib + b.int_off[ii++]; p.aseg_way = ib + b.int_off[ii++]; p.morder = ib + b.int_off[ii++];
+    p.aseg_start = ib + b.int_off[ii++]; p.aseg_way = ib + b.int_off[ii++]; p.morder = ib + b.int_off[ii++]; p.mgrp_start = ib + b.int_off[ii++];
     p.X_pj = fb + b.float_off[fi++]; p.X_cm = fb + b.float_off[fi++]; p.axis = fb + b.float_off[fi++];
     p.I_c = fb + b.float_off[fi++]; p.mass = fb + b.float_off[fi++]; p.target_ke = fb + b.float_off[fi++];
     p.target_kd = fb + b.float_off[fi++]; p.limit_ke = fb + b.float_off[fi++]; p.limit_kd = fb + b.float_off[fi++];

@@ -21,6 +21,7 @@ struct Pack {
     int W;       // muscle way-points
     int nlev;    // tree depth
     int nround;  // rounds of the chain decomposition (below)
+    int MG;      // muscle groups (below)
     int ground;  // model.ground && C > 0
     float gx, gy, gz;
 
@@ -73,11 +74,15 @@ struct Pack {
     const int* mstart;       // (M+1)
     const int* mlinks;       // (W) local link index
     // only the segments whose two way-points sit on DIFFERENT links pull (reference sim.py:1231: l0 == l1 -> skip): the pack
-    // lists them per muscle (the SNU model: 198 of 484 segments, 1-2 per muscle), and orders the muscles by their count
-    // so that the item slots of a warp run the same number of iterations
+    // lists them per muscle (the SNU model: 198 of 484 segments, 1-2 per muscle).  Muscles whose active segments connect
+    // the SAME links (in the same order) form GROUPS of at most 8 segment evaluations: an item slot walks a group, loads the two link
+    // transforms (and, in the adjoint, the two wrench cotangents) once, sums the members' wrenches in registers and
+    // scatters ONE wrench per link and segment position instead of one per muscle (the fixed-point scatter is half of a
+    // muscle's instructions).  Groups are sorted by size, largest first.
     const int* aseg_start;   // (M+1) offsets into aseg_way
     const int* aseg_way;     // way-point index i of an active segment (i, i+1)
-    const int* morder;       // (M) item k works on muscle morder[k]
+    const int* morder;       // (M) muscles sorted by group
+    const int* mgrp_start;   // (MG+1) offsets into morder
     const float* mpoints;    // (W,3)
 };
 

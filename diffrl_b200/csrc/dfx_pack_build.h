@@ -59,6 +59,7 @@ struct PackHost {
         p.aseg_start = ibase + int_off[ii++];
         p.aseg_way = ibase + int_off[ii++];
         p.morder = ibase + int_off[ii++];
+        p.mgrp_start = ibase + int_off[ii++];
         p.X_pj = fbase + float_off[fi++];
         p.X_cm = fbase + float_off[fi++];
         p.axis = fbase + float_off[fi++];
@@ -241,8 +242,39 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
         for (int i = mstart[m]; i < mstart[m + 1] - 1; ++i) if (mlinks[i] != mlinks[i + 1]) aseg_way.push_back(i);
     }
     if (M > 0) aseg_start[M] = (int)aseg_way.size();
-    for (int cnt = 0, placed = 0; placed < M; ++cnt)
-        for (int m = 0; m < M; ++m) if (aseg_start[m + 1] - aseg_start[m] == cnt) { morder.push_back(m); ++placed; }
+    // muscle groups: same (l0, l1) for every active segment; a group's work (members x active segments) is capped at
+    // kMaxEvals segment evaluations and the members of a key are split evenly (SNU: 32 groups of <= 8 evaluations, 96
+    // wrench scatters per substep instead of 396)
+    constexpr int kMaxEvals = 8;
+    std::vector<std::vector<int>> mgroups;
+    {
+        std::vector<std::vector<int>> keys(M);
+        for (int m = 0; m < M; ++m)
+            for (int j = aseg_start[m]; j < aseg_start[m + 1]; ++j) { keys[m].push_back(mlinks[aseg_way[j]]); keys[m].push_back(mlinks[aseg_way[j] + 1]); }
+        std::vector<char> taken(M, 0);
+        for (int m = 0; m < M; ++m) {
+            if (taken[m]) continue;
+            std::vector<int> same;
+            for (int k = m; k < M; ++k) if (!taken[k] && keys[k] == keys[m]) { same.push_back(k); taken[k] = 1; }
+            const int nseg = (int)keys[m].size() / 2;
+            const int cap = nseg > 0 ? (kMaxEvals / nseg > 0 ? kMaxEvals / nseg : 1) : (int)same.size();
+            const int parts = ((int)same.size() + cap - 1) / cap;
+            const int base = (int)same.size() / parts, extra = (int)same.size() % parts;
+            for (int pi = 0, at = 0; pi < parts; ++pi) {
+                const int cnt = base + (pi < extra ? 1 : 0);
+                mgroups.emplace_back(same.begin() + at, same.begin() + at + cnt);
+                at += cnt;
+            }
+        }
+        // most work first (stable): the first round of item slots gets the long walks, a second one the short ones
+        auto work = [&](const std::vector<int>& grp) { return (int)grp.size() * (int)keys[grp[0]].size(); };
+        for (size_t a = 1; a < mgroups.size(); ++a)
+            for (size_t b = a; b > 0 && work(mgroups[b]) > work(mgroups[b - 1]); --b) std::swap(mgroups[b], mgroups[b - 1]);
+    }
+    std::vector<int> mgrp_start;
+    for (const auto& grp : mgroups) { mgrp_start.push_back((int)morder.size()); morder.insert(morder.end(), grp.begin(), grp.end()); }
+    mgrp_start.push_back((int)morder.size());
+    h.MG = (int)mgroups.size();
     std::vector<float> Ic(L * 9), mass(L);
     for (int i = 0; i < L; ++i) {
         const float* I = d.body_I_m + i * 36;
@@ -252,7 +284,7 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
     push_i(type); push_i(parent); push_i(qs); push_i(ds); push_i(level_start); push_i(level_links);
     push_i(child_start); push_i(child_idx); push_i(anc_start); push_i(anc_dofs); push_i(sub_start);
     push_i(sub_links); push_i(path_start); push_i(path_links); push_i(round_start); push_i(chain_start); push_i(chain_links);
-    push_i(dof_link); push_i(cbody_start); push_i(cbody); push_i(mstart); push_i(mlinks); push_i(aseg_start); push_i(aseg_way); push_i(morder);
+    push_i(dof_link); push_i(cbody_start); push_i(cbody); push_i(mstart); push_i(mlinks); push_i(aseg_start); push_i(aseg_way); push_i(morder); push_i(mgrp_start);
     auto vec = [](const float* p, int n) { return p ? std::vector<float>(p, p + n) : std::vector<float>(n, 0.0f); };
     push_f(vec(d.joint_X_pj, L * 7)); push_f(vec(d.joint_X_cm, L * 7)); push_f(vec(d.joint_axis, L * 3));
     push_f(Ic); push_f(mass);

@@ -832,21 +832,30 @@ DFX_HD void muscle_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const SPi lo = sp_int(s + Y.fx);
     const SPi hi = lo + P.L * 6;
     const SPu poison = sp_uint(s + Y.cmask);
-    DFX_FOR(k, P.M) {
-        const int m = P.morder[k];
-        const float act = s[Y.musc + m];
-        for (int j = P.aseg_start[m]; j < P.aseg_start[m + 1]; ++j) {      // the segments that span two links
-            const int i = P.aseg_way[j];
-            const int l0 = P.mlinks[i], l1 = P.mlinks[i + 1];
-            const V3 p0 = xf_point(ld7(s + Y.Xsc + l0 * 7), ld3(P.mpoints + i * 3));
-            const V3 p1 = xf_point(ld7(s + Y.Xsc + l1 * 7), ld3(P.mpoints + (i + 1) * 3));
-            const V3 d = p1 - p0;
-            const float len = sqrtf(dot(d, d));
-            const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
-            const V3 f = n * act;
-            const V3 t0 = cross(p0, f), t1 = cross(p1, f);
-            const float w0[6] = {-t0.x, -t0.y, -t0.z, -f.x, -f.y, -f.z};
-            const float w1[6] = {t1.x, t1.y, t1.z, f.x, f.y, f.z};
+    DFX_FOR(gi, P.MG) {        // one item = a group of muscles whose active segments connect the same links
+        const int mb = P.mgrp_start[gi], me = P.mgrp_start[gi + 1];
+        const int m0 = P.morder[mb];
+        const int nseg = P.aseg_start[m0 + 1] - P.aseg_start[m0];
+        for (int j = 0; j < nseg; ++j) {
+            const int i0 = P.aseg_way[P.aseg_start[m0] + j];
+            const int l0 = P.mlinks[i0], l1 = P.mlinks[i0 + 1];
+            const Xf X0 = ld7(s + Y.Xsc + l0 * 7), X1 = ld7(s + Y.Xsc + l1 * 7);
+            V3 fs = v3zero(), t0s = v3zero(), t1s = v3zero();
+            for (int k = mb; k < me; ++k) {
+                const int m = P.morder[k];
+                const int i = P.aseg_way[P.aseg_start[m] + j];
+                const V3 p0 = xf_point(X0, ld3(P.mpoints + i * 3));
+                const V3 p1 = xf_point(X1, ld3(P.mpoints + (i + 1) * 3));
+                const V3 d = p1 - p0;
+                const float len = sqrtf(dot(d, d));
+                const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
+                const V3 f = n * s[Y.musc + m];
+                fs += f;
+                t0s += cross(p0, f);
+                t1s += cross(p1, f);
+            }
+            const float w0[6] = {-t0s.x, -t0s.y, -t0s.z, -fs.x, -fs.y, -fs.z};
+            const float w1[6] = {t1s.x, t1s.y, t1s.z, fs.x, fs.y, fs.z};
             fx_scatter(lo + l0 * 6, hi + l0 * 6, poison, l0, w0, kFxForward, g);
             fx_scatter(lo + l1 * 6, hi + l1 * 6, poison, l1, w1, kFxForward, g);
         }
@@ -859,39 +868,47 @@ DFX_HD void muscle_adj(const Pack& P, const Layout& Y, SP s, float scale, const 
     const SPi lo = sp_int(s + Y.aXsc);   // still all-zero in this phase: doubles as the low words
     const SPi hi = sp_int(s + Y.fxH);
     const SPu poison = sp_uint(s + Y.cmask);
-    DFX_FOR(k, P.M) {
-        const int m = P.morder[k];
-        const float act = s[Y.musc + m];
-        float aact = 0.0f;
-        for (int j = P.aseg_start[m]; j < P.aseg_start[m + 1]; ++j) {
-            const int i = P.aseg_way[j];
-            const int l0 = P.mlinks[i], l1 = P.mlinks[i + 1];
+    DFX_FOR(gi, P.MG) {
+        const int mb = P.mgrp_start[gi], me = P.mgrp_start[gi + 1];
+        const int m0 = P.morder[mb];
+        const int nseg = P.aseg_start[m0 + 1] - P.aseg_start[m0];
+        for (int j = 0; j < nseg; ++j) {
+            const int i0 = P.aseg_way[P.aseg_start[m0] + j];
+            const int l0 = P.mlinks[i0], l1 = P.mlinks[i0 + 1];
             const Xf X0 = ld7(s + Y.Xsc + l0 * 7), X1 = ld7(s + Y.Xsc + l1 * 7);
-            const V3 r0 = ld3(P.mpoints + i * 3), r1 = ld3(P.mpoints + (i + 1) * 3);
-            const V3 p0 = xf_point(X0, r0), p1 = xf_point(X1, r1);
-            const V3 d = p1 - p0;
-            const float len = sqrtf(dot(d, d));
-            const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
-            const V3 f = n * act;
             const SV c0 = ld6(s + Y.af + l0 * 6), c1 = ld6(s + Y.af + l1 * 6);
-            // L = -c0.(p0 x f, f) + c1.(p1 x f, f)
-            V3 af = c1.v - c0.v + cross(c1.w, p1) - cross(c0.w, p0);
-            V3 ap0 = -cross(f, c0.w);
-            V3 ap1 = cross(f, c1.w);
-            aact += dot(n, af);
-            const V3 an = af * act;
-            if (len > 0.0f) {
-                const V3 ad = (an - n * dot(n, an)) * (1.0f / len);
-                ap1 += ad;
-                ap0 -= ad;
+            V3 ap0s = v3zero(), ap1s = v3zero();
+            Q4 aq0s = qzero(), aq1s = qzero();
+            for (int k = mb; k < me; ++k) {
+                const int m = P.morder[k];
+                const int i = P.aseg_way[P.aseg_start[m] + j];
+                const float act = s[Y.musc + m];
+                const V3 r0 = ld3(P.mpoints + i * 3), r1 = ld3(P.mpoints + (i + 1) * 3);
+                const V3 p0 = xf_point(X0, r0), p1 = xf_point(X1, r1);
+                const V3 d = p1 - p0;
+                const float len = sqrtf(dot(d, d));
+                const V3 n = len > 0.0f ? V3{d.x / len, d.y / len, d.z / len} : v3zero();
+                const V3 f = n * act;
+                // L = -c0.(p0 x f, f) + c1.(p1 x f, f)
+                const V3 af = c1.v - c0.v + cross(c1.w, p1) - cross(c0.w, p0);
+                V3 ap0 = -cross(f, c0.w);
+                V3 ap1 = cross(f, c1.w);
+                s[Y.amusc + m] += dot(n, af);
+                const V3 an = af * act;
+                if (len > 0.0f) {
+                    const V3 ad = (an - n * dot(n, an)) * (1.0f / len);
+                    ap1 += ad;
+                    ap0 -= ad;
+                }
+                ap0s += ap0; ap1s += ap1;
+                aq0s += qrot_adj_q(X0.q, r0, ap0);
+                aq1s += qrot_adj_q(X1.q, r1, ap1);
             }
-            const Q4 aq0 = qrot_adj_q(X0.q, r0, ap0), aq1 = qrot_adj_q(X1.q, r1, ap1);
-            const float g0[7] = {ap0.x, ap0.y, ap0.z, aq0.x, aq0.y, aq0.z, aq0.w};
-            const float g1[7] = {ap1.x, ap1.y, ap1.z, aq1.x, aq1.y, aq1.z, aq1.w};
+            const float g0[7] = {ap0s.x, ap0s.y, ap0s.z, aq0s.x, aq0s.y, aq0s.z, aq0s.w};
+            const float g1[7] = {ap1s.x, ap1s.y, ap1s.z, aq1s.x, aq1s.y, aq1s.z, aq1s.w};
             fx_scatter(lo + l0 * 7, hi + l0 * 7, poison, l0, g0, scale, g);
             fx_scatter(lo + l1 * 7, hi + l1 * 7, poison, l1, g1, scale, g);
         }
-        s[Y.amusc + m] += aact;
     }
 }
 
