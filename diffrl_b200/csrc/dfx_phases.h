@@ -153,20 +153,22 @@ DFX_HD void level_tasks(const Pack& P, SP s, int lev, bool lead, const Grp& g, F
 // Tree recursions by CHAINS (dfx_pack.h): a chain of links without side branches is walked by ONE thread, so consecutive
 // links need no barrier; chains that hang below other chains run in an earlier round.  One barrier per round (2-3) instead
 // of one per tree level (Humanoid: 10), the same per-link operations in the same order.
+// `lead`: what the chains read was last written under group-level barriers only (lane-group kernels spread the tasks of a
+// round over the whole CTA: the first round then needs a CTA-wide barrier in front)
 template <class Grp, class F>
-DFX_HD void chain_rounds_up(const Pack& P, SP s, const Grp& g, F f) {        // leaves -> root
+DFX_HD void chain_rounds_up(const Pack& P, SP s, const Grp& g, F f, bool lead = false) {        // leaves -> root
     for (int r = 0; r < P.nround; ++r) {
         const int b = P.round_start[r], e = P.round_start[r + 1];
-        g.cta_tasks(s, e - b, false, [&](SP se, int k) {
+        g.cta_tasks(s, e - b, lead && r == 0, [&](SP se, int k) {
             for (int j = P.chain_start[b + k]; j < P.chain_start[b + k + 1]; ++j) f(se, P.chain_links[j]);
         });
     }
 }
 template <class Grp, class F>
-DFX_HD void chain_rounds_down(const Pack& P, SP s, const Grp& g, F f) {      // root -> leaves
+DFX_HD void chain_rounds_down(const Pack& P, SP s, const Grp& g, F f, bool lead = false) {      // root -> leaves
     for (int r = P.nround - 1; r >= 0; --r) {
         const int b = P.round_start[r], e = P.round_start[r + 1];
-        g.cta_tasks(s, e - b, false, [&](SP se, int k) {
+        g.cta_tasks(s, e - b, lead && r == P.nround - 1, [&](SP se, int k) {
             for (int j = P.chain_start[b + k + 1] - 1; j >= P.chain_start[b + k]; --j) f(se, P.chain_links[j]);
         });
     }
@@ -308,19 +310,12 @@ DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
         DFX_FOR(i, P.L) kin_velocity_path_fwd(P, Y, s, i);
         g.sync();
     } else {
-        // cheap group barriers, possibly deep trees: level-by-level recursions (root -> leaf)
-        for (int lev = 0; lev < P.nlev; ++lev) {
-            const int b = P.level_start[lev], e = P.level_start[lev + 1];
-            for (int k = b + g.lane; k < e; k += Grp::G) kin_chain_fwd(P, Y, s, P.level_links[k]);
-            g.sync();
-        }
+        // root -> leaf recursions by chains: one barrier per round, each link multiplies ONE transform (O(L) work; the path
+        // passes above do O(L * depth) to save the rounds' barriers)
+        chain_rounds_down(P, s, g, [&](SP se, int i) { kin_chain_fwd(P, Y, se, i); }, true);
         DFX_FOR(i, P.L) kin_motion_fwd<false>(P, Y, s, i);
         g.sync();
-        for (int lev = 0; lev < P.nlev; ++lev) {
-            const int b = P.level_start[lev], e = P.level_start[lev + 1];
-            for (int k = b + g.lane; k < e; k += Grp::G) kin_velocity_fwd(P, Y, s, P.level_links[k]);
-            g.sync();
-        }
+        chain_rounds_down(P, s, g, [&](SP se, int i) { kin_velocity_fwd(P, Y, se, i); }, true);
     }
 }
 
@@ -963,11 +958,7 @@ DFX_HD void tau_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
         DFX_FOR(i, P.L) tau_project_fwd<true>(P, Y, s, i);
         g.sync();
     } else {
-        for (int lev = P.nlev - 1; lev >= 0; --lev) {
-            const int b = P.level_start[lev], e = P.level_start[lev + 1];
-            for (int k = b + g.lane; k < e; k += Grp::G) tau_accum_fwd(P, Y, s, P.level_links[k]);
-            g.sync();
-        }
+        chain_rounds_up(P, s, g, [&](SP se, int i) { tau_accum_fwd(P, Y, se, i); }, true);
         DFX_FOR(i, P.L) tau_project_fwd<false>(P, Y, s, i);
         g.sync();
     }
@@ -1177,10 +1168,17 @@ DFX_HD void solve_adj(const Pack& P, const Layout& Y, SP s, HinvView hv, const G
     const int D = P.D;
     if (hv.g) {
         DFX_FOR(i, D) {
+            // (rows come from L2: keep many loads in flight -- with 4 at a time the 27 loads of a Humanoid row cost 7 round trips)
             const float* row = hv.g + (long long)i * D * hv.hs;
             float acc = 0.0f;
-#pragma unroll 4
-            for (int j = 0; j < D; ++j) acc += row[(long long)j * hv.hs] * s[Y.aqdd + j];
+#pragma unroll 1
+            for (int j0 = 0; j0 < D; j0 += 14) {
+                float h[14];
+#pragma unroll
+                for (int k = 0; k < 14; ++k) h[k] = (j0 + k < D) ? row[(long long)(j0 + k) * hv.hs] : 0.0f;
+#pragma unroll
+                for (int k = 0; k < 14; ++k) if (j0 + k < D) acc += h[k] * s[Y.aqdd + j0 + k];
+            }
             s[Y.tau + i] = acc;
         }
     } else {
