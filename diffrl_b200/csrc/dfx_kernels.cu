@@ -133,11 +133,13 @@ struct GroupCuda {
             for (int i = lane; i < n; i += G_) dst[i] = src[i];
         }
     }
-    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, const float* src, const RowFmt& f, const float* stage, bool first) const {
-        (void)stage;
+    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, const float* src, const RowFmt& f, const float* stage, bool first, bool fenced = false) const {
+        (void)stage; (void)fenced;
         if (!first) block_out(base, b, N, env, src, f.n, true);     // no asynchronous stores here: the whole row at once (always fp32)
     }
     __device__ __forceinline__ void row_unpack(float* dst, float* stage, const RowFmt& f) const { (void)dst; (void)stage; (void)f; }
+    __device__ __forceinline__ void pre_store() const {}
+    __device__ __forceinline__ void store_sync() const { __syncwarp(mask); }      // the group's row copy before integrate overwrites q, qd
     __device__ __forceinline__ void row_reusable() const {}
     __device__ __forceinline__ void finish() const {}
     static constexpr bool kBulkRows = false;

@@ -22,6 +22,7 @@ struct Pack {
     int nlev;    // tree depth
     int nround;  // rounds of the chain decomposition (below)
     int MG;      // muscle groups (below)
+    int root_round_single;   // the last chain round holds nothing but single-link chains of roots (a root -> leaf recursion skips it)
     int ground;  // model.ground && C > 0
     float gx, gy, gz;
 

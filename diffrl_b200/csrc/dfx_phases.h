@@ -110,14 +110,19 @@ struct GroupSerial {  // host / single-lane execution
     // with the second call.)
     // (the host emulation keeps the fp32 tape layout and only ROUNDS the middle through bf16 when f.bf16 is set: the
     //  same values the tile kernels read back from a bf16 tape)
-    DFX_HD void block_out_part(float* base, long long b, int N, int env, SP src, const RowFmt& f, SP stage, bool first) const {
-        (void)stage;
+    DFX_HD void block_out_part(float* base, long long b, int N, int env, SP src, const RowFmt& f, SP stage, bool first, bool fenced = false) const {
+        (void)stage; (void)fenced;
         float* d = base + (b * N + env) * f.n;
         if (first) { for (int i = 0; i < f.early; ++i) d[i] = src[i]; }
         else { for (int i = f.early; i < f.n; ++i) d[i] = (f.bf16 && i >= f.head && i < f.tail) ? bf16_round(src[i]) : src[i]; }
     }
     DFX_HD void row_unpack(SP dst, SP stage, const RowFmt& f) const { (void)dst; (void)stage; (void)f; }
     DFX_HD void row_reusable() const {}        // every asynchronous store has finished READING the scratch
+    // pre_store(): called by every thread before the barrier that precedes a block_out_part(..., fenced = true): policies
+    // with asynchronous (bulk) stores publish their scratch writes to the async proxy here, so that the store can be issued
+    // right after that barrier without a fence + barrier of its own
+    DFX_HD void pre_store() const {}
+    DFX_HD void store_sync() const {}          // orders a synchronous tape store before the scratch is overwritten (no-op for bulk stores)
     DFX_HD void finish() const {}
     static constexpr bool kBulkRows = false;   // true: env_step_backward moves rows with rows_in() (TMA bulk copies)
     DFX_HD void block_in(SP dst, const float* base, long long b, int N, int env, int n, bool rows) const {
@@ -165,10 +170,12 @@ DFX_HD void chain_rounds_up(const Pack& P, SP s, const Grp& g, F f, bool lead = 
     }
 }
 template <class Grp, class F>
-DFX_HD void chain_rounds_down(const Pack& P, SP s, const Grp& g, F f, bool lead = false) {      // root -> leaves
-    for (int r = P.nround - 1; r >= 0; --r) {
+DFX_HD void chain_rounds_down(const Pack& P, SP s, const Grp& g, F f, bool lead = false, bool skip_roots = false) {      // root -> leaves
+    // skip_roots: f() does nothing for a root (it only pulls from the parent): a top round of lone roots is skipped
+    const int top = P.nround - 1 - ((skip_roots && P.root_round_single && P.nround > 1) ? 1 : 0);
+    for (int r = top; r >= 0; --r) {
         const int b = P.round_start[r], e = P.round_start[r + 1];
-        g.cta_tasks(s, e - b, lead && r == P.nround - 1, [&](SP se, int k) {
+        g.cta_tasks(s, e - b, lead && r == top, [&](SP se, int k) {
             for (int j = P.chain_start[b + k + 1] - 1; j >= P.chain_start[b + k]; --j) f(se, P.chain_links[j]);
         });
     }
@@ -326,11 +333,13 @@ DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
 //   A3 (parallel)   adjoint of v_j = S qd and of S(X_sj): aS, aqd, aX_sj and its push to the parent (pX slot)
 //   A4 (leaf->root) aXsc totals (children's pushes gathered); push of this link to its parent -> pX
 //   A5 (parallel)   adjoint of X_l = X_pj X_jc(q) -> aq
+// A1 runs as the tail of the rigid-body force adjoint of the SAME link (body_force_link_adj: aXsm[i] is final there and
+// everything A1 touches is private to the link): it leaves the link's contribution to aXsc in the aXsm slot -- A4 adds it --
+// so it never races with the contact / muscle cotangents that other threads scatter into aXsc at the same time.
 DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, SP s, int i) {    // A1
-    const SP aX = s + Y.aXsc + i * 7;
-    Xf acc = ld7(aX);
+    Xf acc = xf_zero();
     xf_mul_adj_a(ld7(s + Y.Xsc + i * 7), ld7(P.X_cm + i * 7), ld7(s + Y.aXsm + i * 7), acc);
-    st7(aX, acc);
+    st7(s + Y.aXsm + i * 7, acc);                       // from here on: d/dX_sc[i] through X_sm = X_sc X_cm
     st7(s + Y.Xl + i * 7, xf_mul(ld7(P.X_pj + i * 7), joint_transform(P, s + Y.q, i)));
     const int type = P.type[i], ds = P.qd_start[i];
     const SP qd = s + Y.qd;
@@ -396,6 +405,7 @@ DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // 
 DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, SP s, int i) {     // A4
     const int par = P.parent[i];
     Xf aXsc = ld7(s + Y.aXsc + i * 7);
+    aXsc += ld7(s + Y.aXsm + i * 7);                                      // A1's share (through X_sm)
     for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) aXsc += ld7(s + Y.pX + P.child_idx[k] * 7);
     st7(s + Y.aXsc + i * 7, aXsc);                       // total, consumed by A5
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
@@ -424,8 +434,8 @@ DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // 
 template <class Grp>
 DFX_HD void kin_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     // all five passes run as CTA-wide (link, environment) tasks, link-major: uniform joint types per warp
-    g.cta_tasks(s, P.L, true, [&](SP se, int i) { kin_adj_local(P, Y, se, i); });
-    chain_rounds_up(P, s, g, [&](SP se, int i) { kin_adj_velocity(P, Y, se, i); });
+    // (A1 already ran inside the rigid-body force adjoint)
+    chain_rounds_up(P, s, g, [&](SP se, int i) { kin_adj_velocity(P, Y, se, i); }, true);
     g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_motion(P, Y, se, i); });
     chain_rounds_up(P, s, g, [&](SP se, int i) { kin_adj_chain(P, Y, se, i); });
     g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_joint(P, Y, se, i); });
@@ -541,6 +551,7 @@ DFX_HD void body_force_link_adj(const Pack& P, const Layout& Y, SP s, int i, con
         add6(s + Y.av + i * 6, av);
     }
     add6(s + Y.aa + i * 6, aa);
+    kin_adj_local(P, Y, s, i);      // A1 of the kinematics adjoint, same link
 }
 
 template <class Grp>
@@ -1010,7 +1021,7 @@ template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, SP s, SP atau, const Grp& g) {
     const int atau_off = (int)(atau - s);   // (element offset inside the scratch)
     g.cta_tasks(s, P.L, true, [&](SP se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
-    chain_rounds_down(P, s, g, [&](SP se, int i) { tau_accum_adj(P, Y, se, i); });
+    chain_rounds_down(P, s, g, [&](SP se, int i) { tau_accum_adj(P, Y, se, i); }, false, true);
 }
 
 // =====================================================================================
@@ -1156,6 +1167,7 @@ DFX_HD void solve_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
         for (int j = 0; j < D; ++j) acc += s[Y.A + i * D + j] * s[Y.tau + j];
         s[Y.qdd + i] = acc;
     }
+    g.pre_store();         // the row's intermediates and q'' leave for the tape right after this barrier
     g.sync();
 }
 // the cotangent of H is kept SYMMETRISED and packed (upper triangle, row-major): only aH + aH^T enters crba_adj, because
@@ -1195,7 +1207,7 @@ DFX_HD void solve_adj(const Pack& P, const Layout& Y, SP s, HinvView hv, const G
         row[0] -= ti * qi;
         for (int j = i + 1; j < D; ++j) row[j - i] -= ti * s[Y.qdd + j] + s[Y.tau + j] * qi;
     }
-    g.sync();
+    // (no barrier here: the caller's next one -- substep_adj waits for the bulk of the tape row -- comes before any reader of Hs, tau)
 }
 
 // adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), from the symmetrised cotangent Hs
@@ -1280,6 +1292,7 @@ DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, SP s, float dt, i
 template <class Grp>
 DFX_HD void integrate_fwd(const Pack& P, const Layout& Y, SP s, float dt, const Grp& g) {
     DFX_FOR(i, P.L) integrate_link_fwd(P, Y, s, dt, i);
+    g.pre_store();         // (q, qd) of the next substep leave for the tape right after this barrier
     g.sync();
 }
 
@@ -1348,7 +1361,7 @@ template <class Grp>
 DFX_HD void substep_adj(const Pack& P, const Layout& Y, SP s, float dt, bool apply_crba, HinvView hv, const RowFmt& rf, const Grp& g) {
     zero_range(s + Y.aXsc, P.L * 32 + P.D * 6, g);      // aXsc, av, aXsm, aS, aa are adjacent (af is overwritten by tau_adj)
     zero_range(s + Y.aIbar, P.L * 12, g);
-    g.sync();
+    // (no barrier: integrate_adj and solve_adj do not touch the zeroed accumulators, and two barriers follow before their first use)
     // phase_sync(): CTA-wide barrier that keeps the warps of a CTA inside the same phase, so that the
     // instruction working set per SM is one or two phases (~10 KB each) instead of the whole 140 KB body
     integrate_adj(P, Y, s, dt, g);

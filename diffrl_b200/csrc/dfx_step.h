@@ -63,10 +63,13 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
     for (int i = Y.qdd + D + g.lane; i < Y.q + Y.tape_row; i += Grp::G) s[i] = 0.0f;   // row padding
     if (g.lane == 0) s[Y.cmask] = 0.0f;
     DFX_FOR(i, P.L * 12) s[Y.fx + i] = 0.0f;   // fixed-point wrench accumulators (L x 6 low + high words)
+    g.pre_store();
     g.sync();
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
-        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, rf, s + Y.stage, true);    // (q, qd) ENTERING this substep
+        // (q, qd) ENTERING this substep: every thread fenced its writes before the barrier that closed the previous
+        // integrate_fwd (or the loads above), so the store is issued without a barrier of its own
+        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, rf, s + Y.stage, true, true);
         kin_fwd(P, Y, s, g);
         g.phase_sync();
         body_and_contact_fwd(P, Y, s, g);
@@ -90,10 +93,12 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
             }
         }
         solve_fwd(P, Y, s, g);
-        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, rf, s + Y.stage, false);   // the forward intermediates and q''
+        // the forward intermediates and q'': fenced before solve_fwd's closing barrier (a bf16 tape converts first and
+        // fences again)
+        if (a.tape) g.block_out_part(a.tape, sub, a.N, env, s + Y.q, rf, s + Y.stage, false, !rf.bf16);
         if (a.has_derived && sub == a.substeps - 1) dump_derived(P, Y, s, a.derived, env, true, g);
-        g.phase_sync();   // (also orders the tape / dump copies above before integrate_fwd overwrites q, qd)
-        g.sync();
+        g.phase_sync();
+        g.store_sync();   // (synchronous tape stores / dumps above must finish before integrate_fwd overwrites q, qd)
         integrate_fwd(P, Y, s, a.dt_sub, g);
     }
     DFX_FOR(i, Q) a.q_out[(long long)env * Q + i] = s[Y.q + i];

@@ -166,7 +166,8 @@ struct GroupTile {
     }
     // a tape row as bulk stores: (q, qd) when the substep starts; the intermediates and q'' when they exist.  With a bf16
     // tape the middle is first converted into the staging area (flat: the tile's [head, tail) x E floats are contiguous).
-    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, SP src, const RowFmt& f, SP stage, bool first) const {
+    // `fenced`: every thread called pre_store() before the CTA's last barrier and nothing the store reads was written since
+    __device__ __forceinline__ void block_out_part(float* base, long long b, int N, int env, SP src, const RowFmt& f, SP stage, bool first, bool fenced = false) const {
         (void)N; (void)env;
         float* sm = sp_raw(src) - e;
         float* st = sp_raw(stage) - e;
@@ -175,8 +176,10 @@ struct GroupTile {
             __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(st);
             for (int i = threadIdx.x; i < (f.tail - f.head) * E / 2; i += NW * 32) out[i] = __float22bfloat162_rn(in[i]);
         }
-        fence_async_smem();
-        __syncthreads();
+        if (!fenced) {
+            fence_async_smem();
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
             float* d = base + ((b * ntiles + tile) * f.units) * E;
             if (first) {
@@ -192,6 +195,8 @@ struct GroupTile {
             bulk_commit();
         }
     }
+    __device__ __forceinline__ void pre_store() const { fence_async_smem(); }
+    __device__ __forceinline__ void store_sync() const {}
     // called before the first barrier after which the scratch row (and H^-1) may be overwritten again
     __device__ __forceinline__ void row_reusable() const { if (threadIdx.x == 0) bulk_wait_read_all(); }
     __device__ __forceinline__ void finish() const { if (threadIdx.x == 0) bulk_wait_read_all(); }
