@@ -6,7 +6,7 @@ product entry point goes through :func:`lib`.
 import ctypes
 import os
 
-from .modelpack import DfxDerived, DfxModelDesc
+from .modelpack import DfxActionMap, DfxDerived, DfxModelDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DFX_LIBRARY points at another build of the SAME C ABI (same-box A/B timing of two kernel versions); never a fallback
@@ -51,6 +51,11 @@ def lib():
                                    _F, _F, _F, _F, _F, _F, _F, ctypes.POINTER(DfxDerived), ctypes.c_void_p]
     L.dfx_step_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                     _F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_void_p]
+    if hasattr(L, "dfx_step_forward_mapped"):
+        L.dfx_step_forward_mapped.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                              _F, _F, ctypes.POINTER(DfxActionMap), _F, _F, _F, _F, _F, _F, ctypes.c_void_p]
+        L.dfx_step_backward_mapped.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                               ctypes.POINTER(DfxActionMap), _F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_void_p]
     if os.environ.get("DFX_FLAGS"):      # tuning flags of include/dfx.h (A/B runs of the test-suite)
         L.dfx_set_flags(int(os.environ["DFX_FLAGS"]))
     _lib = L

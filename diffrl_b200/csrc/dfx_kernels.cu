@@ -446,6 +446,35 @@ int dfx_launch_plan(const dfx_pack_t* p, int backward, int out[6]) {
     return 0;
 }
 
+static int run_step(const dfx_pack_t* p, StepArgs& a, bool backward, void* stream) {
+    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, a.N), a.substeps, a.mm_freq, p->bf16 != 0).hinv_base;
+    a.tape_bf16 = p->bf16;
+    a.flags = g_flags;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->tile) return (int)launch_tile(p, a, backward, st);
+    if (backward) {
+        switch (pick_group(p)) {
+            case 8: return (int)launch<8, true>(p, a, st);
+            case 16: return (int)launch<16, true>(p, a, st);
+            default: return (int)launch<32, true>(p, a, st);
+        }
+    }
+    switch (pick_group(p)) {
+        case 8: return (int)launch<8, false>(p, a, st);
+        case 16: return (int)launch<16, false>(p, a, st);
+        default: return (int)launch<32, false>(p, a, st);
+    }
+}
+
+static bool bind_map(const dfx_pack_t* p, const DfxActionMap* m, StepArgs& a) {
+    const int width = m->is_muscle ? p->header.M : p->header.D;
+    if (m->num_act <= 0 || m->offset < 0 || m->offset + m->num_act > width || !m->strength) return false;
+    a.map_num_act = m->num_act; a.map_offset = m->offset; a.map_muscle = m->is_muscle ? 1 : 0;
+    a.map_pre_scale = m->pre_scale; a.map_pre_bias = m->pre_bias; a.map_drive_scale = m->drive_scale;
+    a.strength = m->strength;
+    return true;
+}
+
 int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
                      const float* q, const float* qd, const float* act, const float* musc,
                      float* q_out, float* qd_out, float* tape, const DfxDerived* derived, void* stream) {
@@ -457,16 +486,7 @@ int dfx_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, doub
     a.dt_sub = (float)(dt / (double)substeps);
     a.q = q; a.qd = qd; a.act = act; a.musc = musc; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
     if (derived) { a.derived = *derived; a.has_derived = 1; }
-    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq, p->bf16 != 0).hinv_base;
-    a.tape_bf16 = p->bf16;
-    a.flags = g_flags;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p->tile) return (int)launch_tile(p, a, false, st);
-    switch (pick_group(p)) {
-        case 8: return (int)launch<8, false>(p, a, st);
-        case 16: return (int)launch<16, false>(p, a, st);
-        default: return (int)launch<32, false>(p, a, st);
-    }
+    return run_step(p, a, false, stream);
 }
 
 int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
@@ -481,16 +501,39 @@ int dfx_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, dou
     a.dt_sub = (float)(dt / (double)substeps);
     a.act = act; a.musc = musc; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out;
     a.gq = gq; a.gqd = gqd; a.gact = gact; a.gmusc = gmusc;
-    a.hinv_base = tape_geom(p->header.L, p->header.Q, p->header.D, tape_envs(p, n), substeps, mm_freq, p->bf16 != 0).hinv_base;
-    a.tape_bf16 = p->bf16;
-    a.flags = g_flags;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p->tile) return (int)launch_tile(p, a, true, st);
-    switch (pick_group(p)) {
-        case 8: return (int)launch<8, true>(p, a, st);
-        case 16: return (int)launch<16, true>(p, a, st);
-        default: return (int)launch<32, true>(p, a, st);
-    }
+    return run_step(p, a, true, stream);
+}
+
+int dfx_step_forward_mapped(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
+                            const float* q, const float* qd, const DfxActionMap* map, const float* raw, const float* act_other,
+                            float* used, float* q_out, float* qd_out, float* tape, void* stream) {
+    if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0 || !q || !qd || !map || !raw || !q_out || !qd_out) return (int)cudaErrorInvalidValue;
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    if (!bind_map(p, map, a)) return (int)cudaErrorInvalidValue;
+    if (!a.map_muscle && p->header.M > 0 && !act_other) return (int)cudaErrorInvalidValue;
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.q = q; a.qd = qd; a.raw = raw; a.used = used; a.q_out = q_out; a.qd_out = qd_out; a.tape = tape;
+    if (a.map_muscle) a.act = act_other; else a.musc = act_other;
+    return run_step(p, a, false, stream);
+}
+
+int dfx_step_backward_mapped(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
+                             const DfxActionMap* map, const float* raw, const float* act_other, const float* tape,
+                             const float* gq_out, const float* gqd_out, const float* g_used,
+                             float* gq, float* gqd, float* g_raw, void* stream) {
+    if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0 || !tape || !map || !raw) return (int)cudaErrorInvalidValue;
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    if (!bind_map(p, map, a)) return (int)cudaErrorInvalidValue;
+    if (!a.map_muscle && p->header.M > 0 && !act_other) return (int)cudaErrorInvalidValue;
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.raw = raw; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out; a.g_used = g_used;
+    a.gq = gq; a.gqd = gqd; a.g_raw = g_raw;
+    if (a.map_muscle) a.act = act_other; else a.musc = act_other;
+    return run_step(p, a, true, stream);
 }
 
 }  // extern "C"

@@ -33,6 +33,10 @@ struct StepArgs {
     long long hinv_base;
     int flags;   // bit 1: CTA-wide phase barriers
     int tape_bf16;   // the middle of every tape row (the forward intermediates) is stored as bf16 (tile kernels)
+    // action map folded into the step (include/dfx.h dfx_step_*_mapped): raw != nullptr
+    const float* raw; const float* strength; float* used; const float* g_used; float* g_raw;
+    int map_num_act, map_offset, map_muscle;
+    float map_pre_scale, map_pre_bias, map_drive_scale;
 };
 
 // derived State fields of the last substep (reference model.py:375-388); `late` = the ones that exist only after the solve
@@ -53,13 +57,41 @@ DFX_HD void dump_derived(const Pack& P, const Layout& Y, SP s, const DfxDerived&
     if (d.joint_tau) DFX_FOR(i, D) d.joint_tau[(long long)env * D + i] = s[Y.tau + i];
 }
 
+// actuation of one environment: from the caller's arrays, or formed from the raw policy output (same arithmetic as
+// dfx_action_map_forward: used = clip(raw, -1, 1) * pre_scale + pre_bias ; drive = (used * drive_scale) * strength)
+template <class Grp>
+DFX_HD void load_actuation(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a, bool write_used) {
+    const int D = P.D, M = P.M;
+    if (!a.raw) {
+        DFX_FOR(i, D) s[Y.act + i] = a.act[(long long)env * D + i];
+        DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
+        return;
+    }
+    const int A = a.map_num_act, off = a.map_offset;
+    const float* re = a.raw + (long long)env * A;
+    const int width = a.map_muscle ? M : D;
+    const int dst = a.map_muscle ? Y.musc : Y.act;
+    DFX_FOR(i, width) {
+        const int j = i - off;
+        float out = 0.0f;
+        if (j >= 0 && j < A) {
+            const float u = fminf(fmaxf(re[j], -1.0f), 1.0f) * a.map_pre_scale + a.map_pre_bias;
+            out = (u * a.map_drive_scale) * a.strength[j];
+        }
+        s[dst + i] = out;
+    }
+    if (a.map_muscle) { DFX_FOR(i, D) s[Y.act + i] = a.act ? a.act[(long long)env * D + i] : 0.0f; }
+    else { DFX_FOR(i, M) s[Y.musc + i] = a.musc ? a.musc[(long long)env * M + i] : 0.0f; }
+    if (write_used && a.used) DFX_FOR(j, A) a.used[(long long)env * A + j] = fminf(fmaxf(re[j], -1.0f), 1.0f) * a.map_pre_scale + a.map_pre_bias;
+}
+
 template <class Grp>
 DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a) {
-    const int Q = P.Q, D = P.D, M = P.M, DD = D * D;
+    const int Q = P.Q, D = P.D, DD = D * D;
     const RowFmt rf = row_fmt(P, Y, a.tape_bf16 != 0);
     DFX_FOR(i, Q) s[Y.q + i] = a.q[(long long)env * Q + i];
-    DFX_FOR(i, D) { s[Y.qd + i] = a.qd[(long long)env * D + i]; s[Y.act + i] = a.act[(long long)env * D + i]; }
-    DFX_FOR(i, M) s[Y.musc + i] = a.musc[(long long)env * M + i];
+    DFX_FOR(i, D) s[Y.qd + i] = a.qd[(long long)env * D + i];
+    load_actuation(P, Y, s, g, env, a, true);
     for (int i = Y.qdd + D + g.lane; i < Y.q + Y.tape_row; i += Grp::G) s[i] = 0.0f;   // row padding
     if (g.lane == 0) s[Y.cmask] = 0.0f;
     DFX_FOR(i, P.L * 12) s[Y.fx + i] = 0.0f;   // fixed-point wrench accumulators (L x 6 low + high words)
@@ -109,8 +141,9 @@ template <class Grp>
 DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g, int env, const StepArgs& a) {
     const int Q = P.Q, D = P.D, M = P.M, DD = D * D;
     const RowFmt rf = row_fmt(P, Y, a.tape_bf16 != 0);
-    DFX_FOR(i, D) { s[Y.act + i] = a.act[(long long)env * D + i]; s[Y.aact + i] = 0.0f; }
-    DFX_FOR(i, M) { s[Y.musc + i] = a.musc[(long long)env * M + i]; s[Y.amusc + i] = 0.0f; }
+    load_actuation(P, Y, s, g, env, a, false);
+    DFX_FOR(i, D) s[Y.aact + i] = 0.0f;
+    DFX_FOR(i, M) s[Y.amusc + i] = 0.0f;
     if (g.lane == 0) s[Y.cmask] = 0.0f;
     if (P.M > 0) DFX_FOR(i, P.L * 13) s[Y.fxH + i] = 0.0f;  // high words of the fixed-point cotangent accumulators
     DFX_FOR(i, Q) s[Y.aq + i] = a.gq_out ? a.gq_out[(long long)env * Q + i] : 0.0f;
@@ -142,6 +175,15 @@ DFX_HD void env_step_backward(const Pack& P, const Layout& Y, SP s, const Grp& g
     if (a.gqd) DFX_FOR(i, D) a.gqd[(long long)env * D + i] = s[Y.aqd + i];
     if (a.gact) DFX_FOR(i, D) a.gact[(long long)env * D + i] = s[Y.aact + i];
     if (a.gmusc) DFX_FOR(i, M) a.gmusc[(long long)env * M + i] = s[Y.amusc + i];
+    if (a.g_raw) {      // cotangent of the raw policy output (dfx_action_map_backward's arithmetic; clip passes the gradient on [-1, 1])
+        const int A = a.map_num_act, src = (a.map_muscle ? Y.amusc : Y.aact) + a.map_offset;
+        DFX_FOR(j, A) {
+            const float r = a.raw[(long long)env * A + j];
+            float gg = a.g_used ? a.g_used[(long long)env * A + j] : 0.0f;
+            gg += (s[src + j] * a.strength[j]) * a.map_drive_scale;
+            a.g_raw[(long long)env * A + j] = (r >= -1.0f && r <= 1.0f) ? gg * a.map_pre_scale : 0.0f;
+        }
+    }
 }
 
 }  // namespace dfx

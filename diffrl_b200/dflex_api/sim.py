@@ -61,6 +61,21 @@ def _derived_getattr(self, name):
 State.__getattr__ = _derived_getattr
 
 
+def fused_mapped_forward(model, state_in, dt, substeps, mass_matrix_freq, raw_actions, amap):
+    """``SemiImplicitIntegrator.forward`` with the env's action map folded into the launch (the env layer's fast path,
+    ``envs/base.py:_fused_step``): returns (State, used) where ``used`` are the clipped / affinely mapped actions.
+    ``amap`` = (offset, pre_scale, pre_bias, drive_scale, strength, is_muscle)."""
+    from ..engine import MappedSimStepFunction
+    engine = _engine_for(model)
+    q_new, qd_new, used = MappedSimStepFunction.apply(engine, int(substeps), int(mass_matrix_freq), float(dt), amap,
+                                                      state_in.joint_q, state_in.joint_qd, raw_actions)
+    out = State()
+    out.particle_count, out.link_count = model.particle_count, model.link_count
+    out.joint_q, out.joint_qd = q_new, qd_new
+    out.__dict__["_act_proto"] = model.joint_qd
+    return out, used
+
+
 class SemiImplicitIntegrator:
     """Semi-implicit (symplectic) Euler integrator for articulated rigid bodies."""
 

@@ -172,6 +172,55 @@ class ArticulationEngine:
         return gq, gqd, gact, gmusc
 
 
+class MappedSimStepFunction(torch.autograd.Function):
+    """(q, qd, raw policy output) -> (q', qd', used): the env-step with the action map folded into the simulation launch
+    (``dfx_step_forward_mapped`` / ``dfx_step_backward_mapped``): ``used = clip(raw, -1, 1) * pre_scale + pre_bias`` (the env's
+    ``actions``), ``joint_act`` / the muscle activations are formed inside the kernel.  ``amap`` = (offset, pre_scale, pre_bias,
+    drive_scale, strength [A], is_muscle)."""
+
+    @staticmethod
+    def forward(ctx, engine, substeps, mm_freq, dt, amap, q, qd, raw):
+        from .modelpack import DfxActionMap
+        offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = amap
+        dev = engine.device
+        q, qd = _f32c(q.detach(), dev), _f32c(qd.detach(), dev)
+        raw = _f32c(raw.detach(), dev)
+        n, A = engine.N, raw.shape[-1]
+        m = DfxActionMap(int(A), int(offset), int(bool(is_muscle)), float(pre_scale), float(pre_bias), float(drive_scale), strength.data_ptr())
+        need = any(ctx.needs_input_grad[5:8])
+        q_out, qd_out, used = torch.empty_like(q), torch.empty_like(qd), torch.empty_like(raw)
+        tape = torch.empty(engine.tape_floats(substeps, mm_freq), dtype=torch.float32, device=dev) if need else None
+        with torch.cuda.device(dev):
+            code = engine.lib.dfx_step_forward_mapped(engine.pack, n, int(substeps), int(mm_freq), float(dt), _ptr(q), _ptr(qd),
+                                                      ctypes.byref(m), _ptr(raw), None, _ptr(used), _ptr(q_out), _ptr(qd_out),
+                                                      _ptr(tape), engine._stream())
+        _capi.check(code, "dfx_step_forward_mapped")
+        ctx.engine, ctx.cfg, ctx.amap = engine, (substeps, mm_freq, dt), m
+        ctx.strength = strength                      # keeps the device array the struct points at alive
+        ctx.set_materialize_grads(False)
+        ctx.shapes = (q.shape, qd.shape)
+        ctx.save_for_backward(raw, tape)
+        return q_out, qd_out, used
+
+    @staticmethod
+    def backward(ctx, gq_out, gqd_out, g_used):
+        raw, tape = ctx.saved_tensors
+        engine, (substeps, mm_freq, dt) = ctx.engine, ctx.cfg
+        dev = engine.device
+        gq_out = None if gq_out is None else _f32c(gq_out, dev)
+        gqd_out = None if gqd_out is None else _f32c(gqd_out, dev)
+        g_used = None if g_used is None else _f32c(g_used, dev)
+        gq = torch.empty(engine.N * engine.Q, dtype=torch.float32, device=dev)
+        gqd = torch.empty(engine.N * engine.D, dtype=torch.float32, device=dev)
+        g_raw = torch.empty_like(raw)
+        with torch.cuda.device(dev):
+            code = engine.lib.dfx_step_backward_mapped(engine.pack, engine.N, int(substeps), int(mm_freq), float(dt), ctypes.byref(ctx.amap),
+                                                       _ptr(raw), None, _ptr(tape), _ptr(gq_out), _ptr(gqd_out), _ptr(g_used),
+                                                       _ptr(gq), _ptr(gqd), _ptr(g_raw), engine._stream())
+        _capi.check(code, "dfx_step_backward_mapped")
+        return None, None, None, None, None, gq.view(ctx.shapes[0]), gqd.view(ctx.shapes[1]), g_raw
+
+
 class SimStepFunction(torch.autograd.Function):
     """(q, qd, act, musc) -> (q', qd') for one env-step; the drop-in for the reference SimulateFunc."""
 

@@ -33,6 +33,13 @@ class DfxModelDesc(ctypes.Structure):
     ]
 
 
+class DfxActionMap(ctypes.Structure):
+    """include/dfx.h DfxActionMap: the policy-output -> actuation map folded into dfx_step_*_mapped."""
+    _fields_ = [("num_act", ctypes.c_int), ("offset", ctypes.c_int), ("is_muscle", ctypes.c_int),
+                ("pre_scale", ctypes.c_float), ("pre_bias", ctypes.c_float), ("drive_scale", ctypes.c_float),
+                ("strength", ctypes.c_void_p)]
+
+
 class DfxDerived(ctypes.Structure):
     """ctypes mirror of ``DfxDerived`` in include/dfx.h."""
 

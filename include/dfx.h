@@ -215,6 +215,27 @@ int dfx_action_map_forward(int n, int num_act, int width, int offset, float pre_
 int dfx_action_map_backward(int n, int num_act, int width, int offset, float pre_scale, float drive_scale, const float* strength,
                             const float* raw, const float* g_used, const float* g_drive, float* g_raw, void* stream);
 
+/* ---- the simulation step with the action map folded in (saves the two action-map launches per env.step()):
+ * the step kernels form joint_act (or, map.is_muscle, the muscle activations) from the raw policy output while loading it,
+ * write `used` (= the env's `actions`: clip(raw) * pre_scale + pre_bias) and, in the adjoint, turn the actuation cotangent
+ * into the cotangent of the raw policy output -- same arithmetic as dfx_action_map_forward / _backward.
+ * `act_other`: the array the map does NOT drive (joint_act of a muscle model; NULL = zeros). */
+typedef struct {
+    int num_act;         /* policy outputs per environment */
+    int offset;          /* first driven entry of a joint_act / muscle-activation row */
+    int is_muscle;       /* 0: drives joint_act [n, D]; 1: drives the muscle activations [n, M] */
+    float pre_scale, pre_bias, drive_scale;
+    const float* strength;   /* [num_act], device */
+} DfxActionMap;
+int dfx_step_forward_mapped(const dfx_pack_t* pack, int n, int substeps, int mm_freq, double dt,
+                            const float* q, const float* qd, const DfxActionMap* map, const float* raw, const float* act_other,
+                            float* used, float* q_out, float* qd_out, float* tape, void* stream);
+/* cotangents of (q_out, qd_out, used; any NULL == 0) -> gq, gqd, g_raw */
+int dfx_step_backward_mapped(const dfx_pack_t* pack, int n, int substeps, int mm_freq, double dt,
+                             const DfxActionMap* map, const float* raw, const float* act_other, const float* tape,
+                             const float* gq_out, const float* gqd_out, const float* g_used,
+                             float* gq, float* gqd, float* g_raw, void* stream);
+
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
 /* Tuning flags (default 9; for A/B timing and tests).  Lane-group kernels: bit 1 (2) = extra CTA-wide barriers between

@@ -226,3 +226,39 @@ def test_humanoid_invalid_state_gives_zero_reward():
         assert torch.isfinite(rew).all()
         rew.sum().backward()
         assert torch.isfinite(a.grad[torch.arange(8) != 3]).all()
+
+
+@pytest.mark.parametrize("name", ENVS)
+def test_action_map_folded_into_the_step_equals_separate_launch(name):
+    """env.step() with the action map inside the simulation launch (dfx_step_forward_mapped / _backward_mapped: 2 launches
+    forward + 2 backward) against the 3 + 3 launch path: same arithmetic, so observations / rewards / states are
+    bit-identical and the action gradients agree to rounding of the cotangent accumulation -- actions beyond the clip
+    range included (zero gradient there)."""
+    import torch
+    import diffrl_b200.envs as envs
+    from diffrl_b200 import _capi
+    n, T = 40, 5
+    outs = []
+    for folded in (True, False):
+        torch.manual_seed(0)
+        env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=4)
+        env.fused_action_map = folded
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        g = torch.Generator(device="cuda:0").manual_seed(13)
+        acts = [((torch.rand((n, env.num_actions), generator=g, device="cuda:0") * 2 - 1) * 1.5).requires_grad_() for _ in range(T)]
+        l0 = _capi.lib().dfx_launch_count()
+        loss, rec = 0.0, []
+        for a in acts:
+            obs, rew, done, _ = env.step(a)
+            loss = loss + rew.sum() + obs.sum() * 1e-2
+            rec.append((obs.detach().clone(), rew.detach().clone(), done.clone(), env.state.joint_q.detach().clone(), env.actions.detach().clone()))
+        launches_fwd = _capi.lib().dfx_launch_count() - l0
+        loss.backward()
+        outs.append((rec, torch.stack([a.grad for a in acts]), launches_fwd))
+    (r1, g1, l1), (r2, g2, l2) = outs
+    assert l1 == 2 * T and l2 == 3 * T, (l1, l2)
+    for a, b in zip(r1, r2):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert (g1 - g2).abs().max() <= 1e-6 * g2.abs().max() + 1e-9
+    assert bool((g1[(torch.stack([a.detach() for a in acts]).abs() > 1.0)] == 0).all())
