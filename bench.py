@@ -189,7 +189,7 @@ def run_reference(args):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         cores = os.cpu_count() or 1
-    procs = max(1, args.cpu_procs or cores)
+    procs = max(1, args.cpu_procs or min(cores, 64))     # (64 torch processes are ~60 GB of host memory; more adds little on an SMT box)
     ctx = mp.get_context("spawn")
     out_q = ctx.Queue()
     workers = [ctx.Process(target=_cpu_pool_worker, args=(env, n, steps, args.steps, max(1, args.warmup), out_q)) for _ in range(procs)]
