@@ -432,6 +432,30 @@ def roofline_record(m, peaks, peak_kind, traffic=None, fp32=None):
                     "averages over the timed rollouts (CUDA events on the launching stream)"}
 
 
+def profile_numbers(env_name, N, m, sm_mhz):
+    """(DRAM bytes per adjoint launch, fp32 record) from the committed ncu capture of this launch shape (profiles/r0X_traffic.json,
+    tools/make_traffic_json.py), or (None, None) when no capture of this (env, num_envs) is committed."""
+    for tname in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if not os.path.exists(tpath):
+            continue
+        with open(tpath) as f:
+            prof = json.load(f).get(env_name, {})
+        if not prof or prof.get("num_envs", 4096) != N:
+            continue
+        fp32 = None
+        if "bwd_fp32_flop_per_launch" in prof:
+            # SURVEY.md 8d's second yardstick: fp32 FLOP actually executed (counted by ncu for this launch shape) per
+            # second against the CUDA-core peak 148 SMs x 128 lanes x 2 FLOP x the SM clock sampled during the run
+            flop = prof["fwd_fp32_flop_per_launch"] + prof["bwd_fp32_flop_per_launch"]
+            peak = 148 * 128 * 2 * sm_mhz * 1e6
+            secs = (m["fwd_ms"] + m["bwd_ms"]) * 1e-3
+            fp32 = {"achieved_tflops": flop / secs / 1e12, "peak_tflops": peak / 1e12, "frac": flop / secs / peak,
+                    "flop_per_env_step": flop / N, "source": "profiles/%s (ncu instruction counts)" % tname}
+        return prof.get("bwd_dram_bytes_per_launch"), fp32
+    return None, None
+
+
 def config_record(m, world, peaks, peak_kind):
     value = world * m["N"] * m["T"] * m["steps"] / (m["kernel_ms"] * 1e-3)
     e2e = world * m["N"] * m["T"] * m["e2e_steps"] / (m["e2e_ms"] * 1e-3)
@@ -442,7 +466,7 @@ def config_record(m, world, peaks, peak_kind):
             "kernel_ms": {"forward_env_step": m["fwd_ms"], "backward_env_step": m["bwd_ms"]},
             "kernel_family": ("tile (%d envs per CTA)" % m["tile"]) if m["tile"] else "lane group",
             "tape_mb_per_rollout": m["tape_mb"], "gpu_launches": m["launches"],
-            "roofline": roofline_record(m, peaks, peak_kind)}
+            "roofline": roofline_record(m, peaks, peak_kind, *profile_numbers(m["env"], m["N"], m, 1965.0))}
 
 
 def run_ours(args):
@@ -502,25 +526,7 @@ def run_ours(args):
     peaks, peak_kind = measured_peaks()
     value = world * N * T * args.steps / (head["kernel_ms"] * 1e-3)
     e2e_value = world * N * T * head["e2e_steps"] / (head["e2e_ms"] * 1e-3)
-    traffic, fp32 = None, None
-    for tname in ("r02_traffic.json", "r01_traffic.json"):
-        tpath = os.path.join(ROOT, "profiles", tname)
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                prof = json.load(f).get(env_name, {})
-            if prof.get("num_envs", 4096) != N:
-                continue
-            traffic = prof.get("bwd_dram_bytes_per_launch")
-            if "bwd_fp32_flop_per_launch" in prof:
-                # SURVEY.md 8d's second yardstick: fp32 FLOP actually executed (counted by ncu for this launch shape) per
-                # second against the CUDA-core peak 148 SMs x 128 lanes x 2 FLOP x the SM clock sampled during the run
-                flop = prof["fwd_fp32_flop_per_launch"] + prof["bwd_fp32_flop_per_launch"]
-                mhz = clocks.summary().get("sm_mhz") or 1965.0
-                peak = 148 * 128 * 2 * mhz * 1e6
-                fp32 = {"achieved_tflops": flop / ((head["fwd_ms"] + head["bwd_ms"]) * 1e-3) / 1e12, "peak_tflops": peak / 1e12,
-                        "frac": flop / ((head["fwd_ms"] + head["bwd_ms"]) * 1e-3) / peak, "flop_per_env_step": flop / N,
-                        "source": "profiles/%s (ncu instruction counts)" % tname}
-            break
+    traffic, fp32 = profile_numbers(env_name, N, head, clocks.summary().get("sm_mhz") or 1965.0)
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
         "value_is": "kernel path: simulation-kernel launches only, inputs resident (the headline is e2e)",
