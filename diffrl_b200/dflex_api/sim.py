@@ -49,6 +49,16 @@ def _derived_getattr(self, name):
     if name == "joint_act" and "_act_proto" in self.__dict__:     # zero actuation, materialised on first use only
         self.__dict__["joint_act"] = torch.zeros_like(self.__dict__["_act_proto"])
         return self.__dict__["joint_act"]
+    if name in _DERIVED and "_derive_ctx_mapped" in self.__dict__:
+        # the step ran with the action map folded in: form the actuation arrays it used, then fall through
+        engine, q, qd, raw, amap, substeps, mm_freq, dt = self.__dict__.pop("_derive_ctx_mapped")
+        offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = amap
+        from ..env_ops import ActionMapFunction
+        width = engine.M if is_muscle else engine.D
+        with torch.no_grad():
+            _, drive = ActionMapFunction.apply(engine.N, width, offset, pre_scale, pre_bias, drive_scale, strength, raw.view(engine.N, -1))
+        act = torch.zeros(engine.N * engine.D, device=q.device) if is_muscle else drive
+        self.__dict__["_derive_ctx"] = (engine, q, qd, act, drive if is_muscle else None, substeps, mm_freq, dt)
     if name in _DERIVED and "_derive_ctx" in self.__dict__:
         engine, q, qd, act, musc, substeps, mm_freq, dt = self.__dict__["_derive_ctx"]
         _, _, _, dumps = engine.forward(q, qd, act, musc, substeps, mm_freq, dt, want_tape=False, derived=list(_DERIVED))
@@ -73,6 +83,8 @@ def fused_mapped_forward(model, state_in, dt, substeps, mass_matrix_freq, raw_ac
     out.particle_count, out.link_count = model.particle_count, model.link_count
     out.joint_q, out.joint_qd = q_new, qd_new
     out.__dict__["_act_proto"] = model.joint_qd
+    out.__dict__["_derive_ctx_mapped"] = (engine, state_in.joint_q.detach(), state_in.joint_qd.detach(), raw_actions.detach(), amap,
+                                          int(substeps), int(mass_matrix_freq), float(dt))
     return out, used
 
 
