@@ -37,13 +37,7 @@ def _batch(name, N, seed, noise=(2e-3, 2e-2)):
     return d, model, o, q0, qd0, act, musc, cfg
 
 
-def elementwise_bad_envs(a, b, width, rtol, atol_frac=1e-6):
-    """environments with a component outside |a - b| <= rtol |b| + atol_frac max|b| (+ rtol * per-env scale: components
-    that are differences of O(scale) terms carry the rounding of the scale, not of their own magnitude)"""
-    a = np.asarray(a, np.float64).reshape(-1, width); b = np.asarray(b, np.float64).reshape(-1, width)
-    scale = np.abs(b).max(axis=1, keepdims=True)
-    ok = np.abs(a - b) <= rtol * np.abs(b) + rtol * scale + atol_frac * np.abs(b).max()
-    return np.nonzero(~ok.all(axis=1))[0]
+from parity_util import elementwise_bad_envs  # noqa: E402
 
 
 @pytest.mark.parametrize("name,N", [("HumanoidEnv", 8192), ("SNUHumanoidEnv", 4096), ("AntEnv", 8192)])
