@@ -40,8 +40,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG unset / VERSION prints it when the first
 # communicator comes up) off it.  Set before torch / NCCL are loaded: the library latches its debug level on first use.
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
+# ... and whatever NCCL does log (recent versions print the banner at WARN as well) goes to a file, not to stdout
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dfx_bench_nccl.%h.%p.log")
 
 MM_FREQ = {"AntEnv": 16, "HumanoidEnv": 48, "SNUHumanoidEnv": 8, "CartPoleSwingUpEnv": 4, "HopperEnv": 16, "CheetahEnv": 16}
 SUBSTEPS = {"AntEnv": 16, "HumanoidEnv": 48, "SNUHumanoidEnv": 48, "CartPoleSwingUpEnv": 4, "HopperEnv": 16, "CheetahEnv": 16}
