@@ -271,10 +271,11 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
     // the two kernel families lay the tape out differently
     p->tile = 0;
     if (!(g_flags & 32)) {
-        static const int kWidths[3] = {32, 16, 8};
+        // auto: 32 environments per CTA where the scratch allows it, else 8 (two CTAs per SM); 16 only on request (A/B)
+        static const int kWidths[3] = {32, 8, 16};
         for (int k = 0; k < 3 && !p->tile; ++k) {
             const int E = kWidths[k];
-            if ((g_tile_envs == 0 || g_tile_envs == E) && tile_mode(E, p->header) >= 0) p->tile = E;
+            if ((g_tile_envs == 0 ? E != 16 : g_tile_envs == E) && tile_mode(E, p->header) >= 0) p->tile = E;
         }
     }
     if (p->tile) p->host.set_layout_mode(tile_mode(p->tile, p->header));

@@ -326,19 +326,27 @@ using namespace dfx;
 
 // The articulations with a tile kernel of this width:
 //   X(warps forward, warps backward, min CTAs per SM (register budget), path passes, layout mode, L, D, Q, C, M)
+#ifndef DFX_TILE_NWF         // warps of the Ant tile kernels (tuning builds: -DDFX_TILE_NWF=12 -DDFX_TILE_NWB=12 -DDFX_TILE_ONLY_ANT)
+#define DFX_TILE_NWF 16
+#endif
+#ifndef DFX_TILE_NWB
+#define DFX_TILE_NWB 16
+#endif
 #if DFX_TILE_E == 32
 #ifdef DFX_TILE_ONLY_ANT      // (tuning builds)
-#define DFX_TILE_MODELS(X) X(16, 16, 1, true, 0, 9, 14, 15, 25, 0)
+#define DFX_TILE_MODELS(X) X(DFX_TILE_NWF, DFX_TILE_NWB, 1, true, 0, 9, 14, 15, 25, 0)
 #else
 #define DFX_TILE_MODELS(X)                                        \
-    X(16, 16, 1, true, 0, 9, 14, 15, 25, 0) /* Ant */             \
+    X(DFX_TILE_NWF, DFX_TILE_NWB, 1, true, 0, 9, 14, 15, 25, 0) /* Ant */             \
     X(8, 8, 1, true, 0, 3, 2, 2, 0, 0)      /* CartPole */        \
     X(16, 16, 1, true, 0, 6, 6, 6, 8, 0)    /* Hopper */          \
     X(16, 16, 1, true, 0, 9, 9, 9, 16, 0)   /* HalfCheetah */
 #endif
 #elif DFX_TILE_E == 16
 #define DFX_TILE_MODELS(X)                                        \
-    X(8, 8, 2, true, 3, 9, 14, 15, 25, 0)   /* Ant, two CTAs per SM */
+    X(8, 8, 2, true, 3, 9, 14, 15, 25, 0)   /* Ant, two CTAs per SM */   \
+    X(16, 16, 1, true, 3, 22, 27, 28, 35, 0)    /* Humanoid, one CTA of 16 environments per SM (A/B against E = 8 x 2 CTAs) */ \
+    X(16, 16, 1, true, 3, 11, 24, 29, 88, 152)  /* SNU humanoid, same */
 #elif DFX_TILE_E == 8
 #define DFX_TILE_MODELS(X)                                        \
     X(8, 8, 2, true, 3, 22, 27, 28, 35, 0)    /* Humanoid */      \
