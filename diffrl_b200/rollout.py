@@ -90,7 +90,12 @@ class GraphedRollout:
             obs, rew, done, _ = env.step(a_t)
             obs_l.append(obs); rew_l.append(rew); done_l.append(done)
         rew_all = torch.stack(rew_l)                       # one reduction for the whole window
-        loss = rew_all.sum() if self.weight is None else (rew_all * self.weight).sum()
+        # (always through an explicit weight tensor: the cotangent of a bare .sum() is a stride-0 expand, which every step's
+        #  transition adjoint would have to materialise with a copy kernel of its own; the product's cotangent is one dense [T, N]
+        #  tensor whose per-step slices are contiguous views)
+        if self.weight is None:
+            self.weight = torch.ones_like(rew_all)
+        loss = (rew_all * self.weight).sum()
         self.actions.grad = None
         loss.backward()
         self.obs, self.rew, self.done = torch.stack(obs_l).detach(), rew_all.detach(), torch.stack(done_l)
