@@ -1021,7 +1021,20 @@ template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, SP s, SP atau, const Grp& g) {
     const int atau_off = (int)(atau - s);   // (element offset inside the scratch)
     g.cta_tasks(s, P.L, true, [&](SP se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
-    chain_rounds_down(P, s, g, [&](SP se, int i) { tau_accum_adj(P, Y, se, i); }, false, true);
+    // T1': af[i] += af[parent], root -> leaves, as PATH SUMS: every link adds the direct cotangents along its own root path in
+    // root-first order (the same association as the recursion, so the same bits) into the (idle) pX slot, then copies back --
+    // two barriers with all links busy instead of a serial walk down the chains
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) {
+        SV acc = sv_zero();
+        bool first = true;
+        for_path_root_first(P, i, true, [&](int j) {
+            const SV x = ld6(se + Y.af + j * 6);
+            acc = first ? x : acc + x;
+            first = false;
+        });
+        st6(se + Y.pX + i * 7, acc);
+    });
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) { st6(se + Y.af + i * 6, ld6(se + Y.pX + i * 7)); });
 }
 
 // =====================================================================================
