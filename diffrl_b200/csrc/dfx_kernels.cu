@@ -271,14 +271,15 @@ dfx_pack_t* dfx_pack_create(const DfxModelDesc* desc, int device, char* err, int
     // the two kernel families lay the tape out differently
     p->tile = 0;
     if (!(g_flags & 32)) {
-        // auto: 32 environments per CTA where the scratch allows it, else 8 (two CTAs per SM); 16 only on request (A/B)
-        static const int kWidths[3] = {32, 8, 16};
+        // auto: the widest tile kernel that is not an A/B-only instantiation (mode bit 4); dfx_set_tile_envs picks any
+        static const int kWidths[3] = {32, 16, 8};
         for (int k = 0; k < 3 && !p->tile; ++k) {
             const int E = kWidths[k];
-            if ((g_tile_envs == 0 ? E != 16 : g_tile_envs == E) && tile_mode(E, p->header) >= 0) p->tile = E;
+            const int mode = tile_mode(E, p->header);
+            if (mode >= 0 && (g_tile_envs == 0 ? !(mode & 16) : g_tile_envs == E)) p->tile = E;
         }
     }
-    if (p->tile) p->host.set_layout_mode(tile_mode(p->tile, p->header));
+    if (p->tile) p->host.set_layout_mode(tile_mode(p->tile, p->header) & 3);
     p->bf16 = (p->tile && g_tape_bf16) ? 1 : 0;
     return p;
 }

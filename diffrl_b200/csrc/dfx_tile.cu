@@ -344,14 +344,14 @@ using namespace dfx;
 #endif
 #elif DFX_TILE_E == 16
 #define DFX_TILE_MODELS(X)                                        \
-    X(8, 8, 2, true, 3, 9, 14, 15, 25, 0)   /* Ant, two CTAs per SM */   \
-    X(16, 16, 1, true, 3, 22, 27, 28, 35, 0)    /* Humanoid, one CTA of 16 environments per SM (A/B against E = 8 x 2 CTAs) */ \
-    X(16, 16, 1, true, 3, 11, 24, 29, 88, 152)  /* SNU humanoid, same */
+    X(8, 8, 2, true, 3 | 16, 9, 14, 15, 25, 0)   /* Ant, two CTAs per SM (A/B only) */   \
+    X(16, 16, 1, true, 3 | 16, 22, 27, 28, 35, 0) /* Humanoid, one CTA of 16 environments per SM (A/B only: 8 x 2 CTAs is 1-4 % faster) */ \
+    X(16, 16, 1, true, 3, 11, 24, 29, 88, 152)    /* SNU humanoid: one CTA of 16 environments, 16 warps (7 % faster than 8 x 2 CTAs: 152 muscles fill the slots) */
 #elif DFX_TILE_E == 8
 #define DFX_TILE_MODELS(X)                                        \
     X(8, 8, 2, true, 3, 22, 27, 28, 35, 0)    /* Humanoid */      \
-    X(8, 8, 2, true, 3, 11, 24, 29, 88, 152)  /* SNU humanoid (lower body, 152 muscles) */ \
-    X(4, 4, 4, true, 3, 9, 14, 15, 25, 0)     /* Ant, four CTAs per SM */
+    X(8, 8, 2, true, 3 | 16, 11, 24, 29, 88, 152)  /* SNU humanoid (A/B only: its default is E = 16) */ \
+    X(4, 4, 4, true, 3 | 16, 9, 14, 15, 25, 0)     /* Ant, four CTAs per SM (A/B only) */
 #endif
 
 // alternative instantiations, picked by flag bit 6 (64) of dfx_set_flags (A/B timing): level-by-level tree recursions
@@ -367,7 +367,8 @@ using namespace dfx;
 #define DFX_CAT(a, b) DFX_CAT2(a, b)
 #define DFX_TILE_FN(name) DFX_CAT(DFX_CAT(name, _e), DFX_TILE_E)
 
-// layout mode of the tile kernel for this articulation, or -1 when there is none of this width
+// layout mode of the tile kernel for this articulation (bit 4 (16): instantiated for A/B runs only, never picked
+// automatically), or -1 when there is none of this width
 int DFX_TILE_FN(dfx_tile_mode)(int L, int D, int Q, int C, int M) {
 #define X(nwf, nwb, minb, path, mode, l, d, q, c, m) if (L == l && D == d && Q == q && C == c && M == m) return mode;
     DFX_TILE_MODELS(X)
@@ -379,7 +380,7 @@ int DFX_TILE_FN(dfx_tile_mode)(int L, int D, int Q, int C, int M) {
 size_t DFX_TILE_FN(dfx_tile_smem)(const void* kargs, int backward) {
     const KernelArgs& ka = *static_cast<const KernelArgs*>(kargs);
     const int mode = DFX_TILE_FN(dfx_tile_mode)(ka.header.L, ka.header.D, ka.header.Q, ka.header.C, ka.header.M);
-    const Layout Y = make_layout(ka.header.L, ka.header.D, ka.header.Q, ka.header.C, ka.header.M, mode < 0 ? 0 : mode, backward != 0);
+    const Layout Y = make_layout(ka.header.L, ka.header.D, ka.header.Q, ka.header.C, ka.header.M, mode < 0 ? 0 : (mode & 3), backward != 0);
     const int per_env = ((backward ? Y.bwd_size : Y.fwd_size) + 3) & ~3;
     return (size_t)(tile_pack_floats(ka) + tile_area_floats(ka) + per_env * DFX_TILE_E) * sizeof(float);
 }
@@ -390,8 +391,8 @@ int DFX_TILE_FN(dfx_tile_launch)(void* kargs, int backward, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define X(nwf, nwb, minb, path, mode, l, d, q, c, m)                                                   \
     if (h.L == l && h.D == d && h.Q == q && h.C == c && h.M == m)                                      \
-        return (int)(backward ? tile_launch_impl<nwb, minb, true, path, mode, l, d, q, c, m>(ka, st)   \
-                              : tile_launch_impl<nwf, minb, false, path, mode, l, d, q, c, m>(ka, st));
+        return (int)(backward ? tile_launch_impl<nwb, minb, true, path, (mode) & 3, l, d, q, c, m>(ka, st)   \
+                              : tile_launch_impl<nwf, minb, false, path, (mode) & 3, l, d, q, c, m>(ka, st));
     if (ka.step.flags & 64) { DFX_TILE_MODELS_ALT(X) }
     DFX_TILE_MODELS(X)
 #undef X
