@@ -351,6 +351,11 @@ DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, SP s, int i) {    // A
     st6(s + Y.vj + i * 6, vj);
 }
 
+#ifndef DFX_KIN_ADJ_CHAINS
+#define DFX_KIN_ADJ_CHAINS 0     // 1: the leaf -> root recursions A2 / A4 as chain rounds (A/B builds); 0: as subtree sums
+#endif
+
+#if DFX_KIN_ADJ_CHAINS
 DFX_HD void kin_adj_velocity(const Pack& P, const Layout& Y, SP s, int i) {  // A2
     SV av = ld6(s + Y.av + i * 6), aa = ld6(s + Y.aa + i * 6);
     for (int k = P.child_start[i]; k < P.child_start[i + 1]; ++k) {
@@ -440,6 +445,128 @@ DFX_HD void kin_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     chain_rounds_up(P, s, g, [&](SP se, int i) { kin_adj_chain(P, Y, se, i); });
     g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_joint(P, Y, se, i); });
 }
+
+#else
+// The two leaf -> root recursions without a recursion.  Both are LINEAR accumulations towards the root:
+//   * av, aa: a child's cotangent reaches the parent unchanged (v = v_p + v_j, a = a_p + v x v_j), so a link's total is the
+//     sum over its subtree of the links' own terms;
+//   * aX_sc: through X_sc[c] = X_sc[p] X_l[c] the translation part reaches the parent unchanged and the quaternion part as
+//     r (x) conj(X_l[c].q), plus a term at p that depends on the child's translation total.  Writing every quaternion
+//     cotangent w that lives at link j in the WORLD form u = w (x) conj(X_sc[j].q) turns the chain of right-multiplications
+//     into the identity (X_sc[j].q = X_sc[i].q (x) q_(i->j) for i above j): the total at link i is
+//     (sum of u over the subtree) (x) X_sc[i].q / |X_sc[i].q|^2  -- exact for non-unit quaternions too.
+// Every pass is then parallel over ALL links with the subtree lists of the pack (O(L * depth) cheap additions instead of a
+// dependent walk of heavy per-link steps by a handful of threads): four barriers, no idle warps.
+//   B1  aa total (subtree sum) ; adjoint of a = a_p + v x v_j : av[i] += d/dv, vj slot <- d/dv_j
+//   B2  av total (subtree sum) -> av_j ; A3 (S, qd, X_sj) ; pX[i] <- what this link sends to its ancestors through
+//       X_sj = X_p X_pj: translation part and the world form (at the parent) of the quaternion part
+//   B3  translation total of aX_sc (subtree sum) -> vj slot ; world forms: aXsc.q slot <- own quaternion part, aXsm.q slot <-
+//       what the link sends to its ancestors (from B2, plus the term of X_sc[i] = X_p X_l through the translation total)
+//   B4  quaternion total (subtree sums), back to the link's frame ; A5
+DFX_HD void kin_adj_acc(const Pack& P, const Layout& Y, SP s, int i) {        // B1
+    SV aa = sv_zero();
+    for (int k = P.sub_start[i]; k < P.sub_start[i + 1]; ++k) aa += ld6(s + Y.aa + P.sub_links[k] * 6);
+    SV dv = sv_zero(), dvj = sv_zero();
+    sv_cross_adj(ld6(s + Y.v + i * 6), ld6(s + Y.vj + i * 6), aa, dv, dvj);   // a = a_p + v x v_j
+    add6(s + Y.av + i * 6, dv);      // (own slot: the other links read aa only in this pass)
+    st6(s + Y.vj + i * 6, dvj);
+}
+
+DFX_HD Q4 q_conj(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
+
+DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // B2
+    const int par = P.parent[i], type = P.type[i], ds = P.qd_start[i];
+    SV avj = ld6(s + Y.vj + i * 6);
+    for (int k = P.sub_start[i]; k < P.sub_start[i + 1]; ++k) avj += ld6(s + Y.av + P.sub_links[k] * 6);   // v = v_p + v_j
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    const Xf Xpj = ld7(P.X_pj + i * 7);
+    const Xf Xsj = xf_mul(Xp, Xpj);
+    const V3 axis = ld3(P.axis + i * 3);
+    const SP qd = s + Y.qd;
+    const SP S = s + Y.S;
+    const SP aS = s + Y.aS;
+    const SP aqd = s + Y.aqd;
+    Xf aXsj = xf_zero();
+    if (type == JOINT_PRISMATIC) {
+        const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
+        aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
+        aXsj.q += qrot_adj_q(Xsj.q, axis, aSk.v);   // S.v = R axis
+    } else if (type == JOINT_REVOLUTE) {
+        const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
+        aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
+        xf_twist_adj_t(Xsj, SV{axis, v3zero()}, aSk, aXsj);
+    } else if (type == JOINT_BALL) {
+        for (int k = 0; k < 3; ++k) {
+            const SV aSk = ld6(aS + (ds + k) * 6) + avj * qd[ds + k];
+            aqd[ds + k] += sv_dot(ld6(S + (ds + k) * 6), avj);
+            V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
+            xf_twist_adj_t(Xsj, SV{e, v3zero()}, aSk, aXsj);
+        }
+    } else if (type == JOINT_FREE) {
+        add6(aqd + ds, avj);
+    }
+    // X_sj = X_p X_pj: the cotangent of X_p, quaternion part in the world form at the parent
+    Xf aXp = xf_zero();
+    xf_mul_adj_a(Xp, Xpj, aXsj, aXp);
+    st3(s + Y.pX + i * 7, aXp.p);
+    st4(s + Y.pX + i * 7 + 3, qmul(aXp.q, q_conj(Xp.q)));
+}
+
+DFX_HD void kin_adj_world(const Pack& P, const Layout& Y, SP s, int i) {     // B3
+    const int par = P.parent[i];
+    V3 ap = v3zero();
+    for (int k = P.sub_start[i]; k < P.sub_start[i + 1]; ++k) {
+        const int j = P.sub_links[k];
+        ap += ld3(s + Y.aXsc + j * 7) + ld3(s + Y.aXsm + j * 7);          // own parts (aXsm slot: A1's share, through X_sm)
+        if (j != i) ap += ld3(s + Y.pX + j * 7);                          // what j sent upwards through X_sj
+    }
+    const Q4 own = ld4(s + Y.aXsc + i * 7 + 3) + ld4(s + Y.aXsm + i * 7 + 3);
+    const Q4 qi = ld4(s + Y.Xsc + i * 7 + 3);
+    Q4 up = ld4(s + Y.pX + i * 7 + 3);
+    if (par >= 0) {      // X_sc = X_p X_l: the translation total turns X_p.q
+        const Q4 qp = ld4(s + Y.Xsc + par * 7 + 3);
+        up += qmul(qrot_adj_q(qp, ld3(s + Y.Xl + i * 7), ap), q_conj(qp));
+    }
+    st3(s + Y.vj + i * 6, ap);                                  // (vj slot: B2 consumed av_j)
+    st4(s + Y.aXsc + i * 7 + 3, qmul(own, q_conj(qi)));         // (quaternion slots of this link: read by nobody else in this pass)
+    st4(s + Y.aXsm + i * 7 + 3, up);
+}
+
+DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // B4 + A5
+    const int par = P.parent[i], type = P.type[i], qs = P.q_start[i];
+    if (type == JOINT_FIXED) return;
+    Q4 u = Q4{0.f, 0.f, 0.f, 0.f};
+    for (int k = P.sub_start[i]; k < P.sub_start[i + 1]; ++k) {
+        const int j = P.sub_links[k];
+        u += ld4(s + Y.aXsc + j * 7 + 3);
+        if (j != i) u += ld4(s + Y.aXsm + j * 7 + 3);
+    }
+    const Q4 qi = ld4(s + Y.Xsc + i * 7 + 3);
+    const float n2 = qi.x * qi.x + qi.y * qi.y + qi.z * qi.z + qi.w * qi.w;
+    const Xf aXsc = Xf{ld3(s + Y.vj + i * 6), qmul(u, qi) * (1.0f / n2)};     // total cotangent of X_sc[i]
+    const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
+    const Xf Xpj = ld7(P.X_pj + i * 7);
+    const SP q = s + Y.q;
+    const SP aq = s + Y.aq;
+    const Xf aXl = xf_mul_adj_b(Xp, aXsc);                       // X_sc = X_p X_l
+    const Xf aXjc = xf_mul_adj_b(Xpj, aXl);                      // X_l = X_pj X_jc
+    const V3 axis = ld3(P.axis + i * 3);
+    if (type == JOINT_PRISMATIC) aq[qs] += dot(axis, aXjc.p);
+    else if (type == JOINT_REVOLUTE) aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
+    else if (type == JOINT_BALL) add4(aq + qs, aXjc.q);
+    else if (type == JOINT_FREE) { add3(aq + qs, aXjc.p); add4(aq + qs + 3, aXjc.q); }
+}
+
+template <class Grp>
+DFX_HD void kin_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
+    // four passes of CTA-wide (link, environment) tasks, link-major: uniform joint types per warp
+    // (A1 already ran inside the rigid-body force adjoint)
+    g.cta_tasks(s, P.L, true, [&](SP se, int i) { kin_adj_acc(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_motion(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_world(P, Y, se, i); });
+    g.cta_tasks(s, P.L, false, [&](SP se, int i) { kin_adj_joint(P, Y, se, i); });
+}
+#endif
 
 // =====================================================================================
 // rigid-body forces per link:  f = I a + v x* I v - f_gravity, with I in closed form

@@ -136,3 +136,32 @@ def test_explicit_inverse_is_not_the_parity_floor(name):
     assert err["hinv"] < 1e-5 and err["sweeps"] < 1e-5, err
     assert abs(err["hinv"] - err["sweeps"]) < 3e-6, err
     assert err["hinv_fma"] < 2e-5 and err["sweeps_fma"] < 2e-5, err
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv"])
+def test_kinematics_adjoint_subtree_sums_match_the_recursion(name):
+    """The kinematics adjoint accumulates the (v, a) and X_sc cotangents towards the root as subtree sums (quaternion parts in
+    the world form, csrc/dfx_phases.h kin_adj) instead of the leaf -> root recursion the reference's reversed tape performs
+    (adjoint of sim.py:1668 / 1700-1720).  A/B on the host emulation, including states whose root quaternion is NOT unit
+    (the world form is exact for those too): both formulations against the reference's gradients and against each other."""
+    d, model = load_golden(name)
+    N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    sums, chains = EmuSim(model, N), EmuSim(model, N, extra=("-DDFX_KIN_ADJ_CHAINS=1",))
+    rng = np.random.default_rng(5)
+    for k in range(int(d["meta/num_cases"])):
+        p = "case%d/" % k
+        musc = d[p + "musc"] if (p + "musc") in d.files else None
+        for scale in (None, 1.07):
+            q0 = d[p + "q0"].copy()
+            if scale is not None:       # every free root: quaternion scaled away from unit length
+                q0.reshape(N, -1)[:, 3:7] *= scale
+            got = []
+            for sim in (sums, chains):
+                _, _, tape, _ = sim.forward(q0, d[p + "qd0"], d[p + "act"], musc, S, mm, dt)
+                got.append(sim.backward(d[p + "act"], musc, tape, d[p + "gq_out"], d[p + "gqd_out"], S, mm, dt))
+            for a, b, key in zip(got[0], got[1], ("grad_q", "grad_qd", "grad_act", "grad_musc")):
+                if a is None:
+                    continue
+                assert rel(a, b) < 3e-5, (name, k, scale, key, rel(a, b))
+                if scale is None:
+                    assert rel(a, d[p + key]) < GRAD_RTOL and rel(b, d[p + key]) < GRAD_RTOL, (name, k, key)
