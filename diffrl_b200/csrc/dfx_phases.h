@@ -461,7 +461,8 @@ DFX_HD void kin_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
 //   B2  av total (subtree sum) -> av_j ; A3 (S, qd, X_sj) ; pX[i] <- what this link sends to its ancestors through
 //       X_sj = X_p X_pj: translation part and the world form (at the parent) of the quaternion part
 //   B3  translation total of aX_sc (subtree sum) -> vj slot ; world forms: aXsc.q slot <- own quaternion part, aXsm.q slot <-
-//       what the link sends to its ancestors (from B2, plus the term of X_sc[i] = X_p X_l through the translation total)
+//       own + what the link sends to its ancestors (from B2, plus the term of X_sc[i] = X_p X_l through the translation total)
+//       (own and sent-upwards parts are pre-added per link so that every subtree sum runs over ONE array)
 //   B4  quaternion total (subtree sums), back to the link's frame ; A5
 DFX_HD void kin_adj_acc(const Pack& P, const Layout& Y, SP s, int i) {        // B1
     SV aa = sv_zero();
@@ -508,18 +509,19 @@ DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // 
     // X_sj = X_p X_pj: the cotangent of X_p, quaternion part in the world form at the parent
     Xf aXp = xf_zero();
     xf_mul_adj_a(Xp, Xpj, aXsj, aXp);
-    st3(s + Y.pX + i * 7, aXp.p);
+    // translation parts, pre-added so that B3 sums ONE array over the subtree: the link's own (aXsc slot, with A1's share from
+    // the aXsm slot) and, for its ancestors, own + what it sends upwards (pX slot)
+    const V3 own = ld3(s + Y.aXsc + i * 7) + ld3(s + Y.aXsm + i * 7);
+    st3(s + Y.aXsc + i * 7, own);
+    st3(s + Y.pX + i * 7, own + aXp.p);
     st4(s + Y.pX + i * 7 + 3, qmul(aXp.q, q_conj(Xp.q)));
 }
 
 DFX_HD void kin_adj_world(const Pack& P, const Layout& Y, SP s, int i) {     // B3
     const int par = P.parent[i];
-    V3 ap = v3zero();
-    for (int k = P.sub_start[i]; k < P.sub_start[i + 1]; ++k) {
-        const int j = P.sub_links[k];
-        ap += ld3(s + Y.aXsc + j * 7) + ld3(s + Y.aXsm + j * 7);          // own parts (aXsm slot: A1's share, through X_sm)
-        if (j != i) ap += ld3(s + Y.pX + j * 7);                          // what j sent upwards through X_sj
-    }
+    V3 ap = ld3(s + Y.aXsc + i * 7);                                      // own part (B2 added A1's share)
+    for (int k = P.sub_start[i] + 1; k < P.sub_start[i + 1]; ++k)         // (the list starts with i itself)
+        ap += ld3(s + Y.pX + P.sub_links[k] * 7);                         // descendants: own + what they sent upwards through X_sj
     const Q4 own = ld4(s + Y.aXsc + i * 7 + 3) + ld4(s + Y.aXsm + i * 7 + 3);
     const Q4 qi = ld4(s + Y.Xsc + i * 7 + 3);
     Q4 up = ld4(s + Y.pX + i * 7 + 3);
@@ -528,19 +530,16 @@ DFX_HD void kin_adj_world(const Pack& P, const Layout& Y, SP s, int i) {     // 
         up += qmul(qrot_adj_q(qp, ld3(s + Y.Xl + i * 7), ap), q_conj(qp));
     }
     st3(s + Y.vj + i * 6, ap);                                  // (vj slot: B2 consumed av_j)
-    st4(s + Y.aXsc + i * 7 + 3, qmul(own, q_conj(qi)));         // (quaternion slots of this link: read by nobody else in this pass)
-    st4(s + Y.aXsm + i * 7 + 3, up);
+    const Q4 uo = qmul(own, q_conj(qi));
+    st4(s + Y.aXsc + i * 7 + 3, uo);                            // (quaternion slots of this link: read by nobody else in this pass)
+    st4(s + Y.aXsm + i * 7 + 3, uo + up);                       // for the ancestors: own + sent upwards, pre-added (one array in B4)
 }
 
 DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // B4 + A5
     const int par = P.parent[i], type = P.type[i], qs = P.q_start[i];
     if (type == JOINT_FIXED) return;
-    Q4 u = Q4{0.f, 0.f, 0.f, 0.f};
-    for (int k = P.sub_start[i]; k < P.sub_start[i + 1]; ++k) {
-        const int j = P.sub_links[k];
-        u += ld4(s + Y.aXsc + j * 7 + 3);
-        if (j != i) u += ld4(s + Y.aXsm + j * 7 + 3);
-    }
+    Q4 u = ld4(s + Y.aXsc + i * 7 + 3);
+    for (int k = P.sub_start[i] + 1; k < P.sub_start[i + 1]; ++k) u += ld4(s + Y.aXsm + P.sub_links[k] * 7 + 3);
     const Q4 qi = ld4(s + Y.Xsc + i * 7 + 3);
     const float n2 = qi.x * qi.x + qi.y * qi.y + qi.z * qi.z + qi.w * qi.w;
     const Xf aXsc = Xf{ld3(s + Y.vj + i * 6), qmul(u, qi) * (1.0f / n2)};     // total cotangent of X_sc[i]
@@ -1136,32 +1135,26 @@ DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, SP s, SP atau, int i
         for (int k = 0; k < 6; ++k) add6(aS + (ds + k) * 6, f * (-atau[ds + k]));
         af += SV{V3{-atau[ds], -atau[ds + 1], -atau[ds + 2]}, V3{-atau[ds + 3], -atau[ds + 4], -atau[ds + 5]}};
     }
-    st6(s + Y.af + i * 6, af);
-}
-
-DFX_HD void tau_accum_adj(const Pack& P, const Layout& Y, SP s, int i) {
-    const int par = P.parent[i];
-    if (par >= 0) add6(s + Y.af + i * 6, ld6(s + Y.af + par * 6));   // f_tot[parent] = f[parent] + sum f_tot[children]
+    st6(s + Y.pX + i * 7, af);      // (direct part, in the idle pX slot: tau_adj sums it along the root paths into af)
 }
 
 template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, SP s, SP atau, const Grp& g) {
     const int atau_off = (int)(atau - s);   // (element offset inside the scratch)
     g.cta_tasks(s, P.L, true, [&](SP se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
-    // T1': af[i] += af[parent], root -> leaves, as PATH SUMS: every link adds the direct cotangents along its own root path in
-    // root-first order (the same association as the recursion, so the same bits) into the (idle) pX slot, then copies back --
-    // two barriers with all links busy instead of a serial walk down the chains
+    // T1': af[i] = af_direct[i] + af[parent], root -> leaves, as PATH SUMS: tau_project_adj left the direct cotangents in the
+    // (idle) pX slot; every link adds them along its own root path in root-first order (the same association as the
+    // recursion, so the same bits) -- two barriers with all links busy instead of a serial walk down the chains
     g.cta_tasks(s, P.L, false, [&](SP se, int i) {
         SV acc = sv_zero();
         bool first = true;
         for_path_root_first(P, i, true, [&](int j) {
-            const SV x = ld6(se + Y.af + j * 6);
+            const SV x = ld6(se + Y.pX + j * 7);
             acc = first ? x : acc + x;
             first = false;
         });
-        st6(se + Y.pX + i * 7, acc);
+        st6(se + Y.af + i * 6, acc);
     });
-    g.cta_tasks(s, P.L, false, [&](SP se, int i) { st6(se + Y.af + i * 6, ld6(se + Y.pX + i * 7)); });
 }
 
 // =====================================================================================
@@ -1350,6 +1343,10 @@ DFX_HD void solve_adj(const Pack& P, const Layout& Y, SP s, HinvView hv, const G
     // (no barrier here: the caller's next one -- substep_adj waits for the bulk of the tape row -- comes before any reader of Hs, tau)
 }
 
+#ifndef DFX_CRBA_ADJ_DIRECT
+#define DFX_CRBA_ADJ_DIRECT 0     // 1: the direct double sums (A/B builds); 0: composite inertias + per-link moment matrices
+#endif
+#if DFX_CRBA_ADJ_DIRECT
 // adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), from the symmetrised cotangent Hs
 template <class Grp>
 DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
@@ -1396,6 +1393,102 @@ DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     }
     g.sync();
 }
+
+#else
+// adjoint of H(S, I) w.r.t. S (-> aS) and the body inertias (-> aIbar, aXsm.p), from the symmetrised cotangent Hs.
+// With c_aa = Hs_aa, c_ab = Hs_ab / 2 the cotangent is that of  sum_l sum_{a,b in anc(l)} c_ab S_a^T I_l S_b :
+//   * body inertias: the bilinear form of link l is tr(I_l K_l) with the symmetric moment matrix
+//         K_l = sum_{a,b in anc(l)} c_ab S_b S_a^T = sum_{a in anc(l)} (S_a g_a^T + g_a S_a^T),   g_a = c_aa/2 S_a + sum_{b < a} c_ab S_b
+//     (g_a depends on the dof only: formed once per dof), and d tr(I K)/d(R, u) is the vector-pair adjoint of y = I x
+//     summed over the six pairs (x = column k of K, r = e_k) -- 6 instead of |anc(l)| (8-15) evaluations per link and
+//     |anc(l)| rank-2 updates instead of |anc(l)|^2 axpys;
+//   * motion subspace:  aS_a = sum_{l in subtree(link(a))} I_l (2 sum_{b in anc(l)} c_ab S_b)
+//                            = Ic_link(a) p_a + sum_{m strictly below link(a)} Ic_m (sum_{b in dofs(m)} Hs_ab S_b),
+//     p_a = 2 Hs_aa S_a + sum_{b in anc(link(a)), b != a} Hs_ab S_b, with the COMPOSITE inertias Ic_m = sum_{l in subtree(m)} I_l
+//     (packed symmetric 6x6, accumulated leaves -> root in place in the reference's reversed link order, sim.py eval_crba):
+//     one 6x6 product per (dof, link below it) instead of a factored-inertia evaluation plus |anc(l)| axpys.
+// Scratch: the composites (L,21) live in the idle (Xl, vj, pX, af) region; g (D,6) in the aS slot itself, which is still all-zero
+// here (crba_adj is its first writer of the substep) and receives aS in the last pass.
+DFX_HD float hs_at(SP Hs, int D, int a, int b) { return Hs[a < b ? symD_idx(D, a, b) : symD_idx(D, b, a)]; }
+
+template <class Grp>
+DFX_HD void crba_adj(const Pack& P, const Layout& Y, SP s, const Grp& g) {
+    const int D = P.D, L = P.L;
+    const SP Hs = s + Y.Lm;
+    const SP Ic = s + Y.Xl;          // (L,21) <= (L,26)
+    const SP G = s + Y.aS;           // (D,6)
+    DFX_FOR(l, L) inertia_sym21(body_inertia(P, s + Y.Xsm + l * 7, l), Ic + l * 21);
+    DFX_FOR(a, D) {
+        const int la = P.dof_link[a];
+        SV ga = ld6(s + Y.S + a * 6) * (0.5f * Hs[symD_idx(D, a, a)]);
+        for (int kb = P.anc_start[la]; kb < P.anc_start[la + 1]; ++kb) {
+            const int b = P.anc_dofs[kb];
+            if (b >= a) break;                   // (ascending dof index)
+            ga += ld6(s + Y.S + b * 6) * (0.5f * Hs[symD_idx(D, b, a)]);
+        }
+        st6(G + a * 6, ga);
+    }
+    g.sync();
+    // composite inertias in place, leaves -> root (children have larger indices than their parents): one thread per packed entry
+    DFX_FOR(c, 21) {
+        for (int l = L - 1; l > 0; --l) {
+            const int par = P.parent[l];
+            if (par >= 0) Ic[par * 21 + c] += Ic[l * 21 + c];
+        }
+    }
+    // body inertia parameters from the moment matrix of the link
+    DFX_FOR(l, L) {
+        float K[21];
+#pragma unroll
+        for (int e = 0; e < 21; ++e) K[e] = 0.0f;
+        for (int ka = P.anc_start[l]; ka < P.anc_start[l + 1]; ++ka) {
+            const int a = P.anc_dofs[ka];
+            const SV Sa = ld6(s + Y.S + a * 6), ga = ld6(G + a * 6);
+            const float sv[6] = {Sa.w.x, Sa.w.y, Sa.w.z, Sa.v.x, Sa.v.y, Sa.v.z};
+            const float gv[6] = {ga.w.x, ga.w.y, ga.w.z, ga.v.x, ga.v.y, ga.v.z};
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = i; j < 6; ++j) K[sym_idx(i, j)] += sv[i] * gv[j] + gv[i] * sv[j];
+        }
+        const BodyInertia B = body_inertia(P, s + Y.Xsm + l * 7, l);
+        M3 aR = m3_zero();
+        V3 au = v3zero();
+        SV dummy = sv_zero();
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float col[6], ek[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { col[i] = K[i <= k ? sym_idx(i, k) : sym_idx(k, i)]; ek[i] = (i == k) ? 1.0f : 0.0f; }
+            inertia_apply_adj(B, SV{V3{col[0], col[1], col[2]}, V3{col[3], col[4], col[5]}},
+                              SV{V3{ek[0], ek[1], ek[2]}, V3{ek[3], ek[4], ek[5]}}, aR, au, dummy);
+        }
+        const SP o = s + Y.aIbar + l * 12;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) o[r * 3 + c] += aR.m[r][c];
+        add3(o + 9, au);
+    }
+    g.sync();
+    // motion subspace
+    DFX_FOR(a, D) {
+        const int la = P.dof_link[a];
+        SV pa = ld6(s + Y.S + a * 6) * (2.0f * Hs[symD_idx(D, a, a)]);
+        for (int kb = P.anc_start[la]; kb < P.anc_start[la + 1]; ++kb) {
+            const int b = P.anc_dofs[kb];
+            if (b != a) pa += ld6(s + Y.S + b * 6) * hs_at(Hs, D, a, b);
+        }
+        SV acc = sym21_apply(Ic + la * 21, pa);
+        for (int km = P.sub_start[la] + 1; km < P.sub_start[la + 1]; ++km) {      // (the list starts with la itself)
+            const int m = P.sub_links[km];
+            SV x = sv_zero();
+            for (int b = P.qd_start[m]; b < P.qd_start[m + 1]; ++b) x += ld6(s + Y.S + b * 6) * Hs[symD_idx(D, a, b)];    // (a < b)
+            acc += sym21_apply(Ic + m * 21, x);
+        }
+        st6(s + Y.aS + a * 6, acc);      // (over g_a: nobody reads g in this pass, and aS was zero on entry)
+    }
+    g.sync();
+}
+#endif
 
 // =====================================================================================
 // semi-implicit Euler

@@ -138,16 +138,19 @@ def test_explicit_inverse_is_not_the_parity_floor(name):
     assert err["hinv_fma"] < 2e-5 and err["sweeps_fma"] < 2e-5, err
 
 
+@pytest.mark.parametrize("flag", ["-DDFX_KIN_ADJ_CHAINS=1", "-DDFX_CRBA_ADJ_DIRECT=1"])
 @pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv"])
-def test_kinematics_adjoint_subtree_sums_match_the_recursion(name):
-    """The kinematics adjoint accumulates the (v, a) and X_sc cotangents towards the root as subtree sums (quaternion parts in
-    the world form, csrc/dfx_phases.h kin_adj) instead of the leaf -> root recursion the reference's reversed tape performs
-    (adjoint of sim.py:1668 / 1700-1720).  A/B on the host emulation, including states whose root quaternion is NOT unit
-    (the world form is exact for those too): both formulations against the reference's gradients and against each other."""
+def test_restructured_adjoints_match_the_direct_formulations(name, flag):
+    """Two adjoint phases are algebraic restructurings of what the reference's reversed tape performs (csrc/dfx_phases.h):
+      * kin_adj accumulates the (v, a) and X_sc cotangents towards the root as subtree sums, quaternion parts in the world form,
+        instead of the leaf -> root recursion (adjoint of sim.py:1668 / 1700-1720)             [A/B: -DDFX_KIN_ADJ_CHAINS=1]
+      * crba_adj uses composite inertias and one moment matrix per link instead of the double sums over ancestor dofs
+        (adjoint of eval_crba / eval_dense_gemm of the reference)                               [A/B: -DDFX_CRBA_ADJ_DIRECT=1]
+    A/B on the host emulation, including states whose root quaternion is NOT unit (the world form is exact for those too):
+    both formulations against the reference's gradients and against each other."""
     d, model = load_golden(name)
     N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
-    sums, chains = EmuSim(model, N), EmuSim(model, N, extra=("-DDFX_KIN_ADJ_CHAINS=1",))
-    rng = np.random.default_rng(5)
+    new, direct = EmuSim(model, N), EmuSim(model, N, extra=(flag,))
     for k in range(int(d["meta/num_cases"])):
         p = "case%d/" % k
         musc = d[p + "musc"] if (p + "musc") in d.files else None
@@ -156,12 +159,12 @@ def test_kinematics_adjoint_subtree_sums_match_the_recursion(name):
             if scale is not None:       # every free root: quaternion scaled away from unit length
                 q0.reshape(N, -1)[:, 3:7] *= scale
             got = []
-            for sim in (sums, chains):
+            for sim in (new, direct):
                 _, _, tape, _ = sim.forward(q0, d[p + "qd0"], d[p + "act"], musc, S, mm, dt)
                 got.append(sim.backward(d[p + "act"], musc, tape, d[p + "gq_out"], d[p + "gqd_out"], S, mm, dt))
             for a, b, key in zip(got[0], got[1], ("grad_q", "grad_qd", "grad_act", "grad_musc")):
                 if a is None:
                     continue
-                assert rel(a, b) < 3e-5, (name, k, scale, key, rel(a, b))
+                assert rel(a, b) < 6e-5, (name, k, scale, key, rel(a, b))     # (each is within GRAD_RTOL = 5e-5 of the reference)
                 if scale is None:
                     assert rel(a, d[p + key]) < GRAD_RTOL and rel(b, d[p + key]) < GRAD_RTOL, (name, k, key)
