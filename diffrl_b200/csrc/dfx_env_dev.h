@@ -1,0 +1,360 @@
+// dfx_env_dev.h -- per-environment device code of the env layer around the simulation step (observation, reward,
+// termination, masked re-initialisation and their adjoints; reference envs/ant.py:266-307, humanoid.py:314-368,
+// snu_humanoid.py:378-432, hopper.py:170-268, cheetah.py:160-244, cartpole_swing_up.py:120-187).  ONE environment per
+// call.  Used by the stand-alone env kernels (dfx_env.cu: one thread per environment) and by the tile kernels when the
+// transition rides inside the simulation launch (dfx_tile.cu: dfx_env_step_forward / _backward, the E environments of a
+// tile on the first E threads of the CTA).  The stepped state (qe, qde) is a template pointer: a global row for the stand-alone
+// kernels, the environment's strided shared-memory scratch (SP) for the fused launch -- no L2 round trip on the critical path of
+// the epilogue.  Plain pointers elsewhere on purpose: in the fused launch the state rows were written
+// by other threads of the same CTA (ordinary coherent loads after a CTA barrier, never the read-only path).
+#pragma once
+
+#include "../../include/dfx.h"
+#include "dfx_math.h"
+
+namespace dfx {
+
+constexpr int kMaxObs = 96;     // largest walker observation: Humanoid 76 (checked on the host before the launch)
+
+template <class QP, class QDP>
+__device__ __forceinline__ void walker_features(const DfxWalkerParams& p, QP q, QDP qd,
+                                                V3& pos, Q4& rot, V3& ang, V3& lin, V3& tt, float& tn, V3& tdir,
+                                                Q4& tq, V3& up, V3& heading) {
+    pos = ld3(q);
+    rot = ld4(q + 3);
+    ang = ld3(qd);
+    lin = ld3(qd + 3) - cross(pos, ang);   // twist at the world origin -> velocity of the torso origin
+    tt = V3{p.target[0] - pos.x, 0.0f, p.target[2] - pos.z};
+    tn = fmaxf(sqrtf(dot(tt, tt)), 1e-9f);
+    tdir = tt * (1.0f / tn);
+    tq = qmul(rot, ld4(p.inv_start_rot));
+    up = qrot(tq, ld3(p.basis_up));
+    heading = qrot(tq, ld3(p.basis_heading));
+}
+
+__device__ __forceinline__ float height_reward(const DfxWalkerParams& p, float h, float* dh) {
+    if (p.height_mode == 0) { *dh = 1.0f; return h - p.termination_height; }
+    if (p.height_mode == 2) { *dh = 0.0f; return 0.0f; }
+    // clip(h - (term + tol), -1, tol); r<0 -> -200 r^2 ; r>0 -> scale*r        (humanoid.py:348-351)
+    float x = h - (p.termination_height + p.termination_tolerance);
+    float r = fminf(fmaxf(x, -1.0f), p.termination_tolerance);
+    float dr = (x >= -1.0f && x <= p.termination_tolerance) ? 1.0f : 0.0f;   // torch.clip: gradient 1 inside, incl. the ends
+    if (r < 0.0f) { *dh = -400.0f * r * dr; return -200.0f * r * r; }
+    if (r > 0.0f) { *dh = p.height_rew_scale * dr; return p.height_rew_scale * r; }
+    *dh = dr;
+    return r;
+}
+
+// observation (always) and, when want_reward, reward + reset flag of ONE environment; `progress` is the step
+// counter AFTER this step.  `ae` == nullptr stands for all-zero actions (a freshly reset environment).
+template <class QP, class QDP>
+__device__ __forceinline__ void walker_eval(const DfxWalkerParams& p, QP qe, QDP qde,
+                                            const float* ae, long long progress, bool want_reward,
+                                            float* o, float* r_out, long long* rs_out) {
+    V3 pos, ang, lin, tt, tdir, up, heading;
+    Q4 rot, tq;
+    float tn;
+    walker_features(p, qe, qde, pos, rot, ang, lin, tt, tn, tdir, tq, up, heading);
+    int k = 0;
+    o[k++] = pos.y;
+    o[k++] = rot.x; o[k++] = rot.y; o[k++] = rot.z; o[k++] = rot.w;
+    o[k++] = lin.x; o[k++] = lin.y; o[k++] = lin.z;
+    o[k++] = ang.x; o[k++] = ang.y; o[k++] = ang.z;
+    bool bad = false;
+    for (int i = 7; i < p.num_q; ++i) o[k++] = qe[i];
+    for (int i = 6; i < p.num_qd; ++i) o[k++] = p.joint_vel_scale * qde[i];
+    const float up_y = up.y, hproj = dot(heading, tdir);
+    o[k++] = up_y;
+    o[k++] = hproj;
+    float act_sq = 0.0f, act_abs = 0.0f;
+    for (int i = 0; i < p.num_act; ++i) {
+        const float a = ae ? ae[i] : 0.0f;
+        if (p.obs_has_actions) o[k++] = a;
+        act_sq += a * a;
+        act_abs += fabsf(a);
+    }
+    if (!want_reward) return;
+    float dh;
+    const float hr = height_reward(p, pos.y, &dh);
+    float r = lin.x + 0.1f * up_y + hproj;
+    if (p.height_mode != 2) r += hr;
+    r += (p.action_penalty_abs ? act_abs : act_sq) * p.action_penalty;
+    long long rs = 0;
+    if (p.early_termination && pos.y < p.termination_height) rs = 1;
+    if (progress > (long long)p.episode_length - 1) rs = 1;
+    if (p.check_invalid) {
+        for (int i = 0; i < p.num_q; ++i) bad |= !isfinite(qe[i]) || fabsf(qe[i]) > 1e6f;
+        for (int i = 0; i < p.num_qd; ++i) bad |= !isfinite(qde[i]) || fabsf(qde[i]) > 1e6f;
+        for (int i = 0; i < p.num_obs; ++i) bad |= !isfinite(o[i]);
+        if (bad) { rs = 1; if (p.zero_reward_on_invalid) r = 0.0f; }
+    }
+    *r_out = r;
+    *rs_out = rs;
+}
+
+// adjoint of walker_eval for ONE environment: cotangents go (obs, nullable), go2 (a second observation cotangent
+// that is added to the first, nullable), gr (reward) -> gqe, gqde (overwritten), gae (nullable)
+__device__ __forceinline__ void walker_eval_adj(const DfxWalkerParams& p, const float* qe, const float* qde,
+                                                const float* ae, const float* go,
+                                                const float* go2, float gr, bool has_rew,
+                                                float* gqe, float* gqde, float* gae) {
+    V3 pos, ang, lin, tt, tdir, up, heading;
+    Q4 rot, tq;
+    float tn;
+    walker_features(p, qe, qde, pos, rot, ang, lin, tt, tn, tdir, tq, up, heading);
+    if (p.check_invalid && p.zero_reward_on_invalid && has_rew) {
+        bool bad = false;
+        for (int i = 0; i < p.num_q; ++i) bad |= !isfinite(qe[i]) || fabsf(qe[i]) > 1e6f;
+        for (int i = 0; i < p.num_qd; ++i) bad |= !isfinite(qde[i]) || fabsf(qde[i]) > 1e6f;
+        if (bad) gr = 0.0f;
+    }
+    float dh;
+    height_reward(p, pos.y, &dh);
+    int k = 0;
+    auto G = [&](int idx) { return (go ? go[idx] : 0.0f) + (go2 ? go2[idx] : 0.0f); };
+    // cotangents of the features
+    float a_posy = G(0) + (p.height_mode != 2 ? gr * dh : 0.0f);
+    Q4 a_rot = Q4{G(1), G(2), G(3), G(4)};
+    V3 a_lin = V3{G(5) + gr, G(6), G(7)};
+    V3 a_ang = V3{G(8), G(9), G(10)};
+    k = 11;
+    for (int i = 7; i < p.num_q; ++i) gqe[i] = G(k++);
+    for (int i = 6; i < p.num_qd; ++i) gqde[i] = p.joint_vel_scale * G(k++);
+    const float a_upy = G(k) + 0.1f * gr; ++k;
+    const float a_h = G(k) + gr; ++k;
+    if (gae) {
+        for (int i = 0; i < p.num_act; ++i) {
+            const float a = ae[i];
+            float g = p.obs_has_actions ? G(k + i) : 0.0f;
+            g += gr * p.action_penalty * (p.action_penalty_abs ? (a < 0.0f ? -1.0f : (a > 0.0f ? 1.0f : 0.0f)) : 2.0f * a);
+            gae[i] = g;
+        }
+    }
+    // hproj = heading . tdir
+    V3 a_heading = tdir * a_h;
+    V3 a_tdir = heading * a_h;
+    // tdir = tt / tn, tn = max(|tt|, eps)
+    V3 a_tt = a_tdir * (1.0f / tn);
+    if (sqrtf(dot(tt, tt)) > 1e-9f) a_tt -= tdir * (dot(a_tdir, tdir) / tn);
+    V3 a_pos = V3{-a_tt.x, a_posy, -a_tt.z};
+    // up = R(tq) b1 ; heading = R(tq) b0
+    Q4 a_tq = qrot_adj_q(tq, ld3(p.basis_up), V3{0.0f, a_upy, 0.0f});
+    a_tq += qrot_adj_q(tq, ld3(p.basis_heading), a_heading);
+    // tq = rot * inv_start
+    a_rot += qmul_adj_a(ld4(p.inv_start_rot), a_tq);
+    // lin = v - pos x ang
+    V3 a_v = a_lin;
+    V3 nl = -a_lin;
+    cross_adj(pos, ang, nl, a_pos, a_ang);
+    gqe[0] = a_pos.x; gqe[1] = a_pos.y; gqe[2] = a_pos.z;
+    gqe[3] = a_rot.x; gqe[4] = a_rot.y; gqe[5] = a_rot.z; gqe[6] = a_rot.w;
+    gqde[0] = a_ang.x; gqde[1] = a_ang.y; gqde[2] = a_ang.z;
+    gqde[3] = a_v.x; gqde[4] = a_v.y; gqde[5] = a_v.z;
+}
+
+// ---- the whole env transition after the simulation step, for ONE environment e:
+//   progress+1 -> observation, reward, termination (obs_before_reset) -> masked re-initialisation of a
+//   terminated environment (state <- start state, last actions <- 0, progress <- 0) -> observation of the
+//   state the next step starts from.  Replaces, per env.step(), ~35 small PyTorch ops (torch.where masks, clones,
+//   counters) and, in backward, their autograd nodes.
+template <class QP, class QDP>
+__device__ __forceinline__ void walker_transition_forward_env(const DfxWalkerParams& p, int e, QP qe, QDP qde,      // (qe, qde: this environment's rows)
+                                                              const float* actions, const long long* progress,
+                                                              const float* start_q, const float* start_qd,
+                                                              float* obs_before, float* rew, long long* reset,
+                                                              float* q_next, float* qd_next, float* actions_next,
+                                                              long long* progress_next, float* obs_next) {
+    const float* ae = actions + (size_t)e * p.num_act;
+    float* ob = obs_before + (size_t)e * p.num_obs;
+    float* on = obs_next + (size_t)e * p.num_obs;
+    const long long pr = progress[e] + 1;
+    float r = 0.0f;
+    long long rs = 0;
+    // the observation is formed in a thread-local buffer (L1-resident local memory) and written out once: forming it in
+    // place in global memory put a store -> load round trip through L2 on the critical path of this latency-bound code
+    // (the validity check and the pass-through to obs_next both read it back)
+    float o[kMaxObs];
+    walker_eval(p, qe, qde, ae, pr, true, o, &r, &rs);
+    rew[e] = r;
+    reset[e] = rs;
+    progress_next[e] = rs ? 0 : pr;
+    float* qn = q_next + (size_t)e * p.num_q;
+    float* qdn = qd_next + (size_t)e * p.num_qd;
+    float* an = actions_next + (size_t)e * p.num_act;
+    for (int i = 0; i < p.num_obs; ++i) ob[i] = o[i];
+    if (rs) {
+        const float* sq = start_q + (size_t)e * p.num_q;
+        const float* sqd = start_qd + (size_t)e * p.num_qd;
+        for (int i = 0; i < p.num_q; ++i) qn[i] = sq[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = sqd[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = 0.0f;
+        float r2; long long rs2;
+        walker_eval(p, sq, sqd, nullptr, 0, false, o, &r2, &rs2);
+    } else {
+        for (int i = 0; i < p.num_q; ++i) qn[i] = qe[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = qde[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = ae[i];
+    }
+    for (int i = 0; i < p.num_obs; ++i) on[i] = o[i];
+}
+
+// cotangents of (obs_before, rew, q_next, qd_next, actions_next, obs_next), any of them NULL == 0, -> gq, gqd, gact of
+// environment e.  A terminated environment passes nothing through its re-initialised outputs.
+__device__ __forceinline__ void walker_transition_backward_env(const DfxWalkerParams& p, int e, const float* q, const float* qd,
+                                                               const float* actions, const long long* reset,
+                                                               const float* g_obs_before, const float* g_rew,
+                                                               const float* g_q_next, const float* g_qd_next,
+                                                               const float* g_actions_next, const float* g_obs_next,
+                                                               float* gq, float* gqd, float* gact) {
+    const bool live = reset[e] == 0;
+    float* gqe = gq + (size_t)e * p.num_q;
+    float* gqde = gqd + (size_t)e * p.num_qd;
+    float* gae = gact ? gact + (size_t)e * p.num_act : nullptr;
+    walker_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
+                    g_obs_before ? g_obs_before + (size_t)e * p.num_obs : nullptr,
+                    (live && g_obs_next) ? g_obs_next + (size_t)e * p.num_obs : nullptr,
+                    g_rew ? g_rew[e] : 0.0f, g_rew != nullptr, gqe, gqde, gae);
+    if (!live) return;
+    if (g_q_next) { const float* g = g_q_next + (size_t)e * p.num_q;
+    for (int i = 0; i < p.num_q; ++i) gqe[i] += g[i]; }
+    if (g_qd_next) { const float* g = g_qd_next + (size_t)e * p.num_qd;
+    for (int i = 0; i < p.num_qd; ++i) gqde[i] += g[i]; }
+    if (gae && g_actions_next) { const float* g = g_actions_next + (size_t)e * p.num_act;
+    for (int i = 0; i < p.num_act; ++i) gae[i] += g[i]; }
+}
+
+// ---- planar envs (Hopper, HalfCheetah: observation = [q[1:], qd]; CartPole swing-up: [x, xd, sin th, cos th, thd]):
+// the same transition as walker_transition_*, reference envs/hopper.py:170-268, envs/cheetah.py:160-244,
+// envs/cartpole_swing_up.py:120-187
+template <class QP, class QDP>
+__device__ __forceinline__ void planar_eval(const DfxPlanarParams& p, QP qe, QDP qde,
+                                            const float* ae, long long progress, bool want_reward,
+                                            float* o, float* r_out, long long* rs_out) {
+    float act_sq = 0.0f;
+    for (int i = 0; i < p.num_act; ++i) { const float a = ae ? ae[i] : 0.0f; act_sq += a * a; }
+    if (p.kind == 2) {                      // CartPole
+        const float x = qe[0], th = qe[1], xd = qde[0], thd = qde[1];
+        o[0] = x; o[1] = xd; o[2] = sinf(th); o[3] = cosf(th); o[4] = thd;
+        if (!want_reward) return;
+        const float t = atan2f(sinf(th), cosf(th));                  // normalize_angle
+        *r_out = -(t * t) * p.pole_angle_penalty - (thd * thd) * p.pole_velocity_penalty - (x * x) * p.cart_position_penalty
+                 - (xd * xd) * p.cart_velocity_penalty - act_sq * p.action_penalty;
+        *rs_out = (progress > (long long)p.episode_length - 1) ? 1 : 0;
+        return;
+    }
+    int k = 0;
+    for (int i = 1; i < p.num_q; ++i) o[k++] = qe[i];
+    for (int i = 0; i < p.num_qd; ++i) o[k++] = qde[i];
+    if (!want_reward) return;
+    const float vx = qde[0];                // o[num_q - 1]
+    long long rs = (progress > (long long)p.episode_length - 1) ? 1 : 0;
+    if (p.kind == 0) {                      // Hopper
+        const float h0 = qe[1], ang = qe[2];
+        float h = fminf(fmaxf(h0 - (p.termination_height + p.termination_height_tolerance), -1.0f), 0.3f);
+        if (h < 0.0f) h = -200.0f * h * h;
+        if (h > 0.0f) h = p.height_rew_scale * h;
+        const float angle_reward = 1.0f * (-(ang * ang) / (p.termination_angle * p.termination_angle) + 1.0f);
+        *r_out = vx + h + angle_reward + act_sq * p.action_penalty;
+        if (p.early_termination && h0 < p.termination_height) rs = 1;
+    } else {                                // HalfCheetah
+        *r_out = vx + act_sq * p.action_penalty;
+    }
+    *rs_out = rs;
+}
+
+__device__ __forceinline__ void planar_eval_adj(const DfxPlanarParams& p, const float* qe, const float* qde,
+                                                const float* ae, const float* go,
+                                                const float* go2, float gr,
+                                                float* gqe, float* gqde, float* gae) {
+    auto G = [&](int idx) { return (go ? go[idx] : 0.0f) + (go2 ? go2[idx] : 0.0f); };
+    if (gae) for (int i = 0; i < p.num_act; ++i) gae[i] = (p.kind == 2 ? -1.0f : 1.0f) * gr * p.action_penalty * 2.0f * ae[i];
+    if (p.kind == 2) {
+        const float x = qe[0], th = qe[1], xd = qde[0], thd = qde[1];
+        const float t = atan2f(sinf(th), cosf(th));
+        gqe[0] = G(0) - gr * 2.0f * x * p.cart_position_penalty;
+        gqe[1] = G(2) * cosf(th) - G(3) * sinf(th) - gr * 2.0f * t * p.pole_angle_penalty;     // d normalize_angle / d th = 1
+        gqde[0] = G(1) - gr * 2.0f * xd * p.cart_velocity_penalty;
+        gqde[1] = G(4) - gr * 2.0f * thd * p.pole_velocity_penalty;
+        return;
+    }
+    int k = 0;
+    gqe[0] = 0.0f;
+    for (int i = 1; i < p.num_q; ++i) gqe[i] = G(k++);
+    for (int i = 0; i < p.num_qd; ++i) gqde[i] = G(k++);
+    gqde[0] += gr;
+    if (p.kind == 0) {
+        const float h0 = qe[1], ang = qe[2];
+        const float x = h0 - (p.termination_height + p.termination_height_tolerance);
+        const float h = fminf(fmaxf(x, -1.0f), 0.3f);
+        const float dclip = (x >= -1.0f && x <= 0.3f) ? 1.0f : 0.0f;     // torch.clip passes the gradient on the closed interval
+        float dh = dclip;                                                   // h == 0: both torch.where keep h
+        if (h < 0.0f) dh = -400.0f * h * dclip;
+        else if (h > 0.0f) dh = p.height_rew_scale * dclip;
+        gqe[1] += gr * dh;
+        gqe[2] += gr * (-2.0f * ang / (p.termination_angle * p.termination_angle));
+    }
+}
+
+template <class QP, class QDP>
+__device__ __forceinline__ void planar_transition_forward_env(const DfxPlanarParams& p, int e, QP qe, QDP qde,      // (qe, qde: this environment's rows)
+                                                              const float* actions, const long long* progress,
+                                                              const float* start_q, const float* start_qd,
+                                                              float* obs_before, float* rew, long long* reset,
+                                                              float* q_next, float* qd_next, float* actions_next,
+                                                              long long* progress_next, float* obs_next) {
+    const float* ae = actions + (size_t)e * p.num_act;
+    float* ob = obs_before + (size_t)e * p.num_obs;
+    float* on = obs_next + (size_t)e * p.num_obs;
+    const long long pr = progress[e] + 1;
+    float r = 0.0f;
+    long long rs = 0;
+    planar_eval(p, qe, qde, ae, pr, true, ob, &r, &rs);
+    rew[e] = r;
+    reset[e] = rs;
+    progress_next[e] = rs ? 0 : pr;
+    float* qn = q_next + (size_t)e * p.num_q;
+    float* qdn = qd_next + (size_t)e * p.num_qd;
+    float* an = actions_next + (size_t)e * p.num_act;
+    if (rs) {
+        const float* sq = start_q + (size_t)e * p.num_q;
+        const float* sqd = start_qd + (size_t)e * p.num_qd;
+        for (int i = 0; i < p.num_q; ++i) qn[i] = sq[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = sqd[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = p.zero_actions_on_reset ? 0.0f : ae[i];
+        float r2; long long rs2;
+        planar_eval(p, sq, sqd, p.zero_actions_on_reset ? nullptr : ae, 0, false, on, &r2, &rs2);
+    } else {
+        for (int i = 0; i < p.num_q; ++i) qn[i] = qe[i];
+        for (int i = 0; i < p.num_qd; ++i) qdn[i] = qde[i];
+        for (int i = 0; i < p.num_act; ++i) an[i] = ae[i];
+        for (int i = 0; i < p.num_obs; ++i) on[i] = ob[i];
+    }
+}
+
+__device__ __forceinline__ void planar_transition_backward_env(const DfxPlanarParams& p, int e, const float* q, const float* qd,
+                                                               const float* actions, const long long* reset,
+                                                               const float* g_obs_before, const float* g_rew,
+                                                               const float* g_q_next, const float* g_qd_next,
+                                                               const float* g_actions_next, const float* g_obs_next,
+                                                               float* gq, float* gqd, float* gact) {
+    const bool live = reset[e] == 0;
+    float* gqe = gq + (size_t)e * p.num_q;
+    float* gqde = gqd + (size_t)e * p.num_qd;
+    float* gae = gact ? gact + (size_t)e * p.num_act : nullptr;
+    planar_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
+                    g_obs_before ? g_obs_before + (size_t)e * p.num_obs : nullptr,
+                    (live && g_obs_next) ? g_obs_next + (size_t)e * p.num_obs : nullptr,
+                    g_rew ? g_rew[e] : 0.0f, gqe, gqde, gae);
+    // the actions survive a reset in envs that do not clear them (CartPole): their cotangent passes either way
+    if (gae && g_actions_next && (live || !p.zero_actions_on_reset)) {
+        const float* g = g_actions_next + (size_t)e * p.num_act;
+        for (int i = 0; i < p.num_act; ++i) gae[i] += g[i];
+    }
+    if (!live) return;
+    if (g_q_next) { const float* g = g_q_next + (size_t)e * p.num_q;
+    for (int i = 0; i < p.num_q; ++i) gqe[i] += g[i]; }
+    if (g_qd_next) { const float* g = g_qd_next + (size_t)e * p.num_qd;
+    for (int i = 0; i < p.num_qd; ++i) gqde[i] += g[i]; }
+}
+
+}  // namespace dfx

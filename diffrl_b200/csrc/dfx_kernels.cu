@@ -25,6 +25,7 @@ template <int G_>
 struct GroupCuda {
     static constexpr int G = G_;
     static constexpr bool kPathPasses = false;   // group barriers are cheap: level-by-level tree recursions
+    static constexpr bool kFusedPhases = false;  // (merging phases saves CTA-wide barriers: nothing to gain with group-level ones)
     int lane;
     unsigned mask;
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
@@ -220,6 +221,7 @@ static int g_tape_bf16 = 0;   // dfx_set_tape_dtype
 static int g_tile_envs = 0;   // dfx_set_tile_envs: 0 = the widest tile kernel that exists for the articulation
 
 static int tile_mode(int E, const Pack& h) {
+    if (h.jmask & ~tile_joint_mask(h.L, h.D, h.Q, h.C, h.M)) return -1;     // a joint type the tile kernels of these sizes are not compiled for
     switch (E) {
         case 8: return dfx_tile_mode_e8(h.L, h.D, h.Q, h.C, h.M);
         case 16: return dfx_tile_mode_e16(h.L, h.D, h.Q, h.C, h.M);
@@ -535,6 +537,72 @@ int dfx_step_backward_mapped(const dfx_pack_t* p, int n, int substeps, int mm_fr
     a.raw = raw; a.tape_in = tape; a.gq_out = gq_out; a.gqd_out = gqd_out; a.g_used = g_used;
     a.gq = gq; a.gqd = gqd; a.g_raw = g_raw;
     if (a.map_muscle) a.act = act_other; else a.musc = act_other;
+    return run_step(p, a, true, stream);
+}
+
+// ---- env.step() as one launch (include/dfx.h): the mapped step with the transition as epilogue (tile kernels), or the two
+// launches back to back (lane-group kernels)
+static bool transition_ok(int kind, const DfxWalkerParams& w, const DfxPlanarParams& pl, const dfx_pack_t* p, const DfxActionMap* m) {
+    if (kind == 1) return w.num_q == p->header.Q && w.num_qd == p->header.D && w.num_act == m->num_act && w.num_obs > 0 && w.num_obs <= 96;
+    if (kind == 2) return pl.num_q == p->header.Q && pl.num_qd == p->header.D && pl.num_act == m->num_act && pl.num_obs > 0 && pl.kind >= 0 && pl.kind <= 2;
+    return false;
+}
+
+int dfx_env_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
+                         const float* q, const float* qd, const DfxActionMap* map, const float* raw, const float* act_other,
+                         float* used, float* q_sim, float* qd_sim, float* tape, const DfxEnvTransition* tr, void* stream) {
+    if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0 || !q || !qd || !map || !raw || !used || !q_sim || !qd_sim || !tr) return (int)cudaErrorInvalidValue;
+    if (!transition_ok(tr->kind, tr->walker, tr->planar, p, map)) return (int)cudaErrorInvalidValue;
+    if (!tr->progress || !tr->start_q || !tr->start_qd || !tr->obs_before || !tr->rew || !tr->reset || !tr->q_next || !tr->qd_next ||
+        !tr->actions_next || !tr->progress_next || !tr->obs_next) return (int)cudaErrorInvalidValue;
+    if (!p->tile) {
+        const int e = dfx_step_forward_mapped(p, n, substeps, mm_freq, dt, q, qd, map, raw, act_other, used, q_sim, qd_sim, tape, stream);
+        if (e != 0) return e;
+        return tr->kind == 1
+            ? dfx_walker_transition_forward(&tr->walker, n, q_sim, qd_sim, used, tr->progress, tr->start_q, tr->start_qd, tr->obs_before, tr->rew,
+                                            tr->reset, tr->q_next, tr->qd_next, tr->actions_next, tr->progress_next, tr->obs_next, stream)
+            : dfx_planar_transition_forward(&tr->planar, n, q_sim, qd_sim, used, tr->progress, tr->start_q, tr->start_qd, tr->obs_before, tr->rew,
+                                            tr->reset, tr->q_next, tr->qd_next, tr->actions_next, tr->progress_next, tr->obs_next, stream);
+    }
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    if (!bind_map(p, map, a)) return (int)cudaErrorInvalidValue;
+    if (!a.map_muscle && p->header.M > 0 && !act_other) return (int)cudaErrorInvalidValue;
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.q = q; a.qd = qd; a.raw = raw; a.used = used; a.q_out = q_sim; a.qd_out = qd_sim; a.tape = tape;
+    if (a.map_muscle) a.act = act_other; else a.musc = act_other;
+    a.env_kind = tr->kind;
+    a.env = *tr;
+    return run_step(p, a, false, stream);
+}
+
+int dfx_env_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq, double dt,
+                          const DfxActionMap* map, const float* raw, const float* act_other, const float* tape,
+                          const DfxEnvTransitionAdj* tr, float* gq, float* gqd, float* g_raw, void* stream) {
+    if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0 || !tape || !map || !raw || !tr) return (int)cudaErrorInvalidValue;
+    if (!transition_ok(tr->kind, tr->walker, tr->planar, p, map)) return (int)cudaErrorInvalidValue;
+    if (!tr->q_sim || !tr->qd_sim || !tr->used || !tr->reset || !tr->gq_sim || !tr->gqd_sim || !tr->g_used) return (int)cudaErrorInvalidValue;
+    if (!p->tile) {
+        const int e = tr->kind == 1
+            ? dfx_walker_transition_backward(&tr->walker, n, tr->q_sim, tr->qd_sim, tr->used, tr->reset, tr->g_obs_before, tr->g_rew, tr->g_q_next,
+                                             tr->g_qd_next, tr->g_actions_next, tr->g_obs_next, tr->gq_sim, tr->gqd_sim, tr->g_used, stream)
+            : dfx_planar_transition_backward(&tr->planar, n, tr->q_sim, tr->qd_sim, tr->used, tr->reset, tr->g_obs_before, tr->g_rew, tr->g_q_next,
+                                             tr->g_qd_next, tr->g_actions_next, tr->g_obs_next, tr->gq_sim, tr->gqd_sim, tr->g_used, stream);
+        if (e != 0) return e;
+        return dfx_step_backward_mapped(p, n, substeps, mm_freq, dt, map, raw, act_other, tape, tr->gq_sim, tr->gqd_sim, tr->g_used, gq, gqd, g_raw, stream);
+    }
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    if (!bind_map(p, map, a)) return (int)cudaErrorInvalidValue;
+    if (!a.map_muscle && p->header.M > 0 && !act_other) return (int)cudaErrorInvalidValue;
+    a.N = n; a.substeps = substeps; a.mm_freq = mm_freq;
+    a.dt_sub = (float)(dt / (double)substeps);
+    a.raw = raw; a.tape_in = tape; a.gq_out = tr->gq_sim; a.gqd_out = tr->gqd_sim; a.g_used = tr->g_used;
+    a.gq = gq; a.gqd = gqd; a.g_raw = g_raw;
+    if (a.map_muscle) a.act = act_other; else a.musc = act_other;
+    a.env_kind = tr->kind;
+    a.env_adj = *tr;
     return run_step(p, a, true, stream);
 }
 

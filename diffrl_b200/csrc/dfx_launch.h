@@ -41,6 +41,20 @@ __device__ __forceinline__ Pack bind_pack(const Pack& header, const PackBlob& b,
     return p;
 }
 
+// joint types the size-specialised tile kernel of an articulation is COMPILED for (Pack::jmask as a constant: the branches of
+// the other types are not in the binary).  A pack whose links have any other type never gets a tile kernel (dfx_pack_create falls
+// back to the lane-group kernels, which read the mask at run time).
+DFX_LAYOUT_FN int tile_joint_mask(int L, int D, int Q, int C, int M) {
+    constexpr int P = 1 << JOINT_PRISMATIC, R = 1 << JOINT_REVOLUTE, B = 1 << JOINT_BALL, F = 1 << JOINT_FREE;
+    if (L == 9 && D == 14 && Q == 15 && C == 25 && M == 0) return F | R;          // Ant
+    if (L == 22 && D == 27 && Q == 28 && C == 35 && M == 0) return F | R;         // Humanoid
+    if (L == 11 && D == 24 && Q == 29 && C == 88 && M == 152) return F | B | R;   // SNU humanoid
+    if (L == 3 && D == 2 && Q == 2 && C == 0 && M == 0) return P | R | (1 << JOINT_FIXED);   // CartPole (fixed rail link)
+    if (L == 6 && D == 6 && Q == 6 && C == 8 && M == 0) return P | R;             // Hopper
+    if (L == 9 && D == 9 && Q == 9 && C == 16 && M == 0) return P | R;            // HalfCheetah
+    return kJointMaskAll;
+}
+
 struct KernelArgs {
     Pack header;
     PackBlob blob;

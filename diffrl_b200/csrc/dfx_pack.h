@@ -10,6 +10,7 @@
 namespace dfx {
 
 enum JointType { JOINT_PRISMATIC = 0, JOINT_REVOLUTE = 1, JOINT_BALL = 2, JOINT_FIXED = 3, JOINT_FREE = 4 };
+constexpr int kJointMaskAll = 31;
 
 struct Pack {
     // sizes (per environment)
@@ -24,6 +25,9 @@ struct Pack {
     int MG;      // muscle groups (below)
     int root_round_single;   // the last chain round holds nothing but single-link chains of roots (a root -> leaf recursion skips it)
     int ground;  // model.ground && C > 0
+    int jmask;   // bit t set: some link has joint type t.  The size-specialised tile kernels overwrite it with a compile-time constant
+                 // (like L, D, Q, C, M) so that the branches of absent joint types are not compiled in: the per-substep body of the
+                 // adjoint is ~150 KB of SASS against a 32 KB instruction cache, every dead branch costs fetches
     float gx, gy, gz;
 
     // ---- per link (L) ----

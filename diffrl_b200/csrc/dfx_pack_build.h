@@ -219,6 +219,8 @@ inline bool build_pack(const DfxModelDesc& d, PackHost& out, std::string& err) {
     round_start[nround] = (int)chain_start.size();
     chain_start.push_back((int)chain_links.size());
     h.nround = nround;
+    h.jmask = 0;
+    for (int i = 0; i < L; ++i) h.jmask |= 1 << d.joint_type[i];
     h.root_round_single = 1;
     for (size_t c = 0; c < chains.size(); ++c)
         if (chain_round[c] == nround - 1 && (chains[c].size() != 1 || parent[chains[c][0]] >= 0)) h.root_round_single = 0;

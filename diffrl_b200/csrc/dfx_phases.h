@@ -77,6 +77,13 @@ struct GroupSerial {  // host / single-lane execution
 #define DFX_EMU_PATH_PASSES 0
 #endif
     static constexpr bool kPathPasses = DFX_EMU_PATH_PASSES != 0;   // see kin_fwd / tau_fwd
+#ifndef DFX_EMU_FUSED_PHASES
+#define DFX_EMU_FUSED_PHASES 0
+#endif
+    // phases merged to save CTA-wide barriers (tile kernels): the joint-local transforms of the NEXT substep are formed by the
+    // thread that integrates the link (integrate_fwd), and the torque adjoint recomputes the ancestors' direct cotangents along
+    // each link's root path instead of staging them (tau_adj) -- the same operations in the same order, bit-identical results
+    static constexpr bool kFusedPhases = DFX_EMU_FUSED_PHASES != 0;
     int lane;
     DFX_HD void sync() const {}
     DFX_HD void phase_sync() const {}
@@ -141,6 +148,10 @@ struct GroupSerial {  // host / single-lane execution
     DFX_HD void copy_wait_all() const {}
 };
 
+// joint-type test that folds away for the types an articulation does not have (P.jmask is a compile-time constant in the
+// size-specialised tile kernels, dfx_pack.h)
+DFX_HD bool is_joint(const Pack& P, int type, int t) { return ((P.jmask >> t) & 1) != 0 && type == t; }
+
 #define DFX_FOR(i, n) for (int i = g.lane; i < (n); i += Grp::G)
 
 // One level of a HEAVY tree recursion (the two leaf->root passes of the kinematics adjoint).  A level of a DiffRL
@@ -202,10 +213,10 @@ DFX_HD void zero_range(SP p, int n, const Grp& g) {
 DFX_HD Xf joint_transform(const Pack& P, SP q, int i) {
     const int type = P.type[i], qs = P.q_start[i];
     Xf Xjc = xf_ident();
-    if (type == JOINT_PRISMATIC) Xjc.p = ld3(P.axis + i * 3) * q[qs];
-    else if (type == JOINT_REVOLUTE) Xjc.q = q_from_axis_angle(ld3(P.axis + i * 3), q[qs]);
-    else if (type == JOINT_BALL) Xjc.q = ld4(q + qs);
-    else if (type == JOINT_FREE) { Xjc.p = ld3(q + qs); Xjc.q = ld4(q + qs + 3); }
+    if (is_joint(P, type, JOINT_PRISMATIC)) Xjc.p = ld3(P.axis + i * 3) * q[qs];
+    else if (is_joint(P, type, JOINT_REVOLUTE)) Xjc.q = q_from_axis_angle(ld3(P.axis + i * 3), q[qs]);
+    else if (is_joint(P, type, JOINT_BALL)) Xjc.q = ld4(q + qs);
+    else if (is_joint(P, type, JOINT_FREE)) { Xjc.p = ld3(q + qs); Xjc.q = ld4(q + qs + 3); }
     return Xjc;
 }
 
@@ -249,16 +260,16 @@ DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     const SP qd = s + Y.qd;
     const SP S = s + Y.S;
     SV vj = sv_zero();
-    if (type == JOINT_PRISMATIC) {
+    if (is_joint(P, type, JOINT_PRISMATIC)) {
         SV Sk = SV{v3zero(), qrot(Xsj.q, axis)};
         st6(S + ds * 6, Sk);
         vj = Sk * qd[ds];
-    } else if (type == JOINT_REVOLUTE) {
+    } else if (is_joint(P, type, JOINT_REVOLUTE)) {
         V3 w = qrot(Xsj.q, axis);
         SV Sk = SV{w, cross(Xsj.p, w)};
         st6(S + ds * 6, Sk);
         vj = Sk * qd[ds];
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         for (int k = 0; k < 3; ++k) {
             V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
             V3 w = qrot(Xsj.q, e);
@@ -266,7 +277,7 @@ DFX_HD void kin_motion_fwd(const Pack& P, const Layout& Y, SP s, int i) {
             st6(S + (ds + k) * 6, Sk);
             vj = (k == 0) ? Sk * qd[ds] : vj + Sk * qd[ds + k];
         }
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         for (int k = 0; k < 6; ++k)
             for (int c = 0; c < 6; ++c) S[(ds + k) * 6 + c] = (k == c) ? 1.0f : 0.0f;
         vj = ld6(qd + ds);
@@ -307,9 +318,11 @@ DFX_HD void kin_velocity_fwd(const Pack& P, const Layout& Y, SP s, int i) {  // 
 
 template <class Grp>
 DFX_HD void kin_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
-    DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
-    g.row_reusable();      // (K1 wrote temporaries only; from the next pass on the tape row of the previous substep is overwritten)
-    g.sync();
+    if constexpr (!Grp::kFusedPhases) {
+        DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
+        g.row_reusable();      // (K1 wrote temporaries only; from the next pass on the tape row of the previous substep is overwritten)
+        g.sync();
+    }   // (kFusedPhases: K1 ran at the end of the previous substep, inside integrate_fwd -- or before the first substep)
     if constexpr (Grp::kPathPasses) {
         // every barrier is CTA-wide here: each link walks its own path from the root, three barriers in all
         DFX_FOR(i, P.L) kin_motion_fwd<true>(P, Y, s, i);
@@ -345,9 +358,9 @@ DFX_HD void kin_adj_local(const Pack& P, const Layout& Y, SP s, int i) {    // A
     const SP qd = s + Y.qd;
     const SP S = s + Y.S;
     SV vj = sv_zero();
-    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) vj = ld6(S + ds * 6) * qd[ds];
-    else if (type == JOINT_BALL) { for (int k = 0; k < 3; ++k) vj += ld6(S + (ds + k) * 6) * qd[ds + k]; }
-    else if (type == JOINT_FREE) vj = ld6(qd + ds);
+    if (is_joint(P, type, JOINT_PRISMATIC) || is_joint(P, type, JOINT_REVOLUTE)) vj = ld6(S + ds * 6) * qd[ds];
+    else if (is_joint(P, type, JOINT_BALL)) { for (int k = 0; k < 3; ++k) vj += ld6(S + (ds + k) * 6) * qd[ds + k]; }
+    else if (is_joint(P, type, JOINT_FREE)) vj = ld6(qd + ds);
     st6(s + Y.vj + i * 6, vj);
 }
 
@@ -382,22 +395,22 @@ DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // 
     const SP aS = s + Y.aS;
     const SP aqd = s + Y.aqd;
     Xf aXsj = xf_zero();
-    if (type == JOINT_PRISMATIC) {
+    if (is_joint(P, type, JOINT_PRISMATIC)) {
         const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
         aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
         aXsj.q += qrot_adj_q(Xsj.q, axis, aSk.v);   // S.v = R axis
-    } else if (type == JOINT_REVOLUTE) {
+    } else if (is_joint(P, type, JOINT_REVOLUTE)) {
         const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
         aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
         xf_twist_adj_t(Xsj, SV{axis, v3zero()}, aSk, aXsj);
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         for (int k = 0; k < 3; ++k) {
             const SV aSk = ld6(aS + (ds + k) * 6) + avj * qd[ds + k];
             aqd[ds + k] += sv_dot(ld6(S + (ds + k) * 6), avj);
             V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
             xf_twist_adj_t(Xsj, SV{e, v3zero()}, aSk, aXsj);
         }
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         add6(aqd + ds, avj);
     }
     // X_sj = X_p X_pj: this link's push to its parent through the joint frame does not depend on the recursion
@@ -422,7 +435,7 @@ DFX_HD void kin_adj_chain(const Pack& P, const Layout& Y, SP s, int i) {     // 
 
 DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // A5
     const int par = P.parent[i], type = P.type[i], qs = P.q_start[i];
-    if (type == JOINT_FIXED) return;
+    if (is_joint(P, type, JOINT_FIXED)) return;
     const Xf Xp = par >= 0 ? ld7(s + Y.Xsc + par * 7) : xf_ident();
     const Xf Xpj = ld7(P.X_pj + i * 7);
     const SP q = s + Y.q;
@@ -430,10 +443,10 @@ DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // 
     const Xf aXl = xf_mul_adj_b(Xp, ld7(s + Y.aXsc + i * 7));   // X_sc = X_p X_l
     const Xf aXjc = xf_mul_adj_b(Xpj, aXl);                      // X_l = X_pj X_jc
     const V3 axis = ld3(P.axis + i * 3);
-    if (type == JOINT_PRISMATIC) aq[qs] += dot(axis, aXjc.p);
-    else if (type == JOINT_REVOLUTE) aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
-    else if (type == JOINT_BALL) add4(aq + qs, aXjc.q);
-    else if (type == JOINT_FREE) { add3(aq + qs, aXjc.p); add4(aq + qs + 3, aXjc.q); }
+    if (is_joint(P, type, JOINT_PRISMATIC)) aq[qs] += dot(axis, aXjc.p);
+    else if (is_joint(P, type, JOINT_REVOLUTE)) aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
+    else if (is_joint(P, type, JOINT_BALL)) add4(aq + qs, aXjc.q);
+    else if (is_joint(P, type, JOINT_FREE)) { add3(aq + qs, aXjc.p); add4(aq + qs + 3, aXjc.q); }
 }
 
 template <class Grp>
@@ -488,22 +501,22 @@ DFX_HD void kin_adj_motion(const Pack& P, const Layout& Y, SP s, int i) {    // 
     const SP aS = s + Y.aS;
     const SP aqd = s + Y.aqd;
     Xf aXsj = xf_zero();
-    if (type == JOINT_PRISMATIC) {
+    if (is_joint(P, type, JOINT_PRISMATIC)) {
         const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
         aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
         aXsj.q += qrot_adj_q(Xsj.q, axis, aSk.v);   // S.v = R axis
-    } else if (type == JOINT_REVOLUTE) {
+    } else if (is_joint(P, type, JOINT_REVOLUTE)) {
         const SV aSk = ld6(aS + ds * 6) + avj * qd[ds];
         aqd[ds] += sv_dot(ld6(S + ds * 6), avj);
         xf_twist_adj_t(Xsj, SV{axis, v3zero()}, aSk, aXsj);
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         for (int k = 0; k < 3; ++k) {
             const SV aSk = ld6(aS + (ds + k) * 6) + avj * qd[ds + k];
             aqd[ds + k] += sv_dot(ld6(S + (ds + k) * 6), avj);
             V3 e = V3{k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f};
             xf_twist_adj_t(Xsj, SV{e, v3zero()}, aSk, aXsj);
         }
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         add6(aqd + ds, avj);
     }
     // X_sj = X_p X_pj: the cotangent of X_p, quaternion part in the world form at the parent
@@ -537,7 +550,7 @@ DFX_HD void kin_adj_world(const Pack& P, const Layout& Y, SP s, int i) {     // 
 
 DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // B4 + A5
     const int par = P.parent[i], type = P.type[i], qs = P.q_start[i];
-    if (type == JOINT_FIXED) return;
+    if (is_joint(P, type, JOINT_FIXED)) return;
     Q4 u = ld4(s + Y.aXsc + i * 7 + 3);
     for (int k = P.sub_start[i] + 1; k < P.sub_start[i + 1]; ++k) u += ld4(s + Y.aXsm + P.sub_links[k] * 7 + 3);
     const Q4 qi = ld4(s + Y.Xsc + i * 7 + 3);
@@ -550,10 +563,10 @@ DFX_HD void kin_adj_joint(const Pack& P, const Layout& Y, SP s, int i) {     // 
     const Xf aXl = xf_mul_adj_b(Xp, aXsc);                       // X_sc = X_p X_l
     const Xf aXjc = xf_mul_adj_b(Xpj, aXl);                      // X_l = X_pj X_jc
     const V3 axis = ld3(P.axis + i * 3);
-    if (type == JOINT_PRISMATIC) aq[qs] += dot(axis, aXjc.p);
-    else if (type == JOINT_REVOLUTE) aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
-    else if (type == JOINT_BALL) add4(aq + qs, aXjc.q);
-    else if (type == JOINT_FREE) { add3(aq + qs, aXjc.p); add4(aq + qs + 3, aXjc.q); }
+    if (is_joint(P, type, JOINT_PRISMATIC)) aq[qs] += dot(axis, aXjc.p);
+    else if (is_joint(P, type, JOINT_REVOLUTE)) aq[qs] += q_from_axis_angle_adj_angle(axis, q[qs], aXjc.q);
+    else if (is_joint(P, type, JOINT_BALL)) add4(aq + qs, aXjc.q);
+    else if (is_joint(P, type, JOINT_FREE)) { add3(aq + qs, aXjc.p); add4(aq + qs + 3, aXjc.q); }
 }
 
 template <class Grp>
@@ -1072,7 +1085,7 @@ DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, SP s, int i) {
     const SP S = s + Y.S;
     const SP tau = s + Y.tau;
     const float tke = P.target_ke[i], tkd = P.target_kd[i];
-    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+    if (is_joint(P, type, JOINT_PRISMATIC) || is_joint(P, type, JOINT_REVOLUTE)) {
         const float qq = q[qs], qdv = qd[ds];
         const float lower = P.limit_lower[qs], upper = P.limit_upper[qs];
         float limit_f = 0.0f;
@@ -1080,10 +1093,10 @@ DFX_HD void tau_project_fwd(const Pack& P, const Layout& Y, SP s, int i) {
         if (qq > upper) limit_f = P.limit_ke[i] * (upper - qq);
         const float damping_f = (0.0f - P.limit_kd[i]) * qdv;
         tau[ds] = 0.0f - sv_dot(ld6(S + ds * 6), f) - tke * (qq - P.target[qs]) - tkd * qdv + s[Y.act + ds] + limit_f + damping_f;
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         for (int k = 0; k < 3; ++k)
             tau[ds + k] = 0.0f - sv_dot(ld6(S + (ds + k) * 6), f) - qd[ds + k] * tkd - q[qs + k] * tke;
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         tau[ds + 0] = 0.0f - f.w.x; tau[ds + 1] = 0.0f - f.w.y; tau[ds + 2] = 0.0f - f.w.z;
         tau[ds + 3] = 0.0f - f.v.x; tau[ds + 4] = 0.0f - f.v.y; tau[ds + 5] = 0.0f - f.v.z;
     }
@@ -1112,7 +1125,7 @@ DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, SP s, SP atau, int i
     const SP aS = s + Y.aS;
     const SP aq = s + Y.aq;
     const SP aqd = s + Y.aqd;
-    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+    if (is_joint(P, type, JOINT_PRISMATIC) || is_joint(P, type, JOINT_REVOLUTE)) {
         const float at = atau[ds];
         add6(aS + ds * 6, f * (-at));
         af += ld6(S + ds * 6) * (-at);
@@ -1123,7 +1136,7 @@ DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, SP s, SP atau, int i
         aq[qs] += (dlim - P.target_ke[i]) * at;
         aqd[ds] += (0.0f - P.target_kd[i] - P.limit_kd[i]) * at;
         s[Y.aact + ds] += at;
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         for (int k = 0; k < 3; ++k) {
             const float at = atau[ds + k];
             add6(aS + (ds + k) * 6, f * (-at));
@@ -1131,16 +1144,48 @@ DFX_HD void tau_project_adj(const Pack& P, const Layout& Y, SP s, SP atau, int i
             aqd[ds + k] += -P.target_kd[i] * at;
             aq[qs + k] += -P.target_ke[i] * at;
         }
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         for (int k = 0; k < 6; ++k) add6(aS + (ds + k) * 6, f * (-atau[ds + k]));
         af += SV{V3{-atau[ds], -atau[ds + 1], -atau[ds + 2]}, V3{-atau[ds + 3], -atau[ds + 4], -atau[ds + 5]}};
     }
     st6(s + Y.pX + i * 7, af);      // (direct part, in the idle pX slot: tau_adj sums it along the root paths into af)
 }
 
+// the direct part of a(f_tot[j]) alone: what tau_project_adj() stages in pX, recomputed by every link below j (kFusedPhases)
+DFX_HD SV tau_direct_af(const Pack& P, const Layout& Y, SP s, SP atau, int j) {
+    const int type = P.type[j], ds = P.qd_start[j];
+    const SP S = s + Y.S;
+    SV af = sv_zero();
+    if (is_joint(P, type, JOINT_PRISMATIC) || is_joint(P, type, JOINT_REVOLUTE)) {
+        af += ld6(S + ds * 6) * (-atau[ds]);
+    } else if (is_joint(P, type, JOINT_BALL)) {
+        for (int k = 0; k < 3; ++k) af += ld6(S + (ds + k) * 6) * (-atau[ds + k]);
+    } else if (is_joint(P, type, JOINT_FREE)) {
+        af += SV{V3{-atau[ds], -atau[ds + 1], -atau[ds + 2]}, V3{-atau[ds + 3], -atau[ds + 4], -atau[ds + 5]}};
+    }
+    return af;
+}
+
 template <class Grp>
 DFX_HD void tau_adj(const Pack& P, const Layout& Y, SP s, SP atau, const Grp& g) {
     const int atau_off = (int)(atau - s);   // (element offset inside the scratch)
+    if constexpr (Grp::kFusedPhases) {
+        // ONE pass: a link's own projection adjoint (aS, aq, aqd, aact) and af[i] = the direct cotangents summed along its root
+        // path, each ancestor's recomputed on the fly (one scaled load of S per dof) -- same values, same root-first order
+        g.cta_tasks(s, P.L, true, [&](SP se, int i) {
+            SV acc = sv_zero();
+            bool first = true;
+            for_path_root_first(P, i, false, [&](int j) {
+                const SV x = tau_direct_af(P, Y, se, se + atau_off, j);
+                acc = first ? x : acc + x;
+                first = false;
+            });
+            tau_project_adj(P, Y, se, se + atau_off, i);              // (leaves the link's own direct part in pX[i])
+            const SV own = ld6(se + Y.pX + i * 7);
+            st6(se + Y.af + i * 6, first ? own : acc + own);
+        });
+        return;
+    }
     g.cta_tasks(s, P.L, true, [&](SP se, int i) { tau_project_adj(P, Y, se, se + atau_off, i); });
     // T1': af[i] = af_direct[i] + af[parent], root -> leaves, as PATH SUMS: tau_project_adj left the direct cotangents in the
     // (idle) pX slot; every link adds them along its own root path in root-first order (the same association as the
@@ -1232,12 +1277,21 @@ DFX_HD void crba_fwd(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     g.sync();
 }
 
-// Cholesky  L L^T = H + diag(armature)  (column by column), then A <- (L L^T)^-1 column-wise.
+// Cholesky  L L^T = H + diag(armature), then A <- (L L^T)^-1 column-wise.
+// The factorisation runs TWO columns per barrier: every thread forms the 2 x 2 diagonal block (L[j][j], L[j+1][j], L[j+1][j+1])
+// itself -- three short dot products, independent of each other -- and its rows' entries of both columns from ONE pass over the
+// row (the column-(j+1) entry needs the thread's own column-j entry, still in a register).  Every entry is the same expression,
+// accumulated in the same order, as in the column-by-column form (kept below for the host-emulation A/B,
+// tests/test_emu_golden.py): bit-identical factors with half the barriers and two independent FMA chains per thread.
+#ifndef DFX_CHOL_UNBLOCKED
+#define DFX_CHOL_UNBLOCKED 0
+#endif
 template <class Grp>
 DFX_HD void chol_inverse(const Pack& P, const Layout& Y, SP s, const Grp& g) {
     const int D = P.D;
     const SP A = s + Y.A;
     const SP Lm = s + Y.Lm;
+#if DFX_CHOL_UNBLOCKED
     for (int j = 0; j < D; ++j) {
         float sj = A[j * D + j] + P.armature[j];
 #pragma unroll 4
@@ -1253,6 +1307,45 @@ DFX_HD void chol_inverse(const Pack& P, const Layout& Y, SP s, const Grp& g) {
         if (g.lane == j % Grp::G) Lm[j * D + j] = ljj;
         g.sync();
     }
+#else
+    for (int j = 0; j < D; j += 2) {
+        const bool two = j + 1 < D;
+        const int j1 = two ? j + 1 : j;          // (a lone last column reads its own row twice; the second set of results is dropped)
+        float s00 = A[j * D + j] + P.armature[j];
+        float s10 = A[j1 * D + j];
+        float s11 = A[j1 * D + j1] + P.armature[j1];
+#pragma unroll 4
+        for (int k = 0; k < j; ++k) {
+            const float r0 = Lm[j * D + k], r1 = Lm[j1 * D + k];
+            s00 -= r0 * r0;
+            s10 -= r1 * r0;
+            s11 -= r1 * r1;
+        }
+        const float l00 = sqrtf(s00);
+        const float inv0 = 1.0f / l00;
+        const float l10 = s10 * inv0;
+        s11 -= l10 * l10;
+        const float l11 = sqrtf(s11);
+        const float inv1 = 1.0f / l11;
+        for (int i = j + 2 + g.lane; i < D; i += Grp::G) {
+            float si0 = A[i * D + j], si1 = A[i * D + j1];
+#pragma unroll 4
+            for (int k = 0; k < j; ++k) {
+                const float lik = Lm[i * D + k];
+                si0 -= lik * Lm[j * D + k];
+                si1 -= lik * Lm[j1 * D + k];
+            }
+            const float li0 = si0 * inv0;
+            Lm[i * D + j] = li0;
+            if (two) { si1 -= li0 * l10; Lm[i * D + j1] = si1 * inv1; }
+        }
+        if (g.lane == j % Grp::G) {
+            Lm[j * D + j] = l00;
+            if (two) { Lm[j1 * D + j] = l10; Lm[j1 * D + j1] = l11; }
+        }
+        g.sync();
+    }
+#endif
     DFX_FOR(c, D) {
         // L y = e_c  (y_i = 0 for i < c)
         for (int i = 0; i < D; ++i) {
@@ -1498,17 +1591,17 @@ DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, SP s, float dt, i
     const SP q = s + Y.q;
     const SP qd = s + Y.qd;
     const SP qdd = s + Y.qdd;
-    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+    if (is_joint(P, type, JOINT_PRISMATIC) || is_joint(P, type, JOINT_REVOLUTE)) {
         const float qd_new = qd[ds] + qdd[ds] * dt;
         q[qs] = q[qs] + qd_new * dt;
         qd[ds] = qd_new;
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
         const Q4 r = ld4(q + qs);
         const Q4 drdt = qmul(Q4{w.x, w.y, w.z, 0.0f}, r) * 0.5f;
         st4(q + qs, qnormalize(r + drdt * dt));
         st3(qd + ds, w);
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
         const V3 v = ld3(qd + ds + 3) + ld3(qdd + ds + 3) * dt;
         const V3 p = ld3(q + qs);
@@ -1524,8 +1617,15 @@ DFX_HD void integrate_link_fwd(const Pack& P, const Layout& Y, SP s, float dt, i
 
 template <class Grp>
 DFX_HD void integrate_fwd(const Pack& P, const Layout& Y, SP s, float dt, const Grp& g) {
-    DFX_FOR(i, P.L) integrate_link_fwd(P, Y, s, dt, i);
+    DFX_FOR(i, P.L) {
+        integrate_link_fwd(P, Y, s, dt, i);
+        // K1 of the next substep: the joint-local transform depends on the link's own coordinates only, which this thread just
+        // wrote -- no phase and no barrier of its own
+        if constexpr (Grp::kFusedPhases) kin_local_fwd(P, Y, s, i);
+    }
     g.pre_store();         // (q, qd) of the next substep leave for the tape right after this barrier
+    // the next phase (K2 / K3 of the next substep) overwrites the row fields this substep's tape store may still be reading
+    if constexpr (Grp::kFusedPhases) g.row_reusable();
     g.sync();
 }
 
@@ -1539,11 +1639,11 @@ DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, SP s, float dt, i
     const SP aq = s + Y.aq;
     const SP aqd = s + Y.aqd;
     const SP aqdd = s + Y.aqdd;
-    if (type == JOINT_PRISMATIC || type == JOINT_REVOLUTE) {
+    if (is_joint(P, type, JOINT_PRISMATIC) || is_joint(P, type, JOINT_REVOLUTE)) {
         const float aqdn = aqd[ds] + aq[qs] * dt;
         aqd[ds] = aqdn;
         aqdd[ds] = aqdn * dt;
-    } else if (type == JOINT_BALL) {
+    } else if (is_joint(P, type, JOINT_BALL)) {
         const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
         const Q4 r = ld4(q + qs);
         const Q4 W = Q4{w.x, w.y, w.z, 0.0f};
@@ -1555,7 +1655,7 @@ DFX_HD void integrate_link_adj(const Pack& P, const Layout& Y, SP s, float dt, i
         st4(aq + qs, ar);
         st3(aqd + ds, aw);
         st3(aqdd + ds, aw * dt);
-    } else if (type == JOINT_FREE) {
+    } else if (is_joint(P, type, JOINT_FREE)) {
         const V3 w = ld3(qd + ds) + ld3(qdd + ds) * dt;
         const V3 p = ld3(q + qs);
         const Q4 r = ld4(q + qs + 3);

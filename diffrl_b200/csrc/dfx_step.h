@@ -37,6 +37,11 @@ struct StepArgs {
     const float* raw; const float* strength; float* used; const float* g_used; float* g_raw;
     int map_num_act, map_offset, map_muscle;
     float map_pre_scale, map_pre_bias, map_drive_scale;
+    // env transition folded into the step launch (include/dfx.h dfx_env_step_*; tile kernels only): env_kind != 0.  Forward:
+    // `env` is read after the step (epilogue); backward: `env_adj` before it (prologue), writing gq_out / gqd_out / g_used.
+    int env_kind;
+    DfxEnvTransition env;
+    DfxEnvTransitionAdj env_adj;
 };
 
 // derived State fields of the last substep (reference model.py:375-388); `late` = the ones that exist only after the solve
@@ -97,6 +102,10 @@ DFX_HD void env_step_forward(const Pack& P, const Layout& Y, SP s, const Grp& g,
     DFX_FOR(i, P.L * 12) s[Y.fx + i] = 0.0f;   // fixed-point wrench accumulators (L x 6 low + high words)
     g.pre_store();
     g.sync();
+    if constexpr (Grp::kFusedPhases) {      // K1 of the first substep (later ones: inside integrate_fwd)
+        DFX_FOR(i, P.L) kin_local_fwd(P, Y, s, i);
+        g.sync();
+    }
     for (int sub = 0; sub < a.substeps; ++sub) {
         const bool upd = (sub % a.mm_freq) == 0;
         // (q, qd) ENTERING this substep: every thread fenced its writes before the barrier that closed the previous

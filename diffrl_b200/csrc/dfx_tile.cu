@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 
 #include "dfx_launch.h"
+#include "dfx_env_dev.h"
 
 namespace dfx {
 
@@ -66,6 +67,10 @@ struct GroupTile {
     static constexpr int SUB = 32 / E;
     static constexpr int G = NW * SUB;           // item slots of the CTA
     static constexpr bool kPathPasses = PATH;    // path / subtree passes instead of per-level tree recursions
+#ifndef DFX_TILE_FUSED_PHASES
+#define DFX_TILE_FUSED_PHASES 1                  // (0: A/B builds)
+#endif
+    static constexpr bool kFusedPhases = DFX_TILE_FUSED_PHASES != 0;   // K1 inside integrate_fwd, single-pass tau_adj (dfx_phases.h)
     int lane;            // item slot of DFX_FOR
     int e;               // environment inside the tile
     int tile, ntiles;
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) dfx_tile_kernel(const __grid_co
     __syncthreads();
     Pack P = bind_pack(ka.header, ka.blob, ipack, fpack);
     P.L = SL; P.D = SD; P.Q = SQ; P.C = SC; P.M = SM;
+    P.jmask = tile_joint_mask(SL, SD, SQ, SC, SM);      // (dfx_pack_create checked that the links have no other joint type)
     constexpr Layout Y = make_layout(SL, SD, SQ, SC, SM, MODE, BACKWARD);
 
     GroupTile<NW, E, PATH> g;
@@ -289,8 +295,41 @@ __global__ void __launch_bounds__(NW * 32, MINB) dfx_tile_kernel(const __grid_co
     int env = blockIdx.x * E + g.e;
     if (env >= ka.step.N) env = ka.step.N - 1;
     const SP s{g.tile_base + g.e};
-    if (BACKWARD) env_step_backward(P, Y, s, g, env, ka.step);
-    else env_step_forward(P, Y, s, g, env, ka.step);
+    // env.step() as one launch (dfx_env_step_forward / _backward): the transition of this tile's environments -- observation,
+    // reward, termination, masked re-initialisation, next observation -- runs on the first E threads of the CTA, one
+    // environment each, as the epilogue of the simulation step; its adjoint as the prologue of the step adjoint.  The rows
+    // cross in global memory (written and read by this CTA only, on either side of a CTA barrier).
+    const int tenv = blockIdx.x * E + (int)threadIdx.x;
+    const bool tlane = ka.step.env_kind != 0 && threadIdx.x < E && tenv < ka.step.N;
+    if (BACKWARD) {
+        if (ka.step.env_kind) {
+            const DfxEnvTransitionAdj& t = ka.step.env_adj;
+            if (tlane) {
+                if (ka.step.env_kind == 1)
+                    walker_transition_backward_env(t.walker, tenv, t.q_sim, t.qd_sim, t.used, t.reset, t.g_obs_before, t.g_rew, t.g_q_next,
+                                                   t.g_qd_next, t.g_actions_next, t.g_obs_next, t.gq_sim, t.gqd_sim, t.g_used);
+                else
+                    planar_transition_backward_env(t.planar, tenv, t.q_sim, t.qd_sim, t.used, t.reset, t.g_obs_before, t.g_rew, t.g_q_next,
+                                                   t.g_qd_next, t.g_actions_next, t.g_obs_next, t.gq_sim, t.gqd_sim, t.g_used);
+            }
+            __syncthreads();
+        }
+        env_step_backward(P, Y, s, g, env, ka.step);
+    } else {
+        env_step_forward(P, Y, s, g, env, ka.step);
+        if (ka.step.env_kind) {
+            const DfxEnvTransition& t = ka.step.env;
+            __syncthreads();            // `used` of the tile is written (global); the stepped state is still in the scratch tile
+            if (tlane) {                // (threadIdx.x < E: this thread's `s` is the scratch of environment tenv; it reads the state from there)
+                if (ka.step.env_kind == 1)
+                    walker_transition_forward_env(t.walker, tenv, s + Y.q, s + Y.qd, ka.step.used, t.progress, t.start_q, t.start_qd,
+                                                  t.obs_before, t.rew, t.reset, t.q_next, t.qd_next, t.actions_next, t.progress_next, t.obs_next);
+                else
+                    planar_transition_forward_env(t.planar, tenv, s + Y.q, s + Y.qd, ka.step.used, t.progress, t.start_q, t.start_qd,
+                                                  t.obs_before, t.rew, t.reset, t.q_next, t.qd_next, t.actions_next, t.progress_next, t.obs_next);
+            }
+        }
+    }
     g.finish();
 }
 

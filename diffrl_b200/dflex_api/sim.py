@@ -88,6 +88,25 @@ def fused_mapped_forward(model, state_in, dt, substeps, mass_matrix_freq, raw_ac
     return out, used
 
 
+def fused_env_step(model, state_in, dt, substeps, mass_matrix_freq, raw_actions, amap, tparams, progress, start_q, start_qd, nan_guard=False):
+    """env.step() as one launch (``env_ops.EnvStepFunction`` over ``dfx_env_step_forward / _backward``): the simulation step with
+    the action map folded in and the env transition as its epilogue.  Returns (State of the NEXT step's start, (obs_before_reset,
+    rew, reset, actions_next, progress_next, obs_next)).  ``nan_guard``: non-finite cotangents of (q, qd, actions) become 0
+    (the reference's humanoid.py:196-206 hooks)."""
+    from ..env_ops import EnvStepFunction
+    engine = _engine_for(model)
+    (obs_before, rew, reset, q_next, qd_next, actions_next, progress_next, obs_next) = EnvStepFunction.apply(
+        engine, int(substeps), int(mass_matrix_freq), float(dt), amap, tparams, bool(nan_guard), progress, start_q, start_qd,
+        state_in.joint_q, state_in.joint_qd, raw_actions)
+    out = State()
+    out.particle_count, out.link_count = model.particle_count, model.link_count
+    out.joint_q, out.joint_qd = q_next.view(-1), qd_next.view(-1)
+    out.__dict__["_act_proto"] = model.joint_qd
+    out.__dict__["_derive_ctx_mapped"] = (engine, state_in.joint_q.detach(), state_in.joint_qd.detach(), raw_actions.detach(), amap,
+                                          int(substeps), int(mass_matrix_freq), float(dt))
+    return out, (obs_before, rew, reset, actions_next, progress_next, obs_next)
+
+
 class SemiImplicitIntegrator:
     """Semi-implicit (symplectic) Euler integrator for articulated rigid bodies."""
 

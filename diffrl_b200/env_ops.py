@@ -36,6 +36,22 @@ class DfxPlanarParams(ctypes.Structure):
     ]
 
 
+class DfxEnvTransition(ctypes.Structure):
+    """ctypes mirror of ``DfxEnvTransition`` in include/dfx.h (keep field order in sync)."""
+
+    _fields_ = [("kind", ctypes.c_int), ("walker", DfxWalkerParams), ("planar", DfxPlanarParams)] + [
+        (n, ctypes.c_void_p) for n in ("progress", "start_q", "start_qd", "obs_before", "rew", "reset", "q_next", "qd_next",
+                                       "actions_next", "progress_next", "obs_next")]
+
+
+class DfxEnvTransitionAdj(ctypes.Structure):
+    """ctypes mirror of ``DfxEnvTransitionAdj`` in include/dfx.h (keep field order in sync)."""
+
+    _fields_ = [("kind", ctypes.c_int), ("walker", DfxWalkerParams), ("planar", DfxPlanarParams)] + [
+        (n, ctypes.c_void_p) for n in ("q_sim", "qd_sim", "used", "reset", "g_obs_before", "g_rew", "g_q_next", "g_qd_next",
+                                       "g_actions_next", "g_obs_next", "gq_sim", "gqd_sim", "g_used")]
+
+
 def _bind(lib):
     if getattr(lib, "_walker_bound", False):
         return
@@ -51,6 +67,9 @@ def _bind(lib):
     I, F = ctypes.c_int, ctypes.c_float
     lib.dfx_action_map_forward.argtypes = [I, I, I, I, F, F, F, V, V, V, V, V]
     lib.dfx_action_map_backward.argtypes = [I, I, I, I, F, F, V, V, V, V, V, V]
+    Dbl = ctypes.c_double
+    lib.dfx_env_step_forward.argtypes = [V, I, I, I, Dbl, V, V, V, V, V, V, V, V, V, ctypes.POINTER(DfxEnvTransition), V]
+    lib.dfx_env_step_backward.argtypes = [V, I, I, I, Dbl, V, V, V, V, ctypes.POINTER(DfxEnvTransitionAdj), V, V, V, V]
     lib._walker_bound = True
 
 
@@ -196,3 +215,91 @@ class ActionMapFunction(torch.autograd.Function):
                                                _ptr(g_used), _ptr(g_drive), _ptr(g_raw), _stream(raw.device))
         _capi.check(code, "dfx_action_map_backward")
         return None, None, None, None, None, None, None, g_raw
+
+
+def _addr(t):
+    return None if t is None else t.data_ptr()
+
+
+class EnvStepFunction(torch.autograd.Function):
+    """env.step() as ONE launch forward and ONE backward (``dfx_env_step_forward / _backward``): the simulation step with the
+    action map folded in (``MappedSimStepFunction``) and the transition (``WalkerTransitionFunction``) as its epilogue --
+    (q, qd, raw policy output) -> (obs_before_reset, rew, reset, q_next, qd_next, actions_next, progress_next, obs_next), the same
+    values bit for bit.  ``amap`` = (offset, pre_scale, pre_bias, drive_scale, strength, is_muscle); ``params`` a
+    ``DfxWalkerParams`` or ``DfxPlanarParams``; ``progress`` the counter before the step; ``start_q`` / ``start_qd`` the state a
+    terminated environment restarts from (constants for autograd); ``nan_guard``: non-finite input cotangents become 0 (the
+    reference's gradient hooks on the state and the clipped actions, envs/humanoid.py:196-206)."""
+
+    @staticmethod
+    def forward(ctx, engine, substeps, mm_freq, dt, amap, params, nan_guard, progress, start_q, start_qd, q, qd, raw):
+        from .modelpack import DfxActionMap
+        lib = engine.lib
+        _bind(lib)
+        offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = amap
+        dev = engine.device
+        q, qd, raw = _c(q.detach()), _c(qd.detach()), _c(raw.detach())
+        start_q, start_qd = _c(start_q), _c(start_qd)
+        n, A = engine.N, raw.shape[-1]
+        m = DfxActionMap(int(A), int(offset), int(bool(is_muscle)), float(pre_scale), float(pre_bias), float(drive_scale), strength.data_ptr())
+        f32 = dict(dtype=torch.float32, device=dev)
+        q_sim, qd_sim, used = torch.empty_like(q), torch.empty_like(qd), torch.empty_like(raw)
+        need = any(ctx.needs_input_grad[10:13])
+        ctx.nan_guard = nan_guard
+        tape = torch.empty(engine.tape_floats(substeps, mm_freq), **f32) if need else None
+        obs_before = torch.empty((n, params.num_obs), **f32)
+        obs_next = torch.empty((n, params.num_obs), **f32)
+        rew = torch.empty(n, **f32)
+        reset = torch.empty(n, dtype=torch.long, device=dev)
+        progress_next = torch.empty(n, dtype=torch.long, device=dev)
+        q_next, qd_next, actions_next = torch.empty_like(q), torch.empty_like(qd), torch.empty_like(raw)
+        planar = isinstance(params, DfxPlanarParams)
+        tr = DfxEnvTransition(kind=2 if planar else 1)
+        if planar:
+            tr.planar = params
+        else:
+            tr.walker = params
+        for name, t in (("progress", progress), ("start_q", start_q), ("start_qd", start_qd), ("obs_before", obs_before), ("rew", rew),
+                        ("reset", reset), ("q_next", q_next), ("qd_next", qd_next), ("actions_next", actions_next),
+                        ("progress_next", progress_next), ("obs_next", obs_next)):
+            setattr(tr, name, t.data_ptr())
+        with torch.cuda.device(dev):
+            code = lib.dfx_env_step_forward(engine.pack, n, int(substeps), int(mm_freq), float(dt), _ptr(q), _ptr(qd), ctypes.byref(m),
+                                            _ptr(raw), None, _ptr(used), _ptr(q_sim), _ptr(qd_sim), _ptr(tape), ctypes.byref(tr), _stream(dev))
+        _capi.check(code, "dfx_env_step_forward")
+        ctx.engine, ctx.cfg, ctx.amap, ctx.params = engine, (substeps, mm_freq, dt), m, params
+        ctx.strength = strength                      # keeps the device array the struct points at alive
+        ctx.set_materialize_grads(False)             # absent cotangents arrive as None (NULL in the C ABI), not as zero fills
+        ctx.shapes = (q.shape, qd.shape)
+        ctx.save_for_backward(raw, tape, q_sim, qd_sim, used, reset)
+        ctx.mark_non_differentiable(reset, progress_next)
+        return obs_before, rew, reset, q_next, qd_next, actions_next, progress_next, obs_next
+
+    @staticmethod
+    def backward(ctx, g_obs_before, g_rew, g_reset, g_q_next, g_qd_next, g_actions_next, g_progress, g_obs_next):
+        raw, tape, q_sim, qd_sim, used, reset = ctx.saved_tensors
+        engine, (substeps, mm_freq, dt), params = ctx.engine, ctx.cfg, ctx.params
+        lib, dev = engine.lib, engine.device
+        cot = [None if g is None else _c(g) for g in (g_obs_before, g_rew, g_q_next, g_qd_next, g_actions_next, g_obs_next)]
+        planar = isinstance(params, DfxPlanarParams)
+        tr = DfxEnvTransitionAdj(kind=2 if planar else 1)
+        if planar:
+            tr.planar = params
+        else:
+            tr.walker = params
+        # workspace: the cotangents of (q_sim, qd_sim, used) between the transition adjoint and the step adjoint
+        gq_sim, gqd_sim, g_used = torch.empty_like(q_sim), torch.empty_like(qd_sim), torch.empty_like(used)
+        for name, t in (("q_sim", q_sim), ("qd_sim", qd_sim), ("used", used), ("reset", reset), ("g_obs_before", cot[0]), ("g_rew", cot[1]),
+                        ("g_q_next", cot[2]), ("g_qd_next", cot[3]), ("g_actions_next", cot[4]), ("g_obs_next", cot[5]),
+                        ("gq_sim", gq_sim), ("gqd_sim", gqd_sim), ("g_used", g_used)):
+            setattr(tr, name, _addr(t))
+        gq = torch.empty(engine.N * engine.Q, dtype=torch.float32, device=dev)
+        gqd = torch.empty(engine.N * engine.D, dtype=torch.float32, device=dev)
+        g_raw = torch.empty_like(raw)
+        with torch.cuda.device(dev):
+            code = lib.dfx_env_step_backward(engine.pack, engine.N, int(substeps), int(mm_freq), float(dt), ctypes.byref(ctx.amap), _ptr(raw),
+                                             None, _ptr(tape), ctypes.byref(tr), _ptr(gq), _ptr(gqd), _ptr(g_raw), _stream(dev))
+        _capi.check(code, "dfx_env_step_backward")
+        if ctx.nan_guard:
+            for g in (gq, gqd, g_raw):
+                torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0, out=g)
+        return None, None, None, None, None, None, None, None, None, None, gq.view(ctx.shapes[0]), gqd.view(ctx.shapes[1]), g_raw

@@ -124,6 +124,10 @@ class DFlexEnv:
     sync_free_reset = True
     # True: the policy-output -> actuation map is folded into the simulation launch (dfx_step_forward_mapped)
     fused_action_map = True
+    # True: the transition (progress counter, observation, reward, termination, masked re-initialisation, next observation) rides
+    # inside the simulation launch as its epilogue, and its adjoint as the prologue of the adjoint launch (dfx_env_step_forward /
+    # _backward): env.step() is ONE launch forward and ONE backward
+    single_launch_step = True
 
     def step(self, actions):
         actions = actions.view((self.num_envs, self.num_actions))
@@ -160,6 +164,20 @@ class DFlexEnv:
             self._amap = self._action_map()
             self._tparams = self._transition_params()
         width, offset, pre_scale, pre_bias, drive_scale, strength, is_muscle = self._amap
+        if self.single_launch_step and self.fused_action_map and not self.no_grad:
+            from ..dflex_api.sim import fused_env_step
+            start_q, start_qd = self._start_state()
+            # nan_guard (the reference's "ugly fix", humanoid.py:196-206: NaN / Inf gradients flowing into the state and the
+            # clipped actions become 0) is applied to the op's input cotangents inside its backward
+            self.state, (obs_before, self.rew_buf, self.reset_buf, self.actions, self.progress_buf, self.obs_buf) = fused_env_step(
+                self.model, self.state, self.sim_dt, self.sim_substeps, self.MM_caching_frequency, actions.view((n, self.num_actions)),
+                (offset, pre_scale, pre_bias, drive_scale, strength, is_muscle), self._tparams, self.progress_buf, start_q, start_qd,
+                nan_guard=self.nan_guard)
+            self.sim_time += self.sim_dt
+            self.num_frames += 1
+            self.obs_buf_before_reset = obs_before
+            self.extras = {"obs_before_reset": obs_before, "episode_end": self.termination_buf}
+            return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
         if self.fused_action_map and not self.no_grad:
             # the action map rides inside the simulation launch (dfx_step_forward_mapped): 2 launches per step instead of 3
             from ..dflex_api.sim import fused_mapped_forward

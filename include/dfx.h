@@ -236,6 +236,58 @@ int dfx_step_backward_mapped(const dfx_pack_t* pack, int n, int substeps, int mm
                              const float* gq_out, const float* gqd_out, const float* g_used,
                              float* gq, float* gqd, float* g_raw, void* stream);
 
+/* ---- env.step() as ONE launch ("fuse into the step epilogue (and its adjoint)"; reference
+ * envs/ant.py:156-190 = the action map, SemiImplicitIntegrator.forward and the transition, ~40 PyTorch kernels + one per
+ * generated dflex kernel).  Exactly dfx_step_forward_mapped followed by dfx_walker_transition_forward /
+ * dfx_planar_transition_forward on its outputs (q_sim, qd_sim, used) -- the same per-environment code, states / flags / counters
+ * identical, observations and rewards to a few ulp (the two compilations may contract a*b - c*d differently) -- but the
+ * tile kernels run the transition of a tile's environments as the EPILOGUE of the simulation launch (the first E threads of
+ * the CTA, one environment each), and its adjoint as the PROLOGUE of the adjoint launch: one launch per env.step() forward, one
+ * backward.  Articulations without a tile kernel run the two launches back to back inside the call. */
+typedef struct DfxEnvTransition {
+    int kind;                           /* 1: walker (`walker` is read), 2: planar (`planar` is read) */
+    DfxWalkerParams walker;
+    DfxPlanarParams planar;
+    const long long* progress;          /* [n] step counter BEFORE this step */
+    const float* start_q;               /* [n*Q], [n*D]: the state a terminated environment restarts from */
+    const float* start_qd;
+    float* obs_before;                  /* outputs, as in dfx_walker_transition_forward */
+    float* rew;
+    long long* reset;
+    float* q_next;
+    float* qd_next;
+    float* actions_next;
+    long long* progress_next;
+    float* obs_next;
+} DfxEnvTransition;
+/* q_sim [n*Q], qd_sim [n*D]: the state right after the simulation step (before the masked re-initialisation; the adjoint
+ * reads it back); used [n*num_act]: the env's `actions` (required). */
+int dfx_env_step_forward(const dfx_pack_t* pack, int n, int substeps, int mm_freq, double dt,
+                         const float* q, const float* qd, const DfxActionMap* map, const float* raw, const float* act_other,
+                         float* used, float* q_sim, float* qd_sim, float* tape, const DfxEnvTransition* tr, void* stream);
+typedef struct DfxEnvTransitionAdj {
+    int kind;
+    DfxWalkerParams walker;
+    DfxPlanarParams planar;
+    const float* q_sim;                 /* saved by the forward call */
+    const float* qd_sim;
+    const float* used;
+    const long long* reset;
+    const float* g_obs_before;          /* cotangents of the six differentiable transition outputs (NULL == 0) */
+    const float* g_rew;
+    const float* g_q_next;
+    const float* g_qd_next;
+    const float* g_actions_next;
+    const float* g_obs_next;
+    float* gq_sim;                      /* workspace [n*Q], [n*D], [n*num_act]: the cotangents of (q_sim, qd_sim, used) on their */
+    float* gqd_sim;                     /* way from the transition adjoint into the step adjoint (overwritten)                   */
+    float* g_used;
+} DfxEnvTransitionAdj;
+/* -> gq, gqd, g_raw (overwritten), as dfx_step_backward_mapped */
+int dfx_env_step_backward(const dfx_pack_t* pack, int n, int substeps, int mm_freq, double dt,
+                          const DfxActionMap* map, const float* raw, const float* act_other, const float* tape,
+                          const DfxEnvTransitionAdj* tr, float* gq, float* gqd, float* g_raw, void* stream);
+
 /* Launch configuration knob: lanes cooperating on one environment (8, 16 or 32; 0 = auto). */
 int dfx_set_group_size(int lanes);
 /* Tuning flags (default 9; for A/B timing and tests).  Lane-group kernels: bit 1 (2) = extra CTA-wide barriers between

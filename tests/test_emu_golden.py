@@ -168,3 +168,49 @@ def test_restructured_adjoints_match_the_direct_formulations(name, flag):
                 assert rel(a, b) < 6e-5, (name, k, scale, key, rel(a, b))     # (each is within GRAD_RTOL = 5e-5 of the reference)
                 if scale is None:
                     assert rel(a, d[p + key]) < GRAD_RTOL and rel(b, d[p + key]) < GRAD_RTOL, (name, k, key)
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "CartPoleSwingUpEnv", "HopperEnv"])
+def test_two_column_cholesky_is_bit_identical_to_column_by_column(name):
+    """chol_inverse factorises two columns per barrier (csrc/dfx_phases.h): every entry of L is the same expression accumulated
+    in the same order as column by column [A/B: -DDFX_CHOL_UNBLOCKED=1], so the final state, the whole tape (rows and the
+    H^-1 blocks) and the dumped factor agree bit for bit -- odd and even numbers of dofs (14, 27, 24, 2, 6).  With FMA contraction
+    left to the host compiler the two code shapes may be contracted differently (g++ vectorises the three diagonal-block chains):
+    there the results agree to rounding only."""
+    d, model = load_golden(name)
+    N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    for fma in ((), ("-ffp-contract=fast", "-mfma")):
+        blocked, plain = EmuSim(model, N, extra=fma), EmuSim(model, N, extra=("-DDFX_CHOL_UNBLOCKED=1",) + fma)
+        p = "case0/"
+        musc = d[p + "musc"] if (p + "musc") in d.files else None
+        out = []
+        for sim in (blocked, plain):
+            q, qd, tape, dumps = sim.forward(d[p + "q0"], d[p + "qd0"], d[p + "act"], musc, S, mm, dt, derived=True)
+            out.append((q, qd, dumps["L"], dumps["H"], tape))
+        for a, b in zip(*out):
+            if not fma:
+                assert np.array_equal(a, b)
+        for a, b in zip(out[0][:3], out[1][:3]):
+            assert rel(a, b) < 2e-6, rel(a, b)
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "CartPoleSwingUpEnv", "CheetahEnv"])
+def test_merged_phases_are_bit_identical(name):
+    """The tile kernels merge two pairs of phases to save CTA-wide barriers (Grp::kFusedPhases, csrc/dfx_phases.h): the
+    joint-local transforms of the next substep are formed by the thread that integrates the link, and the torque adjoint
+    recomputes the ancestors' direct wrench cotangents along each link's root path instead of staging them and summing in a
+    second pass.  The same operations in the same order [A/B: -DDFX_EMU_FUSED_PHASES=1, path-pass build]: final state, tape and
+    all gradients agree bit for bit."""
+    d, model = load_golden(name)
+    N, S, mm, dt = int(d["meta/num_envs"]), int(d["meta/substeps"]), int(d["meta/mass_matrix_freq"]), float(d["meta/dt"])
+    plain, merged = EmuSim(model, N, es=3, path_passes=True), EmuSim(model, N, es=3, path_passes=True, extra=("-DDFX_EMU_FUSED_PHASES=1",))
+    for k in range(int(d["meta/num_cases"])):
+        p = "case%d/" % k
+        musc = d[p + "musc"] if (p + "musc") in d.files else None
+        out = []
+        for sim in (plain, merged):
+            q, qd, tape, _ = sim.forward(d[p + "q0"], d[p + "qd0"], d[p + "act"], musc, S, mm, dt)
+            g = sim.backward(d[p + "act"], musc, tape, d[p + "gq_out"], d[p + "gqd_out"], S, mm, dt)
+            out.append([q, qd, tape] + [x for x in g if x is not None])
+        for a, b in zip(*out):
+            assert np.array_equal(a, b)

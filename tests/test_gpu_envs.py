@@ -115,10 +115,11 @@ def test_fused_transition_equals_unfused_step(name):
     import diffrl_b200.envs as envs
     n, T = 48, 7
     outs = []
-    for mode in ("fused", "epilogue", "torch"):
+    for mode in ("single", "fused", "epilogue", "torch"):
         torch.manual_seed(0)
         env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=3)
-        env.fused_transition = mode == "fused"
+        env.single_launch_step = mode == "single"       # the transition as the epilogue of the simulation launch (dfx_env_step_*)
+        env.fused_transition = mode in ("single", "fused")
         env.fused_epilogue = mode != "torch"
         env.clear_grad(); env.reset(); env.initialize_trajectory()
         g = torch.Generator(device="cuda:0").manual_seed(11)
@@ -133,9 +134,9 @@ def test_fused_transition_equals_unfused_step(name):
                         extras["obs_before_reset"].detach().clone()))
         loss.backward()
         outs.append((rec, torch.stack([a.grad for a in acts]), float(loss.detach())))
-    ref_rec, ref_grad, ref_loss = outs[2]
+    ref_rec, ref_grad, ref_loss = outs[3]
     assert any(bool(r[2].any()) for r in ref_rec), "the window must contain terminations"
-    for rec, grad, loss in outs[:2]:
+    for rec, grad, loss in outs[:3]:
         for a, b in zip(rec, ref_rec):
             assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
             for x, y in zip(a[:2] + a[4:], b[:2] + b[4:]):
@@ -243,6 +244,7 @@ def test_action_map_folded_into_the_step_equals_separate_launch(name):
         torch.manual_seed(0)
         env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=4)
         env.fused_action_map = folded
+        env.single_launch_step = False
         env.clear_grad(); env.reset(); env.initialize_trajectory()
         g = torch.Generator(device="cuda:0").manual_seed(13)
         acts = [((torch.rand((n, env.num_actions), generator=g, device="cuda:0") * 2 - 1) * 1.5).requires_grad_() for _ in range(T)]
@@ -262,3 +264,53 @@ def test_action_map_folded_into_the_step_equals_separate_launch(name):
             assert torch.equal(x, y)
     assert (g1 - g2).abs().max() <= 1e-6 * g2.abs().max() + 1e-9
     assert bool((g1[(torch.stack([a.detach() for a in acts]).abs() > 1.0)] == 0).all())
+
+
+@pytest.mark.parametrize("name", ENVS)
+@pytest.mark.parametrize("n", [40, 67])
+def test_single_launch_step_equals_the_two_launch_step(name, n):
+    """env.step() as ONE launch forward and ONE backward (dfx_env_step_forward / _backward: the transition as the epilogue of
+    the simulation launch, its adjoint as the prologue of the adjoint launch) against the two-launch path (dfx_step_*_mapped +
+    dfx_*_transition_*): the same per-environment code on the same values -- flags, counters and states exactly equal,
+    observations / rewards / action gradients to a few ulp -- with terminations inside the window, actions beyond the clip range,
+    batch sizes that are not a multiple of the tile width, the humanoids' gradient guard, and the launch count checked through
+    dfx_launch_count()."""
+    import torch
+    import diffrl_b200.envs as envs
+    from diffrl_b200 import _capi
+    T = 6
+    outs = []
+    for single in (True, False):
+        torch.manual_seed(0)
+        env = getattr(envs, name)(num_envs=n, device="cuda:0", no_grad=False, MM_caching_frequency=MM[name], episode_length=3)
+        env.single_launch_step = single
+        env.clear_grad(); env.reset(); env.initialize_trajectory()
+        g = torch.Generator(device="cuda:0").manual_seed(17)
+        acts = [((torch.rand((n, env.num_actions), generator=g, device="cuda:0") * 2 - 1) * 1.5).requires_grad_() for _ in range(T)]
+        w = torch.linspace(0.5, 1.5, env.num_obs, device="cuda:0")
+        l0 = _capi.lib().dfx_launch_count()
+        loss, rec = 0.0, []
+        for a in acts:
+            obs, rew, done, extras = env.step(a)
+            loss = loss + rew.sum() + (obs * w).sum() * 1e-2 + (extras["obs_before_reset"] * w).sum() * 3e-3
+            rec.append((obs.detach().clone(), rew.detach().clone(), done.clone(), env.progress_buf.clone(), env.state.joint_q.detach().clone(),
+                        env.state.joint_qd.detach().clone(), env.actions.detach().clone(), extras["obs_before_reset"].detach().clone()))
+        l1 = _capi.lib().dfx_launch_count()
+        loss.backward()
+        l2 = _capi.lib().dfx_launch_count()
+        outs.append((rec, torch.stack([a.grad for a in acts]), l1 - l0, l2 - l1))
+    (r1, g1, f1, b1), (r2, g2, f2, b2) = outs
+    assert (f1, b1) == (T, T) and (f2, b2) == (2 * T, 2 * T), (f1, b1, f2, b2)
+    assert any(bool(r[2].any()) for r in r2), "the window must contain terminations"
+    names = ("obs", "rew", "done", "progress", "joint_q", "joint_qd", "actions", "obs_before_reset")
+    for t, (a, b) in enumerate(zip(r1, r2)):
+        for key, x, y in zip(names, a, b):
+            if key in ("done", "progress", "joint_q", "joint_qd", "actions"):
+                # the simulation step is the same kernel code on the same inputs; flags, counters and the (copied or re-initialised) next state are exact
+                assert torch.equal(x, y), (t, key, float((x.float() - y.float()).abs().max()))
+            else:
+                # the transition arithmetic is the same source compiled into two kernels: FMA contraction of a*b - c*d may differ -> a few ulp
+                assert torch.allclose(x, y, rtol=2e-6, atol=2e-6), (t, key, float((x - y).abs().max()))
+    # (gradients: the contact adjoint's float atomics are not order-deterministic from run to run, and ulp differences of the
+    #  transition cotangents pass through the ill-conditioned humanoid steps)
+    assert (g1 - g2).abs().max() <= 1e-4 * g2.abs().max() + 1e-6, float((g1 - g2).abs().max() / g2.abs().max())
