@@ -33,8 +33,8 @@ __global__ void walker_backward_kernel(DfxWalkerParams p, int n, const float* __
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     walker_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
-                    g_obs ? g_obs + (size_t)e * p.num_obs : nullptr, nullptr, g_rew ? g_rew[e] : 0.0f, g_rew != nullptr,
-                    gq + (size_t)e * p.num_q, gqd + (size_t)e * p.num_qd, gact ? gact + (size_t)e * p.num_act : nullptr);
+                    g_obs + (size_t)e * p.num_obs, g_obs != nullptr, g_obs, false, g_rew ? g_rew[e] : 0.0f, g_rew != nullptr,
+                    gq + (size_t)e * p.num_q, gqd + (size_t)e * p.num_qd, gact + (size_t)e * p.num_act, gact != nullptr);
 }
 
 // ---- the whole env transition after the simulation step as its own launch, one thread per environment (the per-environment

@@ -47,10 +47,10 @@ __device__ __forceinline__ float height_reward(const DfxWalkerParams& p, float h
 
 // observation (always) and, when want_reward, reward + reset flag of ONE environment; `progress` is the step
 // counter AFTER this step.  `ae` == nullptr stands for all-zero actions (a freshly reset environment).
-template <class QP, class QDP>
+template <class QP, class QDP, class OP>
 __device__ __forceinline__ void walker_eval(const DfxWalkerParams& p, QP qe, QDP qde,
                                             const float* ae, long long progress, bool want_reward,
-                                            float* o, float* r_out, long long* rs_out) {
+                                            OP o, float* r_out, long long* rs_out) {
     V3 pos, ang, lin, tt, tdir, up, heading;
     Q4 rot, tq;
     float tn;
@@ -94,10 +94,12 @@ __device__ __forceinline__ void walker_eval(const DfxWalkerParams& p, QP qe, QDP
 
 // adjoint of walker_eval for ONE environment: cotangents go (obs, nullable), go2 (a second observation cotangent
 // that is added to the first, nullable), gr (reward) -> gqe, gqde (overwritten), gae (nullable)
-__device__ __forceinline__ void walker_eval_adj(const DfxWalkerParams& p, const float* qe, const float* qde,
-                                                const float* ae, const float* go,
-                                                const float* go2, float gr, bool has_rew,
-                                                float* gqe, float* gqde, float* gae) {
+// (IP: where the inputs live -- global rows, or the staged shared-memory copies of the fused launch; has_go / has_go2 / has_gae:
+//  whether that array is present at all)
+template <class IP, class OP>
+__device__ __forceinline__ void walker_eval_adj(const DfxWalkerParams& p, IP qe, IP qde, IP ae, IP go, bool has_go,
+                                                IP go2, bool has_go2, float gr, bool has_rew,
+                                                OP gqe, OP gqde, OP gae, bool has_gae) {
     V3 pos, ang, lin, tt, tdir, up, heading;
     Q4 rot, tq;
     float tn;
@@ -111,7 +113,7 @@ __device__ __forceinline__ void walker_eval_adj(const DfxWalkerParams& p, const 
     float dh;
     height_reward(p, pos.y, &dh);
     int k = 0;
-    auto G = [&](int idx) { return (go ? go[idx] : 0.0f) + (go2 ? go2[idx] : 0.0f); };
+    auto G = [&](int idx) { return (has_go ? go[idx] : 0.0f) + (has_go2 ? go2[idx] : 0.0f); };
     // cotangents of the features
     float a_posy = G(0) + (p.height_mode != 2 ? gr * dh : 0.0f);
     Q4 a_rot = Q4{G(1), G(2), G(3), G(4)};
@@ -122,7 +124,7 @@ __device__ __forceinline__ void walker_eval_adj(const DfxWalkerParams& p, const 
     for (int i = 6; i < p.num_qd; ++i) gqde[i] = p.joint_vel_scale * G(k++);
     const float a_upy = G(k) + 0.1f * gr; ++k;
     const float a_h = G(k) + gr; ++k;
-    if (gae) {
+    if (has_gae) {
         for (int i = 0; i < p.num_act; ++i) {
             const float a = ae[i];
             float g = p.obs_has_actions ? G(k + i) : 0.0f;
@@ -211,9 +213,9 @@ __device__ __forceinline__ void walker_transition_backward_env(const DfxWalkerPa
     float* gqde = gqd + (size_t)e * p.num_qd;
     float* gae = gact ? gact + (size_t)e * p.num_act : nullptr;
     walker_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
-                    g_obs_before ? g_obs_before + (size_t)e * p.num_obs : nullptr,
-                    (live && g_obs_next) ? g_obs_next + (size_t)e * p.num_obs : nullptr,
-                    g_rew ? g_rew[e] : 0.0f, g_rew != nullptr, gqe, gqde, gae);
+                    g_obs_before + (size_t)e * p.num_obs, g_obs_before != nullptr,
+                    g_obs_next + (size_t)e * p.num_obs, live && g_obs_next != nullptr,
+                    g_rew ? g_rew[e] : 0.0f, g_rew != nullptr, gqe, gqde, gae, gae != nullptr);
     if (!live) return;
     if (g_q_next) { const float* g = g_q_next + (size_t)e * p.num_q;
     for (int i = 0; i < p.num_q; ++i) gqe[i] += g[i]; }
@@ -226,10 +228,10 @@ __device__ __forceinline__ void walker_transition_backward_env(const DfxWalkerPa
 // ---- planar envs (Hopper, HalfCheetah: observation = [q[1:], qd]; CartPole swing-up: [x, xd, sin th, cos th, thd]):
 // the same transition as walker_transition_*, reference envs/hopper.py:170-268, envs/cheetah.py:160-244,
 // envs/cartpole_swing_up.py:120-187
-template <class QP, class QDP>
+template <class QP, class QDP, class OP>
 __device__ __forceinline__ void planar_eval(const DfxPlanarParams& p, QP qe, QDP qde,
                                             const float* ae, long long progress, bool want_reward,
-                                            float* o, float* r_out, long long* rs_out) {
+                                            OP o, float* r_out, long long* rs_out) {
     float act_sq = 0.0f;
     for (int i = 0; i < p.num_act; ++i) { const float a = ae ? ae[i] : 0.0f; act_sq += a * a; }
     if (p.kind == 2) {                      // CartPole
@@ -262,12 +264,12 @@ __device__ __forceinline__ void planar_eval(const DfxPlanarParams& p, QP qe, QDP
     *rs_out = rs;
 }
 
-__device__ __forceinline__ void planar_eval_adj(const DfxPlanarParams& p, const float* qe, const float* qde,
-                                                const float* ae, const float* go,
-                                                const float* go2, float gr,
-                                                float* gqe, float* gqde, float* gae) {
-    auto G = [&](int idx) { return (go ? go[idx] : 0.0f) + (go2 ? go2[idx] : 0.0f); };
-    if (gae) for (int i = 0; i < p.num_act; ++i) gae[i] = (p.kind == 2 ? -1.0f : 1.0f) * gr * p.action_penalty * 2.0f * ae[i];
+template <class IP, class OP>
+__device__ __forceinline__ void planar_eval_adj(const DfxPlanarParams& p, IP qe, IP qde, IP ae, IP go, bool has_go,
+                                                IP go2, bool has_go2, float gr,
+                                                OP gqe, OP gqde, OP gae, bool has_gae) {
+    auto G = [&](int idx) { return (has_go ? go[idx] : 0.0f) + (has_go2 ? go2[idx] : 0.0f); };
+    if (has_gae) for (int i = 0; i < p.num_act; ++i) gae[i] = (p.kind == 2 ? -1.0f : 1.0f) * gr * p.action_penalty * 2.0f * ae[i];
     if (p.kind == 2) {
         const float x = qe[0], th = qe[1], xd = qde[0], thd = qde[1];
         const float t = atan2f(sinf(th), cosf(th));
@@ -342,9 +344,9 @@ __device__ __forceinline__ void planar_transition_backward_env(const DfxPlanarPa
     float* gqde = gqd + (size_t)e * p.num_qd;
     float* gae = gact ? gact + (size_t)e * p.num_act : nullptr;
     planar_eval_adj(p, q + (size_t)e * p.num_q, qd + (size_t)e * p.num_qd, actions + (size_t)e * p.num_act,
-                    g_obs_before ? g_obs_before + (size_t)e * p.num_obs : nullptr,
-                    (live && g_obs_next) ? g_obs_next + (size_t)e * p.num_obs : nullptr,
-                    g_rew ? g_rew[e] : 0.0f, gqe, gqde, gae);
+                    g_obs_before + (size_t)e * p.num_obs, g_obs_before != nullptr,
+                    g_obs_next + (size_t)e * p.num_obs, live && g_obs_next != nullptr,
+                    g_rew ? g_rew[e] : 0.0f, gqe, gqde, gae, gae != nullptr);
     // the actions survive a reset in envs that do not clear them (CartPole): their cotangent passes either way
     if (gae && g_actions_next && (live || !p.zero_actions_on_reset)) {
         const float* g = g_actions_next + (size_t)e * p.num_act;
@@ -355,6 +357,144 @@ __device__ __forceinline__ void planar_transition_backward_env(const DfxPlanarPa
     for (int i = 0; i < p.num_q; ++i) gqe[i] += g[i]; }
     if (g_qd_next) { const float* g = g_qd_next + (size_t)e * p.num_qd;
     for (int i = 0; i < p.num_qd; ++i) gqde[i] += g[i]; }
+}
+
+// =====================================================================================
+// The transition of a whole TILE of E environments by all NT threads of its CTA (dfx_tile.cu: the epilogue of the simulation
+// launch and the prologue of the adjoint launch of dfx_env_step_forward / _backward).  One thread per environment alone is slow
+// as an epilogue -- ~150 dependent, uncoalesced global accesses by a single warp (~9 us, as long as the stand-alone launch it
+// replaces) -- so the rows are STAGED in the (dead) scratch tile: thread e < E evaluates environment e entirely in shared memory,
+// and all NT threads move the rows between the tile and global memory, element k of environment e by thread k * E + e
+// (conflict-free scratch accesses).  Same per-environment arithmetic as above.
+// =====================================================================================
+__device__ __forceinline__ bool env_zero_actions_on_reset(const DfxWalkerParams&) { return true; }
+__device__ __forceinline__ bool env_zero_actions_on_reset(const DfxPlanarParams& p) { return p.zero_actions_on_reset != 0; }
+template <class QP, class QDP, class OP>
+__device__ __forceinline__ void env_eval(const DfxWalkerParams& p, QP qe, QDP qde, const float* ae, long long progress, bool want_reward,
+                                         OP o, float* r, long long* rs) { walker_eval(p, qe, qde, ae, progress, want_reward, o, r, rs); }
+template <class QP, class QDP, class OP>
+__device__ __forceinline__ void env_eval(const DfxPlanarParams& p, QP qe, QDP qde, const float* ae, long long progress, bool want_reward,
+                                         OP o, float* r, long long* rs) { planar_eval(p, qe, qde, ae, progress, want_reward, o, r, rs); }
+template <class IP, class OP>
+__device__ __forceinline__ void env_eval_adj(const DfxWalkerParams& p, IP qe, IP qde, IP ae, IP go, bool has_go, IP go2, bool has_go2,
+                                             float gr, bool has_rew, OP gqe, OP gqde, OP gae) {
+    walker_eval_adj(p, qe, qde, ae, go, has_go, go2, has_go2, gr, has_rew, gqe, gqde, gae, true);
+}
+template <class IP, class OP>
+__device__ __forceinline__ void env_eval_adj(const DfxPlanarParams& p, IP qe, IP qde, IP ae, IP go, bool has_go, IP go2, bool has_go2,
+                                             float gr, bool has_rew, OP gqe, OP gqde, OP gae) {
+    (void)has_rew;
+    planar_eval_adj(p, qe, qde, ae, go, has_go, go2, has_go2, gr, gqe, gqde, gae, true);
+}
+
+// scratch floats per environment the staged transition needs (host-side check in dfx_env_step_*: enough dead scratch, or two launches)
+inline __host__ __device__ int env_stage_floats_forward(int num_obs) { return 2 * num_obs + 1; }
+inline __host__ __device__ int env_stage_floats_backward(int num_obs, int num_q, int num_qd, int num_act) {
+    return 2 * num_obs + 3 * (num_q + num_qd + num_act);
+}
+
+// forward.  The stepped state is at scratch offsets q_off / qd_off of every environment; [stage_off, stage_off + 2 num_obs + 1) is free.
+template <int NT, int E, class Params>
+__device__ __forceinline__ void tile_transition_forward(const Params& p, const DfxEnvTransition& t, const float* used, float* tile_base,
+                                                        int q_off, int qd_off, int stage_off, int N) {
+    const int tid = (int)threadIdx.x, env0 = (int)blockIdx.x * E;
+    const int ob = stage_off, on = ob + p.num_obs, rsf = on + p.num_obs;
+    if (tid < E && env0 + tid < N) {
+        const int env = env0 + tid;
+        const SP se{tile_base + tid};
+        const float* ae = used + (size_t)env * p.num_act;
+        const long long pr = t.progress[env] + 1;
+        float r = 0.0f;
+        long long rs = 0;
+        env_eval(p, se + q_off, se + qd_off, ae, pr, true, se + ob, &r, &rs);
+        t.rew[env] = r;
+        t.reset[env] = rs;
+        t.progress_next[env] = rs ? 0 : pr;
+        if (rs) {       // observation of the state the environment restarts from
+            float r2; long long rs2;
+            env_eval(p, t.start_q + (size_t)env * p.num_q, t.start_qd + (size_t)env * p.num_qd,
+                     env_zero_actions_on_reset(p) ? (const float*)nullptr : ae, 0, false, se + on, &r2, &rs2);
+        }
+        sp_int(se + rsf)[0] = (int)rs;
+    }
+    __syncthreads();
+    const int nenv = (N - env0) < E ? (N - env0) : E;
+    const bool zero_act = env_zero_actions_on_reset(p);
+    for (int j = tid; j < E * p.num_obs; j += NT) {
+        const int e = j % E, k = j / E;
+        if (e >= nenv) continue;
+        const SP se{tile_base + e};
+        const size_t row = (size_t)(env0 + e) * p.num_obs + k;
+        const float v = se[ob + k];
+        t.obs_before[row] = v;
+        t.obs_next[row] = sp_int(se + rsf)[0] ? se[on + k] : v;
+    }
+    for (int j = tid; j < E * p.num_q; j += NT) {
+        const int e = j % E, k = j / E;
+        if (e >= nenv) continue;
+        const SP se{tile_base + e};
+        const size_t row = (size_t)(env0 + e) * p.num_q + k;
+        t.q_next[row] = sp_int(se + rsf)[0] ? t.start_q[row] : se[q_off + k];
+    }
+    for (int j = tid; j < E * p.num_qd; j += NT) {
+        const int e = j % E, k = j / E;
+        if (e >= nenv) continue;
+        const SP se{tile_base + e};
+        const size_t row = (size_t)(env0 + e) * p.num_qd + k;
+        t.qd_next[row] = sp_int(se + rsf)[0] ? t.start_qd[row] : se[qd_off + k];
+    }
+    for (int j = tid; j < E * p.num_act; j += NT) {
+        const int e = j % E, k = j / E;
+        if (e >= nenv) continue;
+        const SP se{tile_base + e};
+        const size_t row = (size_t)(env0 + e) * p.num_act + k;
+        t.actions_next[row] = (sp_int(se + rsf)[0] && zero_act) ? 0.0f : used[row];
+    }
+}
+
+// backward.  The whole scratch tile is free (the step adjoint has not started); [0, env_stage_floats_backward()) is used.
+template <int NT, int E, class Params>
+__device__ __forceinline__ void tile_transition_backward(const Params& p, const DfxEnvTransitionAdj& t, float* tile_base, int N) {
+    const int tid = (int)threadIdx.x, env0 = (int)blockIdx.x * E;
+    const int nenv = (N - env0) < E ? (N - env0) : E;
+    const int nq = p.num_q, nd = p.num_qd, na = p.num_act, no = p.num_obs;
+    // staged inputs, then outputs
+    const int g1 = 0, g2 = g1 + no, gq = g2 + no, gd = gq + nq, ga = gd + nd, qs = ga + na, ds = qs + nq, us = ds + nd;
+    const int oq = us + na, od = oq + nq, oa = od + nd;
+    auto stage = [&](int dst, const float* src, int width) {
+        if (!src) return;
+        for (int j = tid; j < E * width; j += NT) {
+            const int e = j % E, k = j / E;
+            if (e < nenv) SP{tile_base + e}[dst + k] = src[(size_t)(env0 + e) * width + k];
+        }
+    };
+    stage(g1, t.g_obs_before, no); stage(g2, t.g_obs_next, no);
+    stage(gq, t.g_q_next, nq); stage(gd, t.g_qd_next, nd); stage(ga, t.g_actions_next, na);
+    stage(qs, t.q_sim, nq); stage(ds, t.qd_sim, nd); stage(us, t.used, na);
+    __syncthreads();
+    if (tid < E && tid < nenv) {
+        const int env = env0 + tid;
+        const SP se{tile_base + tid};
+        const bool live = t.reset[env] == 0;
+        env_eval_adj(p, se + qs, se + ds, se + us, se + g1, t.g_obs_before != nullptr, se + g2, live && t.g_obs_next != nullptr,
+                     t.g_rew ? t.g_rew[env] : 0.0f, t.g_rew != nullptr, se + oq, se + od, se + oa);
+        // what passes through the (not re-initialised) next state and actions
+        const bool act_pass = live || !env_zero_actions_on_reset(p);
+        if (t.g_actions_next && act_pass) for (int i = 0; i < na; ++i) se[oa + i] += se[ga + i];
+        if (live) {
+            if (t.g_q_next) for (int i = 0; i < nq; ++i) se[oq + i] += se[gq + i];
+            if (t.g_qd_next) for (int i = 0; i < nd; ++i) se[od + i] += se[gd + i];
+        }
+    }
+    __syncthreads();
+    auto unstage = [&](float* dst, int src, int width) {
+        for (int j = tid; j < E * width; j += NT) {
+            const int e = j % E, k = j / E;
+            if (e < nenv) dst[(size_t)(env0 + e) * width + k] = SP{tile_base + e}[src + k];
+        }
+    };
+    unstage(t.gq_sim, oq, nq); unstage(t.gqd_sim, od, nd); unstage(t.g_used, oa, na);
+    __syncthreads();
 }
 
 }  // namespace dfx

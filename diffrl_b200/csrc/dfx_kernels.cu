@@ -542,6 +542,14 @@ int dfx_step_backward_mapped(const dfx_pack_t* p, int n, int substeps, int mm_fr
 
 // ---- env.step() as one launch (include/dfx.h): the mapped step with the transition as epilogue (tile kernels), or the two
 // launches back to back (lane-group kernels)
+// the tile kernels stage the transition in dead scratch (dfx_env_dev.h tile_transition_*): is there enough of it?
+static bool transition_fits(const dfx_pack_t* p, int kind, const DfxWalkerParams& w, const DfxPlanarParams& pl, bool backward) {
+    if (!p->tile) return false;
+    const int no = kind == 1 ? w.num_obs : pl.num_obs, na = kind == 1 ? w.num_act : pl.num_act;
+    if (backward) return 2 * no + 3 * (p->header.Q + p->header.D + na) <= p->host.layout_bwd.bwd_size;
+    return 2 * no + 1 <= p->host.layout.fwd_size - p->host.layout.act;
+}
+
 static bool transition_ok(int kind, const DfxWalkerParams& w, const DfxPlanarParams& pl, const dfx_pack_t* p, const DfxActionMap* m) {
     if (kind == 1) return w.num_q == p->header.Q && w.num_qd == p->header.D && w.num_act == m->num_act && w.num_obs > 0 && w.num_obs <= 96;
     if (kind == 2) return pl.num_q == p->header.Q && pl.num_qd == p->header.D && pl.num_act == m->num_act && pl.num_obs > 0 && pl.kind >= 0 && pl.kind <= 2;
@@ -555,7 +563,7 @@ int dfx_env_step_forward(const dfx_pack_t* p, int n, int substeps, int mm_freq, 
     if (!transition_ok(tr->kind, tr->walker, tr->planar, p, map)) return (int)cudaErrorInvalidValue;
     if (!tr->progress || !tr->start_q || !tr->start_qd || !tr->obs_before || !tr->rew || !tr->reset || !tr->q_next || !tr->qd_next ||
         !tr->actions_next || !tr->progress_next || !tr->obs_next) return (int)cudaErrorInvalidValue;
-    if (!p->tile) {
+    if (!transition_fits(p, tr->kind, tr->walker, tr->planar, false)) {
         const int e = dfx_step_forward_mapped(p, n, substeps, mm_freq, dt, q, qd, map, raw, act_other, used, q_sim, qd_sim, tape, stream);
         if (e != 0) return e;
         return tr->kind == 1
@@ -583,7 +591,7 @@ int dfx_env_step_backward(const dfx_pack_t* p, int n, int substeps, int mm_freq,
     if (!p || n <= 0 || substeps <= 0 || mm_freq <= 0 || !tape || !map || !raw || !tr) return (int)cudaErrorInvalidValue;
     if (!transition_ok(tr->kind, tr->walker, tr->planar, p, map)) return (int)cudaErrorInvalidValue;
     if (!tr->q_sim || !tr->qd_sim || !tr->used || !tr->reset || !tr->gq_sim || !tr->gqd_sim || !tr->g_used) return (int)cudaErrorInvalidValue;
-    if (!p->tile) {
+    if (!transition_fits(p, tr->kind, tr->walker, tr->planar, true)) {
         const int e = tr->kind == 1
             ? dfx_walker_transition_backward(&tr->walker, n, tr->q_sim, tr->qd_sim, tr->used, tr->reset, tr->g_obs_before, tr->g_rew, tr->g_q_next,
                                              tr->g_qd_next, tr->g_actions_next, tr->g_obs_next, tr->gq_sim, tr->gqd_sim, tr->g_used, stream)

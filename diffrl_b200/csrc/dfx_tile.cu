@@ -296,38 +296,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) dfx_tile_kernel(const __grid_co
     if (env >= ka.step.N) env = ka.step.N - 1;
     const SP s{g.tile_base + g.e};
     // env.step() as one launch (dfx_env_step_forward / _backward): the transition of this tile's environments -- observation,
-    // reward, termination, masked re-initialisation, next observation -- runs on the first E threads of the CTA, one
-    // environment each, as the epilogue of the simulation step; its adjoint as the prologue of the step adjoint.  The rows
-    // cross in global memory (written and read by this CTA only, on either side of a CTA barrier).
-    const int tenv = blockIdx.x * E + (int)threadIdx.x;
-    const bool tlane = ka.step.env_kind != 0 && threadIdx.x < E && tenv < ka.step.N;
+    // reward, termination, masked re-initialisation, next observation -- runs as the epilogue of the simulation step, its adjoint
+    // as the prologue of the step adjoint, both staged in the scratch tile (dfx_env_dev.h tile_transition_*): thread e < E
+    // evaluates environment e in shared memory, all threads move the rows.  The cotangents of (q_sim, qd_sim, used) reach the step
+    // adjoint through three small global work arrays written and read by this CTA only, on either side of a CTA barrier.
     if (BACKWARD) {
-        if (ka.step.env_kind) {
-            const DfxEnvTransitionAdj& t = ka.step.env_adj;
-            if (tlane) {
-                if (ka.step.env_kind == 1)
-                    walker_transition_backward_env(t.walker, tenv, t.q_sim, t.qd_sim, t.used, t.reset, t.g_obs_before, t.g_rew, t.g_q_next,
-                                                   t.g_qd_next, t.g_actions_next, t.g_obs_next, t.gq_sim, t.gqd_sim, t.g_used);
-                else
-                    planar_transition_backward_env(t.planar, tenv, t.q_sim, t.qd_sim, t.used, t.reset, t.g_obs_before, t.g_rew, t.g_q_next,
-                                                   t.g_qd_next, t.g_actions_next, t.g_obs_next, t.gq_sim, t.gqd_sim, t.g_used);
-            }
-            __syncthreads();
-        }
+        if (ka.step.env_kind == 1) tile_transition_backward<NW * 32, E>(ka.step.env_adj.walker, ka.step.env_adj, g.tile_base, ka.step.N);
+        else if (ka.step.env_kind == 2) tile_transition_backward<NW * 32, E>(ka.step.env_adj.planar, ka.step.env_adj, g.tile_base, ka.step.N);
         env_step_backward(P, Y, s, g, env, ka.step);
     } else {
         env_step_forward(P, Y, s, g, env, ka.step);
         if (ka.step.env_kind) {
-            const DfxEnvTransition& t = ka.step.env;
-            __syncthreads();            // `used` of the tile is written (global); the stepped state is still in the scratch tile
-            if (tlane) {                // (threadIdx.x < E: this thread's `s` is the scratch of environment tenv; it reads the state from there)
-                if (ka.step.env_kind == 1)
-                    walker_transition_forward_env(t.walker, tenv, s + Y.q, s + Y.qd, ka.step.used, t.progress, t.start_q, t.start_qd,
-                                                  t.obs_before, t.rew, t.reset, t.q_next, t.qd_next, t.actions_next, t.progress_next, t.obs_next);
-                else
-                    planar_transition_forward_env(t.planar, tenv, s + Y.q, s + Y.qd, ka.step.used, t.progress, t.start_q, t.start_qd,
-                                                  t.obs_before, t.rew, t.reset, t.q_next, t.qd_next, t.actions_next, t.progress_next, t.obs_next);
-            }
+            // the stepped state is still in the scratch tile; everything past the tape row (actuation, tau, H^-1, ...) is dead:
+            // that is where the observations are formed.  `used` (global) was written by this CTA before the barrier.
+            g.row_reusable();           // (no bulk store -- the H^-1 block of a last-substep update -- still reads that region)
+            __syncthreads();
+            if (ka.step.env_kind == 1)
+                tile_transition_forward<NW * 32, E>(ka.step.env.walker, ka.step.env, ka.step.used, g.tile_base, Y.q, Y.qd, Y.act, ka.step.N);
+            else
+                tile_transition_forward<NW * 32, E>(ka.step.env.planar, ka.step.env, ka.step.used, g.tile_base, Y.q, Y.qd, Y.act, ka.step.N);
         }
     }
     g.finish();
