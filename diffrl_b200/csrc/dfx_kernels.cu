@@ -236,7 +236,19 @@ static void set_err(char* err, int n, const std::string& m) {
 
 extern "C" {
 
-const char* dfx_version(void) { return "diffrl_b200 dfx 0.1 (sm_100a)"; }
+const char* dfx_version(void) { return "diffrl_b200 dfx 0.2 (sm_100a)"; }
+int dfx_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(DfxModelDesc);
+        case 1: return (int)sizeof(DfxDerived);
+        case 2: return (int)sizeof(DfxWalkerParams);
+        case 3: return (int)sizeof(DfxPlanarParams);
+        case 4: return (int)sizeof(DfxActionMap);
+        case 5: return (int)sizeof(DfxEnvTransition);
+        case 6: return (int)sizeof(DfxEnvTransitionAdj);
+    }
+    return -1;
+}
 long long dfx_launch_count(void) { return g_launches.load(); }
 int dfx_set_flags(int flags) { g_flags = flags; return 0; }
 int dfx_set_tape_dtype(int bf16) { g_tape_bf16 = bf16 ? 1 : 0; return 0; }

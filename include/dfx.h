@@ -316,6 +316,10 @@ int dfx_launch_plan(const dfx_pack_t* pack, int backward, int out[6]);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 long long dfx_launch_count(void);
 const char* dfx_version(void);
+/* sizeof() of the parameter structs as THIS library was compiled (a binding's struct mirrors can check themselves against it):
+ * 0 DfxModelDesc, 1 DfxDerived, 2 DfxWalkerParams, 3 DfxPlanarParams, 4 DfxActionMap, 5 DfxEnvTransition, 6 DfxEnvTransitionAdj;
+ * anything else: -1. */
+int dfx_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }

@@ -55,3 +55,36 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(os.path.join(root, "diffrl_b200", "libdfx.so"))
     for n in names:
         assert hasattr(lib, n), n
+
+
+def test_c_abi_rejects_invalid_arguments_before_touching_the_gpu():
+    """Error behaviour of the boundary: every entry point validates its arguments first and returns
+    cudaErrorInvalidValue (1) -- no launch, no exception, nothing that needs a device -- and the ctypes mirrors of the parameter
+    structs have the layout the header declares (a size mismatch would shift every pointer of DfxEnvTransition)."""
+    import ctypes, os
+    from diffrl_b200 import env_ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = ctypes.CDLL(os.path.join(root, "diffrl_b200", "libdfx.so"))
+    env_ops._bind(lib)
+    INVALID = 1
+    null = ctypes.c_void_p(None)
+    tr, tra = env_ops.DfxEnvTransition(kind=1), env_ops.DfxEnvTransitionAdj(kind=1)
+    assert lib.dfx_env_step_forward(null, 4, 16, 16, 0.01, null, null, null, null, null, null, null, null, null, ctypes.byref(tr), null) == INVALID
+    assert lib.dfx_env_step_backward(null, 4, 16, 16, 0.01, null, null, null, null, ctypes.byref(tra), null, null, null, null) == INVALID
+    wp = env_ops.DfxWalkerParams(num_q=15, num_qd=14, num_act=8, num_obs=37)
+    assert lib.dfx_walker_transition_forward(ctypes.byref(wp), 0, *([null] * 15)) == INVALID        # n <= 0
+    assert lib.dfx_walker_transition_forward(ctypes.byref(wp), 4, *([null] * 15)) == INVALID        # null rows
+    pp = env_ops.DfxPlanarParams(num_q=2, num_qd=2, num_act=1, num_obs=5, kind=7)
+    assert lib.dfx_planar_transition_forward(ctypes.byref(pp), 4, *([null] * 15)) == INVALID
+    # struct layouts: the ctypes mirrors against sizeof() as the library was compiled, and against the header read by hand
+    from diffrl_b200.modelpack import DfxActionMap, DfxDerived, DfxModelDesc
+    for which, mirror in enumerate((DfxModelDesc, DfxDerived, env_ops.DfxWalkerParams, env_ops.DfxPlanarParams, DfxActionMap,
+                                    env_ops.DfxEnvTransition, env_ops.DfxEnvTransitionAdj)):
+        assert lib.dfx_abi_sizeof(which) == ctypes.sizeof(mirror), (which, mirror.__name__)
+    assert lib.dfx_abi_sizeof(99) == -1
+    assert ctypes.sizeof(env_ops.DfxWalkerParams) == 4 * (11 + 5 + 3 + 4 + 3 + 3)
+    assert ctypes.sizeof(env_ops.DfxPlanarParams) == 4 * (8 + 9)
+    head = 4 + ctypes.sizeof(env_ops.DfxWalkerParams) + ctypes.sizeof(env_ops.DfxPlanarParams)
+    head += (-head) % 8
+    assert ctypes.sizeof(env_ops.DfxEnvTransition) == head + 8 * 11
+    assert ctypes.sizeof(env_ops.DfxEnvTransitionAdj) == head + 8 * 13
