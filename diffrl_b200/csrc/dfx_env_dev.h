@@ -394,106 +394,141 @@ inline __host__ __device__ int env_stage_floats_backward(int num_obs, int num_q,
 }
 
 // forward.  The stepped state is at scratch offsets q_off / qd_off of every environment; [stage_off, stage_off + 2 num_obs + 1) is free.
-template <int NT, int E, class Params>
-__device__ __forceinline__ void tile_transition_forward(const Params& p, const DfxEnvTransition& t, const float* used, float* tile_base,
+// (One body for both env families: only the per-environment evaluation depends on the parameter struct.  The row loops are not
+//  unrolled: this code runs once per launch from a cold instruction cache, and each iteration is one dependent load -> store anyway.)
+template <int NT, int E>
+__device__ __forceinline__ void tile_transition_forward(int kind, const DfxEnvTransition& t, const float* used, float* tile_base,
                                                         int q_off, int qd_off, int stage_off, int N) {
     const int tid = (int)threadIdx.x, env0 = (int)blockIdx.x * E;
-    const int ob = stage_off, on = ob + p.num_obs, rsf = on + p.num_obs;
+    const bool walker = kind == 1;
+    const int nq = walker ? t.walker.num_q : t.planar.num_q, nd = walker ? t.walker.num_qd : t.planar.num_qd;
+    const int na = walker ? t.walker.num_act : t.planar.num_act, no = walker ? t.walker.num_obs : t.planar.num_obs;
+    const bool zero_act = walker ? env_zero_actions_on_reset(t.walker) : env_zero_actions_on_reset(t.planar);
+    const int ob = stage_off, on = ob + no, rsf = on + no;
     if (tid < E && env0 + tid < N) {
         const int env = env0 + tid;
         const SP se{tile_base + tid};
-        const float* ae = used + (size_t)env * p.num_act;
+        const float* ae = used + (size_t)env * na;
+        const float* ae0 = zero_act ? (const float*)nullptr : ae;
+        const float* sq = t.start_q + (size_t)env * nq;
+        const float* sqd = t.start_qd + (size_t)env * nd;
         const long long pr = t.progress[env] + 1;
-        float r = 0.0f;
-        long long rs = 0;
-        env_eval(p, se + q_off, se + qd_off, ae, pr, true, se + ob, &r, &rs);
+        float r = 0.0f, r2;
+        long long rs = 0, rs2;
+        if (walker) {
+            env_eval(t.walker, se + q_off, se + qd_off, ae, pr, true, se + ob, &r, &rs);
+            if (rs) env_eval(t.walker, sq, sqd, ae0, 0, false, se + on, &r2, &rs2);     // observation of the state it restarts from
+        } else {
+            env_eval(t.planar, se + q_off, se + qd_off, ae, pr, true, se + ob, &r, &rs);
+            if (rs) env_eval(t.planar, sq, sqd, ae0, 0, false, se + on, &r2, &rs2);
+        }
         t.rew[env] = r;
         t.reset[env] = rs;
         t.progress_next[env] = rs ? 0 : pr;
-        if (rs) {       // observation of the state the environment restarts from
-            float r2; long long rs2;
-            env_eval(p, t.start_q + (size_t)env * p.num_q, t.start_qd + (size_t)env * p.num_qd,
-                     env_zero_actions_on_reset(p) ? (const float*)nullptr : ae, 0, false, se + on, &r2, &rs2);
-        }
         sp_int(se + rsf)[0] = (int)rs;
     }
     __syncthreads();
     const int nenv = (N - env0) < E ? (N - env0) : E;
-    const bool zero_act = env_zero_actions_on_reset(p);
-    for (int j = tid; j < E * p.num_obs; j += NT) {
+#pragma unroll 1
+    for (int j = tid; j < E * no; j += NT) {
         const int e = j % E, k = j / E;
         if (e >= nenv) continue;
         const SP se{tile_base + e};
-        const size_t row = (size_t)(env0 + e) * p.num_obs + k;
+        const size_t row = (size_t)(env0 + e) * no + k;
         const float v = se[ob + k];
         t.obs_before[row] = v;
         t.obs_next[row] = sp_int(se + rsf)[0] ? se[on + k] : v;
     }
-    for (int j = tid; j < E * p.num_q; j += NT) {
-        const int e = j % E, k = j / E;
+#pragma unroll 1
+    for (int j = tid; j < E * (nq + nd + na); j += NT) {       // q_next, qd_next, actions_next
+        const int e = j % E;
+        int k = j / E;
         if (e >= nenv) continue;
         const SP se{tile_base + e};
-        const size_t row = (size_t)(env0 + e) * p.num_q + k;
-        t.q_next[row] = sp_int(se + rsf)[0] ? t.start_q[row] : se[q_off + k];
-    }
-    for (int j = tid; j < E * p.num_qd; j += NT) {
-        const int e = j % E, k = j / E;
-        if (e >= nenv) continue;
-        const SP se{tile_base + e};
-        const size_t row = (size_t)(env0 + e) * p.num_qd + k;
-        t.qd_next[row] = sp_int(se + rsf)[0] ? t.start_qd[row] : se[qd_off + k];
-    }
-    for (int j = tid; j < E * p.num_act; j += NT) {
-        const int e = j % E, k = j / E;
-        if (e >= nenv) continue;
-        const SP se{tile_base + e};
-        const size_t row = (size_t)(env0 + e) * p.num_act + k;
-        t.actions_next[row] = (sp_int(se + rsf)[0] && zero_act) ? 0.0f : used[row];
+        const bool rs = sp_int(se + rsf)[0] != 0;
+        if (k < nq) {
+            const size_t row = (size_t)(env0 + e) * nq + k;
+            t.q_next[row] = rs ? t.start_q[row] : se[q_off + k];
+        } else if (k < nq + nd) {
+            k -= nq;
+            const size_t row = (size_t)(env0 + e) * nd + k;
+            t.qd_next[row] = rs ? t.start_qd[row] : se[qd_off + k];
+        } else {
+            k -= nq + nd;
+            const size_t row = (size_t)(env0 + e) * na + k;
+            t.actions_next[row] = (rs && zero_act) ? 0.0f : used[row];
+        }
     }
 }
 
 // backward.  The whole scratch tile is free (the step adjoint has not started); [0, env_stage_floats_backward()) is used.
-template <int NT, int E, class Params>
-__device__ __forceinline__ void tile_transition_backward(const Params& p, const DfxEnvTransitionAdj& t, float* tile_base, int N) {
+template <int NT, int E>
+__device__ __forceinline__ void tile_transition_backward(int kind, const DfxEnvTransitionAdj& t, float* tile_base, int N) {
     const int tid = (int)threadIdx.x, env0 = (int)blockIdx.x * E;
     const int nenv = (N - env0) < E ? (N - env0) : E;
-    const int nq = p.num_q, nd = p.num_qd, na = p.num_act, no = p.num_obs;
-    // staged inputs, then outputs
-    const int g1 = 0, g2 = g1 + no, gq = g2 + no, gd = gq + nq, ga = gd + nd, qs = ga + na, ds = qs + nq, us = ds + nd;
-    const int oq = us + na, od = oq + nq, oa = od + nd;
-    auto stage = [&](int dst, const float* src, int width) {
-        if (!src) return;
-        for (int j = tid; j < E * width; j += NT) {
+    const bool walker = kind == 1;
+    const int nq = walker ? t.walker.num_q : t.planar.num_q, nd = walker ? t.walker.num_qd : t.planar.num_qd;
+    const int na = walker ? t.walker.num_act : t.planar.num_act, no = walker ? t.walker.num_obs : t.planar.num_obs;
+    // staged inputs (8 rows per environment), then the outputs (3)
+    const float* src[8] = {t.g_obs_before, t.g_obs_next, t.g_q_next, t.g_qd_next, t.g_actions_next, t.q_sim, t.qd_sim, t.used};
+    const int width[8] = {no, no, nq, nd, na, nq, nd, na};
+    int off[9];
+    off[0] = 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) off[a + 1] = off[a] + width[a];
+    const int g1 = off[0], g2 = off[1], gq = off[2], gd = off[3], ga = off[4], qs = off[5], ds = off[6], us = off[7];
+    const int oq = off[8], od = oq + nq, oa = od + nd;
+#pragma unroll 1
+    for (int a = 0; a < 8; ++a) {
+        const float* sa = src[a];
+        if (!sa) continue;
+        const int w = width[a], d0 = off[a];
+#pragma unroll 1
+        for (int j = tid; j < E * w; j += NT) {
             const int e = j % E, k = j / E;
-            if (e < nenv) SP{tile_base + e}[dst + k] = src[(size_t)(env0 + e) * width + k];
+            if (e < nenv) SP{tile_base + e}[d0 + k] = sa[(size_t)(env0 + e) * w + k];
         }
-    };
-    stage(g1, t.g_obs_before, no); stage(g2, t.g_obs_next, no);
-    stage(gq, t.g_q_next, nq); stage(gd, t.g_qd_next, nd); stage(ga, t.g_actions_next, na);
-    stage(qs, t.q_sim, nq); stage(ds, t.qd_sim, nd); stage(us, t.used, na);
+    }
     __syncthreads();
     if (tid < E && tid < nenv) {
         const int env = env0 + tid;
         const SP se{tile_base + tid};
         const bool live = t.reset[env] == 0;
-        env_eval_adj(p, se + qs, se + ds, se + us, se + g1, t.g_obs_before != nullptr, se + g2, live && t.g_obs_next != nullptr,
-                     t.g_rew ? t.g_rew[env] : 0.0f, t.g_rew != nullptr, se + oq, se + od, se + oa);
+        const bool has1 = t.g_obs_before != nullptr, has2 = live && t.g_obs_next != nullptr, has_rew = t.g_rew != nullptr;
+        const float gr = has_rew ? t.g_rew[env] : 0.0f;
+        bool act_pass;
+        if (walker) {
+            env_eval_adj(t.walker, se + qs, se + ds, se + us, se + g1, has1, se + g2, has2, gr, has_rew, se + oq, se + od, se + oa);
+            act_pass = live || !env_zero_actions_on_reset(t.walker);
+        } else {
+            env_eval_adj(t.planar, se + qs, se + ds, se + us, se + g1, has1, se + g2, has2, gr, has_rew, se + oq, se + od, se + oa);
+            act_pass = live || !env_zero_actions_on_reset(t.planar);
+        }
         // what passes through the (not re-initialised) next state and actions
-        const bool act_pass = live || !env_zero_actions_on_reset(p);
-        if (t.g_actions_next && act_pass) for (int i = 0; i < na; ++i) se[oa + i] += se[ga + i];
-        if (live) {
-            if (t.g_q_next) for (int i = 0; i < nq; ++i) se[oq + i] += se[gq + i];
-            if (t.g_qd_next) for (int i = 0; i < nd; ++i) se[od + i] += se[gd + i];
+        if (t.g_actions_next && act_pass) {
+#pragma unroll 1
+            for (int i = 0; i < na; ++i) se[oa + i] += se[ga + i];
+        }
+        if (live && t.g_q_next) {
+#pragma unroll 1
+            for (int i = 0; i < nq; ++i) se[oq + i] += se[gq + i];
+        }
+        if (live && t.g_qd_next) {
+#pragma unroll 1
+            for (int i = 0; i < nd; ++i) se[od + i] += se[gd + i];
         }
     }
     __syncthreads();
-    auto unstage = [&](float* dst, int src, int width) {
-        for (int j = tid; j < E * width; j += NT) {
-            const int e = j % E, k = j / E;
-            if (e < nenv) dst[(size_t)(env0 + e) * width + k] = SP{tile_base + e}[src + k];
-        }
-    };
-    unstage(t.gq_sim, oq, nq); unstage(t.gqd_sim, od, nd); unstage(t.g_used, oa, na);
+#pragma unroll 1
+    for (int j = tid; j < E * (nq + nd + na); j += NT) {       // -> gq_sim, gqd_sim, g_used
+        const int e = j % E;
+        int k = j / E;
+        if (e >= nenv) continue;
+        const float v = SP{tile_base + e}[oq + k];              // (oq, od, oa are adjacent)
+        if (k < nq) t.gq_sim[(size_t)(env0 + e) * nq + k] = v;
+        else if (k < nq + nd) t.gqd_sim[(size_t)(env0 + e) * nd + (k - nq)] = v;
+        else t.g_used[(size_t)(env0 + e) * na + (k - nq - nd)] = v;
+    }
     __syncthreads();
 }
 

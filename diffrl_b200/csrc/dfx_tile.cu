@@ -301,8 +301,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) dfx_tile_kernel(const __grid_co
     // evaluates environment e in shared memory, all threads move the rows.  The cotangents of (q_sim, qd_sim, used) reach the step
     // adjoint through three small global work arrays written and read by this CTA only, on either side of a CTA barrier.
     if (BACKWARD) {
-        if (ka.step.env_kind == 1) tile_transition_backward<NW * 32, E>(ka.step.env_adj.walker, ka.step.env_adj, g.tile_base, ka.step.N);
-        else if (ka.step.env_kind == 2) tile_transition_backward<NW * 32, E>(ka.step.env_adj.planar, ka.step.env_adj, g.tile_base, ka.step.N);
+        if (ka.step.env_kind) tile_transition_backward<NW * 32, E>(ka.step.env_kind, ka.step.env_adj, g.tile_base, ka.step.N);
         env_step_backward(P, Y, s, g, env, ka.step);
     } else {
         env_step_forward(P, Y, s, g, env, ka.step);
@@ -311,10 +310,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) dfx_tile_kernel(const __grid_co
             // that is where the observations are formed.  `used` (global) was written by this CTA before the barrier.
             g.row_reusable();           // (no bulk store -- the H^-1 block of a last-substep update -- still reads that region)
             __syncthreads();
-            if (ka.step.env_kind == 1)
-                tile_transition_forward<NW * 32, E>(ka.step.env.walker, ka.step.env, ka.step.used, g.tile_base, Y.q, Y.qd, Y.act, ka.step.N);
-            else
-                tile_transition_forward<NW * 32, E>(ka.step.env.planar, ka.step.env, ka.step.used, g.tile_base, Y.q, Y.qd, Y.act, ka.step.N);
+            tile_transition_forward<NW * 32, E>(ka.step.env_kind, ka.step.env, ka.step.used, g.tile_base, Y.q, Y.qd, Y.act, ka.step.N);
         }
     }
     g.finish();

@@ -154,10 +154,13 @@ class DFlexEnv:
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _fused_step(self, actions):
-        """env.step() as three launches: policy output -> actuation (``dfx_action_map_forward``), the simulation step,
-        and the transition (progress counter, observation, reward, termination, masked re-initialisation, next
-        observation: ``dfx_walker_transition_forward`` / ``dfx_planar_transition_forward``).  The env provides
-        ``_action_map()`` and ``_transition_params()``; results equal the op-by-op ``step`` (tests/test_gpu_envs.py)."""
+        """env.step() through the fused env layer.  Default (``single_launch_step``): ONE launch forward and ONE backward --
+        ``dfx_env_step_forward / _backward``: the policy output -> actuation map is folded into the simulation launch and the
+        transition (progress counter, observation, reward, termination, masked re-initialisation, next observation) runs as
+        its epilogue, the transition adjoint as the prologue of the adjoint launch.  Otherwise two launches (mapped step +
+        ``dfx_walker_transition_*`` / ``dfx_planar_transition_*``; also what no-grad envs use, whose integrator works in place) or
+        three (``fused_action_map = False``: ``dfx_action_map_*`` on its own).  The env provides ``_action_map()`` and
+        ``_transition_params()``; results equal the op-by-op ``step`` (tests/test_gpu_envs.py)."""
         from ..env_ops import ActionMapFunction, WalkerTransitionFunction
         n = self.num_envs
         if getattr(self, "_amap", None) is None:

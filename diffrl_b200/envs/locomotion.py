@@ -103,7 +103,7 @@ class _FreeRootWalker(DFlexEnv):
             start_qd = 0.5 * (torch.rand(size=(n, self.num_joint_qd), device=dev) - 0.5)
         return start_q, start_qd
 
-    # ---- fused step (DFlexEnv._fused_step): action map, simulation step, transition = 3 launches ----
+    # ---- fused step (DFlexEnv._fused_step): action map, simulation step and transition in ONE launch (dfx_env_step_forward) ----
     fused_transition = True
 
     def _action_map(self):

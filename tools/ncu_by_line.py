@@ -114,6 +114,7 @@ def subphase_of(chain):
     return phase_of(chain)
 by_sub, samp_sub, thr_sub = collections.Counter(), collections.Counter(), collections.Counter()
 by_phase, samp_phase, thr_phase = collections.Counter(), collections.Counter(), collections.Counter()
+static_phase = collections.Counter()      # SASS instructions of the kernel that belong to the phase (16 bytes each): its instruction-cache footprint
 stall_phase = collections.defaultdict(collections.Counter)
 by_line, by_func = collections.Counter(), collections.Counter()
 samp_line, samp_func, thr_func = collections.Counter(), collections.Counter(), collections.Counter()
@@ -125,7 +126,7 @@ for r in body:
     n, s, th = float(r[ie] or 0), float(r[isamp] or 0), float(r[ith] or 0)
     fn = func_of(*loc)
     ph = phase_of(off2chain.get(off) or [])
-    by_phase[ph] += n; samp_phase[ph] += s; thr_phase[ph] += th
+    by_phase[ph] += n; samp_phase[ph] += s; thr_phase[ph] += th; static_phase[ph] += 1
     sp = subphase_of(off2chain.get(off) or [])
     by_sub[sp] += n; samp_sub[sp] += s; thr_sub[sp] += th
     for c in stall_cols:
@@ -139,6 +140,10 @@ print("\n== by phase (outermost phase function on the inline chain): %inst  %sam
 for fn, n in by_phase.most_common(30):
     st = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(1, samp_phase[fn])) for k, v in stall_phase[fn].most_common(4))
     print("%6.2f%% %6.2f%%  %5.1f  %-26s %s" % (100 * n / tot, 100 * samp_phase[fn] / max(1, tots), thr_phase[fn] / max(1, n), fn, st))
+print("\n== code size by phase (SASS bytes of the kernel, executed or not): KB")
+for fn, n in static_phase.most_common(14):
+    print("%7.1f  %s" % (n * 16 / 1024.0, fn))
+print("%7.1f  (whole kernel)" % (sum(static_phase.values()) * 16 / 1024.0))
 print("\n== by phase > callee: %inst  %samples  lanes/inst")
 for fn, n in by_sub.most_common(40):
     print("%6.2f%% %6.2f%%  %5.1f  %s" % (100 * n / tot, 100 * samp_sub[fn] / max(1, tots), thr_sub[fn] / max(1, n), fn))
