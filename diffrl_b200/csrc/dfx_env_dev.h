@@ -1,12 +1,14 @@
-// dfx_env_dev.h -- per-environment device code of the env layer around the simulation step (observation, reward,
-// termination, masked re-initialisation and their adjoints; reference envs/ant.py:266-307, humanoid.py:314-368,
-// snu_humanoid.py:378-432, hopper.py:170-268, cheetah.py:160-244, cartpole_swing_up.py:120-187).  ONE environment per
-// call.  Used by the stand-alone env kernels (dfx_env.cu: one thread per environment) and by the tile kernels when the
-// transition rides inside the simulation launch (dfx_tile.cu: dfx_env_step_forward / _backward, the E environments of a
-// tile on the first E threads of the CTA).  The stepped state (qe, qde) is a template pointer: a global row for the stand-alone
-// kernels, the environment's strided shared-memory scratch (SP) for the fused launch -- no L2 round trip on the critical path of
-// the epilogue.  Plain pointers elsewhere on purpose: in the fused launch the state rows were written
-// by other threads of the same CTA (ordinary coherent loads after a CTA barrier, never the read-only path).
+// dfx_env_dev.h -- device code of the env layer around the simulation step (observation, reward, termination, masked
+// re-initialisation and their adjoints; reference envs/ant.py:266-307, humanoid.py:314-368, snu_humanoid.py:378-432,
+// hopper.py:170-268, cheetah.py:160-244, cartpole_swing_up.py:120-187), in two granularities:
+//   * per ENVIRONMENT (walker_eval / planar_eval, their adjoints, *_transition_*_env): one call = one environment.  What the
+//     stand-alone env kernels run (dfx_env.cu: one thread per environment, rows in global memory);
+//   * per TILE (tile_transition_forward / _backward, at the end of the file): the transition of the E environments of a tile
+//     kernel's CTA as the epilogue of the simulation launch / the prologue of the adjoint launch (dfx_env_step_*), staged in
+//     the scratch tile -- the same per-environment functions, instantiated on strided shared-memory pointers (SP).
+// Hence the template pointer types (QP / QDP: stepped state, OP: outputs, IP: adjoint inputs): global rows or scratch slots.
+// Plain (not __restrict__) pointers on purpose: in the fused launch the rows were written by other threads of the same CTA
+// (ordinary coherent accesses on either side of a CTA barrier, never the read-only path).
 #pragma once
 
 #include "../../include/dfx.h"
@@ -387,11 +389,8 @@ __device__ __forceinline__ void env_eval_adj(const DfxPlanarParams& p, IP qe, IP
     planar_eval_adj(p, qe, qde, ae, go, has_go, go2, has_go2, gr, gqe, gqde, gae, true);
 }
 
-// scratch floats per environment the staged transition needs (host-side check in dfx_env_step_*: enough dead scratch, or two launches)
-inline __host__ __device__ int env_stage_floats_forward(int num_obs) { return 2 * num_obs + 1; }
-inline __host__ __device__ int env_stage_floats_backward(int num_obs, int num_q, int num_qd, int num_act) {
-    return 2 * num_obs + 3 * (num_q + num_qd + num_act);
-}
+// (scratch floats per environment the staged transition needs: 2 num_obs + 1 forward, 2 num_obs + 3 (num_q + num_qd + num_act)
+//  backward -- dfx_kernels.cu transition_fits() checks them against the layout on the host, else the call runs two launches)
 
 // forward.  The stepped state is at scratch offsets q_off / qd_off of every environment; [stage_off, stage_off + 2 num_obs + 1) is free.
 // (One body for both env families: only the per-environment evaluation depends on the parameter struct.  The row loops are not
