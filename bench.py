@@ -20,7 +20,9 @@ horizon 32.  Prints ONE JSON line (rank 0):
                the same with the bytes this design really moves (tape rows incl. the forward intermediates + H^-1 blocks);
                ``fp32`` = executed fp32 FLOP against the CUDA-core peak: the path is issue / latency bound, not HBM bound.
 * ``configs``  the other named configs of BASELINE.json, each with value / e2e / kernel_ms / section-8d roofline:
-               ``humanoid8192`` (C2), ``snu4096_bptt128`` (C3), ``cartpole64`` (C0's shape on the GPU); under torchrun also
+               ``humanoid8192`` (C2, fp32 tape) and ``humanoid8192_bf16_tape`` (C2 as named: "bf16 states" -- the tape stores the
+               link velocities, bias accelerations and wrenches of every row as bf16; arithmetic and the state stay fp32),
+               ``snu4096_bptt128`` (C3), ``cartpole64`` (C0's shape on the GPU); under torchrun also
                ``c4``: Ant at 8192 envs per GPU with the policy-gradient all-reduce (C4).
 * ``cpu_baseline`` / ``gpu_baseline``  the UNMODIFIED reference through its own public API (``oracle/ref_gpu_arm.py`` on the
                install under ``baseline/_ref``): its CPU path on one host core, and its CUDA codegen path (rebuilt for
@@ -244,9 +246,12 @@ def run_reference_cuda(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def measure_config(env_name, N, T, steps, warmup, dev, rank, world, dist, e2e_mode="graph", comm_floats=0,
-                   ncu_range=False, ncu_range_e2e=False, clocks=None):
-    """Kernel path + end-to-end numbers of one workload on this rank.  Returns a dict of raw timings and geometry."""
+                   ncu_range=False, ncu_range_e2e=False, clocks=None, tape_dtype="fp32"):
+    """Kernel path + end-to-end numbers of one workload on this rank.  Returns a dict of raw timings and geometry.
+    tape_dtype "bf16": the adjoint tape stores (v, a, f_tot) of every row as bf16 (BASELINE config C2 "bf16 states"; arithmetic
+    and the state stay fp32)."""
     import torch
+    import diffrl_b200
     from diffrl_b200 import _capi
     import diffrl_b200.envs as envs
     from diffrl_b200.dflex_api.sim import _engine_for
@@ -255,7 +260,11 @@ def measure_config(env_name, N, T, steps, warmup, dev, rank, world, dist, e2e_mo
     torch.manual_seed(1234 + rank)
     env = getattr(envs, env_name)(num_envs=N, device=str(dev), render=False, seed=rank, stochastic_init=False,
                                   no_grad=False, MM_caching_frequency=mm)
-    eng = _engine_for(env.model)
+    diffrl_b200.set_tape_dtype(tape_dtype)      # read when the pack is created (next line)
+    try:
+        eng = _engine_for(env.model)
+    finally:
+        diffrl_b200.set_tape_dtype("fp32")
     Q, D, M = eng.Q, eng.D, eng.M
     lib = _capi.lib()
     dt = env.sim_dt
@@ -404,7 +413,7 @@ def measure_config(env_name, N, T, steps, warmup, dev, rank, world, dist, e2e_mo
     row = int(lib.dfx_pack_query(eng.pack, 8))   # DFX_QUERY_TAPE_ROW_FLOATS
     out = dict(env=env_name, N=N, T=T, S=S, mm=mm, Q=Q, D=D, M=M, row=row, tile=tile, kernel_ms=kernel_ms, e2e_ms=e2e_ms,
                eager_ms=eager_ms, fwd_ms=fwd_ms, bwd_ms=bwd_ms, launches=int(launches), steps=steps, e2e_steps=e2e_steps,
-               tape_mb=tape_mb, e2e_api=e2e_api, h2d=int(host_actions.numel() * 4), d2h=int(host_grad.numel() * 4 + 4),
+               tape_mb=tape_mb, tape_dtype=tape_dtype, e2e_api=e2e_api, h2d=int(host_actions.numel() * 4), d2h=int(host_grad.numel() * 4 + 4),
                comm_floats=comm_floats if comm is not None else 0)
     del env, eng, acts, muscs, host_actions, host_grad
     import gc
@@ -471,7 +480,8 @@ def config_record(m, world, peaks, peak_kind):
                     "eager_env_step_loop": world * m["N"] * m["T"] * m["e2e_steps"] / (m["eager_ms"] * 1e-3)},
             "kernel_ms": {"forward_env_step": m["fwd_ms"], "backward_env_step": m["bwd_ms"]},
             "kernel_family": ("tile (%d envs per CTA)" % m["tile"]) if m["tile"] else "lane group",
-            "tape_mb_per_rollout": m["tape_mb"], "gpu_launches": m["launches"],
+            "tape_mb_per_rollout": m["tape_mb"], "tape_storage": "fp32" if m.get("tape_dtype", "fp32") == "fp32" else "bf16 for (v, a, f_tot) of every row, fp32 otherwise (arithmetic fp32)",
+            "gpu_launches": m["launches"],
             "roofline": roofline_record(m, peaks, peak_kind, *profile_numbers(m["env"], m["N"], m, 1965.0))}
 
 
@@ -501,11 +511,12 @@ def run_ours(args):
         if world > 1:
             plan.append(("c4", "AntEnv", 8192, 32, max(2, args.steps // 2), 2))
         else:
-            plan += [("humanoid8192", "HumanoidEnv", 8192, 32, 2, 1), ("snu4096_bptt128", "SNUHumanoidEnv", 4096, 128, 2, 1),
-                     ("cartpole64", "CartPoleSwingUpEnv", 64, 32, 4, 2)]
+            plan += [("humanoid8192", "HumanoidEnv", 8192, 32, 2, 1), ("humanoid8192_bf16_tape", "HumanoidEnv", 8192, 32, 2, 1),
+                     ("snu4096_bptt128", "SNUHumanoidEnv", 4096, 128, 2, 1), ("cartpole64", "CartPoleSwingUpEnv", 64, 32, 4, 2)]
         for key, e, n, t, k, w in plan:
             try:
-                subs[key] = measure_config(e, n, t, k, w, dev, rank, world, dist, e2e_mode=args.e2e, comm_floats=comm_floats)
+                subs[key] = measure_config(e, n, t, k, w, dev, rank, world, dist, e2e_mode=args.e2e, comm_floats=comm_floats,
+                                           tape_dtype="bf16" if key.endswith("bf16_tape") else "fp32")
             except Exception as exc:     # a sub-config must not take the headline down
                 subs[key] = {"error": repr(exc)[:300]}
 
