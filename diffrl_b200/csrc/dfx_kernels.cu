@@ -237,6 +237,7 @@ static void set_err(char* err, int n, const std::string& m) {
 extern "C" {
 
 const char* dfx_version(void) { return "diffrl_b200 dfx 0.2 (sm_100a)"; }
+int dfx_tile_joint_mask(int L, int D, int Q, int C, int M) { return tile_joint_mask(L, D, Q, C, M); }
 int dfx_abi_sizeof(int which) {
     switch (which) {
         case 0: return (int)sizeof(DfxModelDesc);
@@ -319,6 +320,7 @@ int dfx_pack_query(const dfx_pack_t* p, int what) {
         case DFX_QUERY_TREE_DEPTH: return p->header.nlev;
         case DFX_QUERY_TAPE_TILE: return p->tile;
         case DFX_QUERY_TAPE_BF16: return p->bf16;
+        case DFX_QUERY_JOINT_MASK: return p->header.jmask;
     }
     return -1;
 }

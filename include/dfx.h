@@ -103,7 +103,8 @@ enum {
     DFX_QUERY_TAPE_ROW_FLOATS = 8,    /* floats per (substep, environment) tape row */
     DFX_QUERY_TAPE_TILE = 9,          /* 0: tape blocks are [block][env][n]; E = 8 / 16 / 32: [block][tile of E envs][n][E] (tile kernels) */
     DFX_QUERY_TAPE_BF16 = 10,         /* 1: the middle of every tape row (the forward intermediates) is stored as bf16 */
-    DFX_QUERY_TAPE_ROW_UNITS = 11     /* 4-byte units per (substep, environment) row IN THE TAPE (== row floats unless bf16) */
+    DFX_QUERY_TAPE_ROW_UNITS = 11,    /* 4-byte units per (substep, environment) row IN THE TAPE (== row floats unless bf16) */
+    DFX_QUERY_JOINT_MASK = 12         /* bit t set: some link has joint type t (0 prismatic, 1 revolute, 2 ball, 3 fixed, 4 free) */
 };
 
 /* Build the device-resident pack for CUDA device `device` (>= 0).  Returns NULL on failure and
@@ -320,6 +321,10 @@ const char* dfx_version(void);
  * 0 DfxModelDesc, 1 DfxDerived, 2 DfxWalkerParams, 3 DfxPlanarParams, 4 DfxActionMap, 5 DfxEnvTransition, 6 DfxEnvTransitionAdj;
  * anything else: -1. */
 int dfx_abi_sizeof(int which);
+/* Joint types the size-specialised tile kernels of an articulation with these sizes are COMPILED for (a bit mask as in
+ * DFX_QUERY_JOINT_MASK; 31 = no tile kernel of these sizes, the run-time-generic lane-group kernels take every type).  A pack whose
+ * links have any other joint type stays on the lane-group kernels (DFX_QUERY_TAPE_TILE == 0). */
+int dfx_tile_joint_mask(int L, int D, int Q, int C, int M);
 
 #ifdef __cplusplus
 }

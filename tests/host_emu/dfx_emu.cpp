@@ -52,6 +52,7 @@ int emu_pack_query(const EmuPack* p, int what) {
         case DFX_QUERY_BWD_SCRATCH_FLOATS: return p->host.layout_bwd.bwd_size;
         case DFX_QUERY_TAPE_ROW_FLOATS: return p->host.layout.tape_row;
         case DFX_QUERY_TREE_DEPTH: return p->pack.nlev;
+        case DFX_QUERY_JOINT_MASK: return p->pack.jmask;
     }
     return -1;
 }

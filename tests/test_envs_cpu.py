@@ -88,3 +88,30 @@ def test_c_abi_rejects_invalid_arguments_before_touching_the_gpu():
     head += (-head) % 8
     assert ctypes.sizeof(env_ops.DfxEnvTransition) == head + 8 * 11
     assert ctypes.sizeof(env_ops.DfxEnvTransitionAdj) == head + 8 * 13
+
+
+@pytest.mark.parametrize("name", ["AntEnv", "HumanoidEnv", "SNUHumanoidEnv", "CartPoleSwingUpEnv", "HopperEnv", "CheetahEnv"])
+def test_tile_kernels_are_compiled_for_the_joint_types_of_the_six_articulations(name):
+    """The size-specialised tile kernels carry the articulation's joint types as a compile-time constant (Pack::jmask,
+    csrc/dfx_launch.h tile_joint_mask): branches of absent types are not in the binary.  dfx_pack_create keeps a pack with any
+    other joint type on the run-time-generic lane-group kernels -- correct, but several times slower -- so the masks compiled
+    into the library must cover what the six DiffRL articulations really contain (pack built on the host emulation: no GPU)."""
+    import ctypes, os
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path)
+    from emu_util import EmuSim, load_golden
+    root = os.path.dirname(sys_path)
+    lib = ctypes.CDLL(os.path.join(root, "diffrl_b200", "libdfx.so"))
+    d, model = load_golden(name)
+    sim = EmuSim(model, int(d["meta/num_envs"]))
+    q = lambda what: sim.lib.emu_pack_query(sim.pack, what)
+    L, D, Q, C, M = q(0), q(1), q(2), q(3), q(4)
+    have = q(12)                                                    # DFX_QUERY_JOINT_MASK
+    n = int(d["meta/num_envs"])
+    types = set(int(t) for t in model["joint_type"][: len(model["joint_type"]) // n])
+    assert have == sum(1 << t for t in types), (have, types)
+    compiled = lib.dfx_tile_joint_mask(L, D, Q, C, M)
+    assert compiled != 31, "no size-specialised tile kernel for %s (%d, %d, %d, %d, %d)" % (name, L, D, Q, C, M)
+    assert have & ~compiled == 0, (name, bin(have), bin(compiled))
+    assert lib.dfx_tile_joint_mask(5, 5, 5, 5, 5) == 31             # unknown sizes: every type
