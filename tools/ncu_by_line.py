@@ -84,6 +84,7 @@ def func_of(file, line):
 PHASES = ["kin_fwd", "body_force_fwd", "contact_fwd", "muscle_fwd", "wrench_collect", "tau_fwd", "crba_fwd", "chol_inverse",
           "solve_fwd", "integrate_fwd", "integrate_adj", "solve_adj", "crba_adj", "tau_adj", "muscle_adj", "contact_adj",
           "adj_scatter_scale", "adj_collect", "body_force_adj", "kin_adj", "zero_range", "dump_derived",
+          "tile_transition_forward", "tile_transition_backward",      # env transition as epilogue / prologue (dfx_env_dev.h)
           # the items / tasks of the combined rigid-body + contact phases (cta_compact_with)
           "contact_point_fwd", "contact_point_adj", "body_force_link_fwd", "body_force_link_adj", "contact_penetrates",
           "fx_scatter", "cta_compact_with", "cta_compact", "block_in", "block_out", "row_in"]
